@@ -1,0 +1,120 @@
+"""Host-side mirror of the reference's estimation interface (Julia is not installed here, so the host layer the
+parity tests drive is Python; hmc.jl_b200/julia/HmcGPU.jl is the same thing for a Julia user).
+
+  EstOpt           <- Hmc.estopt           (src/Hmc.jl:17-73)   same field names and defaults
+  estimatemodel    <- Hmc.estimatemodel    (src/Hmc.jl:850-865) returns (μ, σ, πb, A, forecasts, obsdates)
+  estimate_windows <- the SLURM array of run_hmm.jl jobs (slurmscripts/base_estimation.sh:5,17): many end dates at once
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import binding as B
+
+
+@dataclass
+class EstOpt:
+    """Mirror of `mutable struct estopt` (src/Hmc.jl:17-60).  Ranges are 1-based inclusive like Julia's."""
+    rawdata: np.ndarray
+    dates: Sequence
+    sampleRange: range = range(1, 122)          # 1:121
+    signalRange: range = range(2, 2)            # 2:1 (empty)
+    signalSave: range = range(2, 2)
+    endIndex: int = 121
+    horizons: Sequence[int] = (12,)
+    D: int = 3
+    burnin: int = 1000
+    Nrun: int = 1000
+    signalburnin: int = 1000
+    signalNrun: int = 1000
+    noise: float = 0.0
+    noiseSamples: int = 1
+    σsignal: float = 0.0
+    series: str = "offical"
+    seed: int = 1234
+    # extensions of the GPU path (not in the reference)
+    n_chains: int = 1
+    precision: int = 64
+    device: int = 0
+    full_pib: bool = False
+    extra: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        sr = self.sampleRange
+        if len(sr) < 2 or sr.step != 1:
+            raise ValueError("sampleRange must be a contiguous range of at least 2 observations")
+        if len(self.signalRange) != 0:
+            raise NotImplementedError("signalRange: the noisy-signal tier (estimatesignals!) is not implemented on the GPU path")
+        if sr[0] < 1 or sr[-1] > len(self.rawdata):
+            raise ValueError("sampleRange outside rawdata")
+
+
+def estimatemodel(opt: EstOpt, ctx: Optional[B.Context] = None):
+    """GPU drop-in for Hmc.estimatemodel(opt) (src/Hmc.jl:850-865).
+
+    Returns a namespace with the reference's NamedTuple fields and shapes:
+      μ (Nrun, D), σ (Nrun, D) [variances], A (Nrun, D, D), forecasts (Nrun, 2*len(horizons)), obsdates (Nrun,),
+      πb (Nrun, 1, D): only the end-of-window row is materialised — `saveresults` reads πb[:, end, :] (:744), which
+      works unchanged on this array; the full Nrun x N x D tensor (3.5 GB per end date in production) is never built.
+    With n_chains > 1 the draw axis is n_chains*Nrun (chain-major).
+    """
+    own = ctx is None
+    ctx = ctx or B.Context(opt.device)
+    try:
+        sr = opt.sampleRange
+        spec = B.ProblemSpec(np.asarray(opt.rawdata, dtype=np.float64), [sr[0]], [sr[-1]], K=opt.D, n_chains=opt.n_chains,
+                             burnin=opt.burnin, nrun=opt.Nrun, seed=opt.seed, horizons=list(opt.horizons),
+                             precision=opt.precision, flags=B.FLAG_REF_Q1 | B.FLAG_DRAWS)
+        o = B.estimate(ctx, spec)
+    finally:
+        if own:
+            ctx.close()
+    R = opt.n_chains * opt.Nrun
+    date = opt.dates[opt.endIndex - 1] if opt.dates is not None else None
+    return SimpleNamespace(
+        μ=o.mu[0].T.copy(), σ=o.sigma2[0].T.copy(),
+        A=np.transpose(o.A[0], (2, 1, 0)).copy(),            # stored [s][r][draw] -> (draw, r, s)
+        πb=o.pi_end[0].T.copy()[:, None, :],
+        forecasts=o.forecasts[0].T.copy() if o.forecasts is not None else np.empty((R, 0)),
+        obsdates=np.array([date] * R, dtype=object), events=o.events, gpu_ms=o.gpu_ms)
+
+
+def expanding_windows(first_end: int, last_end: int, start: int = 1):
+    """The reference's rolling scheme: sampleRange = startindex:dateindex for every end date (code/run_hmm.jl:80,98)."""
+    ends = np.arange(first_end, last_end + 1, dtype=np.int32)
+    return np.full_like(ends, start), ends
+
+
+def shard_windows(T: Sequence[int], n_shards: int):
+    """Longest-processing-time-first assignment of windows to shards by T_w (cost of a window is ∝ T_w).
+    Returns a list of index arrays, one per shard (the same rule hmcgpu_estimate_multi applies)."""
+    T = np.asarray(T)
+    order = np.argsort(-T, kind="stable")
+    load = np.zeros(n_shards, dtype=np.int64)
+    out = [[] for _ in range(n_shards)]
+    for w in order:
+        d = int(np.argmin(load))
+        out[d].append(int(w))
+        load[d] += int(T[w])
+    return [np.array(sorted(s), dtype=np.int64) for s in out]
+
+
+def estimate_windows(y, win_start, win_end, *, K=3, n_chains=1, burnin=1000, nrun=1000, seed=1234, horizons=(12,),
+                     precision=32, draws=False, summary=True, smoothed=False, loglik=False, win_id=None,
+                     win_series=None, ctx: Optional[B.Context] = None, device: int = 0):
+    """Many end-date windows in one call (what the SLURM job array does one process at a time)."""
+    flags = B.FLAG_REF_Q1 | (B.FLAG_DRAWS if draws else 0) | (B.FLAG_SUMMARY if summary else 0) \
+        | (B.FLAG_SMOOTHED_MEAN if smoothed else 0) | (B.FLAG_LOGLIK if loglik else 0)
+    spec = B.ProblemSpec(y, win_start, win_end, K=K, n_chains=n_chains, burnin=burnin, nrun=nrun, seed=seed,
+                         horizons=list(horizons), precision=precision, flags=flags, win_id=win_id, win_series=win_series)
+    own = ctx is None
+    ctx = ctx or B.Context(device)
+    try:
+        return B.estimate(ctx, spec)
+    finally:
+        if own:
+            ctx.close()

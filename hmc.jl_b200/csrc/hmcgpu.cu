@@ -1,0 +1,1129 @@
+// hmcgpu.cu — C ABI (include/hmcgpu.h) and kernels of the B200 Gibbs/FFBS path.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --shared (see hmc.jl_b200/build.py).
+#include "../../include/hmcgpu.h"
+#include "gibbs_kernel.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace hmc;
+
+// ============================================================================================ context
+struct hmcgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int sm_count = 0;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(hmcgpu_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? HMCGPU_ERR_ALLOC : HMCGPU_ERR_CUDA,     \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);   \
+    } while (0)
+
+// RAII device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = n;
+        if (n == 0) return cudaSuccess;
+        return cudaMalloc(&p, n);
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+extern "C" int hmcgpu_version(void) { return 100; }
+
+extern "C" int hmcgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int hmcgpu_ctx_create(int device, hmcgpu_ctx** out) {
+    if (!out) return fail(nullptr, HMCGPU_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = hmcgpu_device_count();
+    if (n <= 0) return fail(nullptr, HMCGPU_ERR_NODEVICE, "no CUDA device visible (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, HMCGPU_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+    hmcgpu_ctx* ctx = new hmcgpu_ctx();
+    ctx->device = device;
+    CU(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        delete ctx;
+        return fail(nullptr, HMCGPU_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    device, prop.major, prop.minor);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    *out = ctx;
+    return HMCGPU_OK;
+}
+
+extern "C" void hmcgpu_ctx_destroy(hmcgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* hmcgpu_last_error(const hmcgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int hmcgpu_ctx_sync(hmcgpu_ctx* ctx) {
+    if (!ctx) return HMCGPU_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return HMCGPU_OK;
+}
+
+static bool k_supported(int K) { return K == 2 || K == 3 || K == 4; }
+
+#define DISPATCH_K(K, ...)                          \
+    switch (K) {                                    \
+        case 2: { constexpr int KK = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int KK = 3; __VA_ARGS__; } break; \
+        case 4: { constexpr int KK = 4; __VA_ARGS__; } break; \
+        default: break;                             \
+    }
+
+// ============================================================================================ deterministic entry points
+// One thread per batch element; host arrays are fp64 row-major and are converted on the fly.
+
+template <typename R, int K>
+__global__ void filter_kernel(long long B, long long T, const double* __restrict__ y, long long ystride,
+                              const double* __restrict__ A, const double* __restrict__ mu, const double* __restrict__ sig2,
+                              const double* __restrict__ rho, double* __restrict__ pif, double* __restrict__ totals,
+                              double* __restrict__ loglik) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    R a[K][K], m[K], s2[K], pf[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+        m[r] = (R)mu[b * K + r]; s2[r] = (R)sig2[b * K + r]; pf[r] = (R)rho[b * K + r];
+#pragma unroll
+        for (int s = 0; s < K; ++s) a[r][s] = (R)A[(b * K + r) * K + s];
+    }
+    Emission<R, K> em;
+    em.prepare(m, s2);
+    const double* yb = y + b * ystride;
+    double ll = 0.0;
+    for (long long t = 0; t < T; ++t) {
+        R e[K];
+        const R m2 = em.eval((R)yb[t], e);
+        bool ok;
+        const R tot = forward_step<R, K>(a, e, pf, ok);
+        // natural-log normaliser of the unscaled recursion (what the reference's `total` is, :417/:430)
+        const double lt = (sizeof(R) == 4) ? ((double)Real<float>::lg2((float)tot) + (double)m2) * 0.6931471805599453
+                                           : log((double)tot);
+        ll += lt;
+        if (totals) totals[b * T + t] = (sizeof(R) == 4) ? exp(lt) : (double)tot;
+#pragma unroll
+        for (int s = 0; s < K; ++s) pif[(b * T + t) * K + s] = (double)pf[s];
+    }
+    if (loglik) loglik[b] = ll;
+}
+
+template <typename R, int K>
+__global__ void smooth_kernel(long long B, long long T, const double* __restrict__ A, const double* __restrict__ pif,
+                              double* __restrict__ pib) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    R a[K][K], pb[K], pf[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r)
+#pragma unroll
+        for (int s = 0; s < K; ++s) a[r][s] = (R)A[(b * K + r) * K + s];
+#pragma unroll
+    for (int s = 0; s < K; ++s) { pb[s] = (R)pif[(b * T + T - 1) * K + s]; pib[(b * T + T - 1) * K + s] = (double)pb[s]; }
+    for (long long t = T - 2; t >= 0; --t) {
+#pragma unroll
+        for (int s = 0; s < K; ++s) pf[s] = (R)pif[(b * T + t) * K + s];
+        smooth_step<R, K>(a, pf, pb);
+#pragma unroll
+        for (int s = 0; s < K; ++s) pib[(b * T + t) * K + s] = (double)pb[s];
+    }
+}
+
+// fp64, operation-for-operation the oracle's pif form (bit-exact state paths under injected uniforms)
+template <int K>
+__global__ void sample_states_kernel(long long B, long long T, const double* __restrict__ A, const double* __restrict__ pif,
+                                     const double* __restrict__ piN, const double* __restrict__ u, long long* __restrict__ X) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double a[K][K], p[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r)
+#pragma unroll
+        for (int s = 0; s < K; ++s) a[r][s] = A[(b * K + r) * K + s];
+#pragma unroll
+    for (int s = 0; s < K; ++s) p[s] = piN ? piN[b * K + s] : pif[(b * T + T - 1) * K + s];
+    int x = categorical_exact<K>(p, u[b * T + T - 1]);
+    X[b * T + T - 1] = x + 1;
+    for (long long k = T - 2; k >= 0; --k) {
+        double total = 0.0;
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+            p[r] = __dmul_rn(pif[(b * T + k) * K + r], select_k<double, K>(a[r], x));
+            total = __dadd_rn(total, p[r]);
+        }
+        const double gate = pif[(b * T + k + 1) * K + x];
+        if (gate > 2.220446049250313e-16 && total > 0.0) {
+#pragma unroll
+            for (int r = 0; r < K; ++r) p[r] = __ddiv_rn(p[r], total);
+        } else {
+#pragma unroll
+            for (int r = 0; r < K; ++r) p[r] = 1.0 / K;
+        }
+        x = categorical_exact<K>(p, u[b * T + k]);
+        X[b * T + k] = x + 1;
+    }
+}
+
+template <typename R, int K>
+__global__ void draw_params_kernel(long long B, const long long* __restrict__ Ni, const double* __restrict__ S,
+                                   const double* __restrict__ S2, const long long* __restrict__ trans,
+                                   const double* __restrict__ xi, const double* __restrict__ alpha, const double* __restrict__ nu,
+                                   const double* __restrict__ beta, unsigned k0, unsigned k1, unsigned chain0, unsigned sweep,
+                                   double* __restrict__ sig2o, double* __restrict__ muo, double* __restrict__ rhoo,
+                                   double* __restrict__ Ao) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int cnt[K], tr[K][K];
+    R Sd[K], Qd[K], sig2[K], mu[K], rho[K], A[K][K];
+    Hyper<R, K> hp;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        cnt[i] = (int)Ni[b * K + i];
+        const double s = S[b * K + i], n = (double)cnt[i];
+        const double ybar = cnt[i] > 0 ? s / n : 0.0;
+        Sd[i] = (R)s;                                // shift c = 0
+        Qd[i] = (R)(S2[b * K + i] + n * ybar * ybar); // raw second moment
+        hp.xi[i] = (R)xi[i]; hp.alpha[i] = (R)alpha[i]; hp.nu[i] = (R)nu[i]; hp.beta[i] = (R)beta[i];
+        sig2[i] = R(1);
+#pragma unroll
+        for (int j = 0; j < K; ++j) tr[i][j] = (int)trans[(b * K + i) * K + j] - 1;  // API counts include the +1 prior
+    }
+    const RngKey key{k0, k1, chain0 + (unsigned)b};
+    draw_params<R, K>(cnt, Sd, Qd, tr, R(0), hp, key, sweep, sig2, mu, rho, A);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        sig2o[b * K + i] = (double)sig2[i]; muo[b * K + i] = (double)mu[i]; rhoo[b * K + i] = (double)rho[i];
+#pragma unroll
+        for (int j = 0; j < K; ++j) Ao[(b * K + i) * K + j] = (double)A[i][j];
+    }
+}
+
+template <int K>
+__global__ void forecast_kernel(long long B, const double* __restrict__ mu, const double* __restrict__ A,
+                                const double* __restrict__ pi, const int* __restrict__ horizons, int n_h,
+                                const double* __restrict__ yreal, double* __restrict__ out) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double a[K][K], m[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+        m[r] = mu[b * K + r];
+#pragma unroll
+        for (int s = 0; s < K; ++s) a[r][s] = A[(b * K + r) * K + s];
+    }
+    for (int j = 0; j < n_h; ++j) {
+        double v[K];
+#pragma unroll
+        for (int s = 0; s < K; ++s) v[s] = pi[b * K + s];
+        for (int h = 0; h < horizons[j]; ++h) {
+            double nv[K];
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                double acc = v[0] * a[0][s];
+#pragma unroll
+                for (int r = 1; r < K; ++r) acc = fma(v[r], a[r][s], acc);
+                nv[s] = acc;
+            }
+#pragma unroll
+            for (int s = 0; s < K; ++s) v[s] = nv[s];
+        }
+        double f = 0.0;
+#pragma unroll
+        for (int s = 0; s < K; ++s) f = fma(v[s], m[s], f);
+        out[(b * n_h + j) * 2] = f;
+        out[(b * n_h + j) * 2 + 1] = f - yreal[j];
+    }
+}
+
+__global__ void philox_kernel(long long n, const unsigned* __restrict__ ctr, const unsigned* __restrict__ key, unsigned* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 r = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1]);
+    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
+// ---- host helpers for the deterministic calls
+struct Xfer {
+    hmcgpu_ctx* ctx;
+    std::vector<DevBuf*> owned;
+    ~Xfer() { for (auto* b : owned) delete b; }
+    template <typename T> int up(const T* host, size_t n, T** dev) {
+        DevBuf* b = new DevBuf();
+        owned.push_back(b);
+        CU(ctx, b->alloc(n * sizeof(T)));
+        if (host) CU(ctx, cudaMemcpyAsync(b->p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        *dev = b->as<T>();
+        return 0;
+    }
+    template <typename T> int down(T* host, const T* dev, size_t n) {
+        if (host) CU(ctx, cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+        return 0;
+    }
+};
+
+#define TRY(x) do { int rc__ = (x); if (rc__ != 0) return rc__; } while (0)
+
+static int check_common(hmcgpu_ctx* ctx, int K, long long B, long long T) {
+    if (!ctx) return HMCGPU_ERR_ARG;
+    if (!k_supported(K)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "K=%d not supported (2..4)", K);
+    if (B <= 0 || T <= 0) return fail(ctx, HMCGPU_ERR_ARG, "empty batch (B=%lld, T=%lld)", B, T);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, HMCGPU_ERR_CUDA, "cudaSetDevice failed");
+    return 0;
+}
+
+static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+extern "C" int hmcgpu_filter(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, int64_t T, const double* y,
+                             int64_t ystride, const double* A, const double* mu, const double* sigma2, const double* rho,
+                             double* pif, double* totals, double* loglik) {
+    TRY(check_common(ctx, K, B, T));
+    if (!y || !A || !mu || !sigma2 || !rho || !pif) return fail(ctx, HMCGPU_ERR_ARG, "NULL input");
+    if (precision != 32 && precision != 64) return fail(ctx, HMCGPU_ERR_ARG, "precision must be 32 or 64");
+    if (ystride != 0 && ystride < T) return fail(ctx, HMCGPU_ERR_ARG, "y_batch_stride < T");
+    Xfer x{ctx};
+    double *dy, *dA, *dmu, *ds, *dr, *dp, *dt = nullptr, *dl = nullptr;
+    TRY(x.up(y, (size_t)(ystride ? B * ystride : T), &dy));
+    TRY(x.up(A, (size_t)B * K * K, &dA)); TRY(x.up(mu, (size_t)B * K, &dmu));
+    TRY(x.up(sigma2, (size_t)B * K, &ds)); TRY(x.up(rho, (size_t)B * K, &dr));
+    TRY(x.up((double*)nullptr, (size_t)B * T * K, &dp));
+    if (totals) TRY(x.up((double*)nullptr, (size_t)B * T, &dt));
+    if (loglik) TRY(x.up((double*)nullptr, (size_t)B, &dl));
+    DISPATCH_K(K, {
+        if (precision == 32) filter_kernel<float, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dy, ystride, dA, dmu, ds, dr, dp, dt, dl);
+        else filter_kernel<double, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dy, ystride, dA, dmu, ds, dr, dp, dt, dl);
+    });
+    CU(ctx, cudaGetLastError());
+    TRY(x.down(pif, dp, (size_t)B * T * K)); TRY(x.down(totals, dt, (size_t)B * T)); TRY(x.down(loglik, dl, (size_t)B));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return HMCGPU_OK;
+}
+
+extern "C" int hmcgpu_smooth(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, int64_t T, const double* A,
+                             const double* pif, double* pib) {
+    TRY(check_common(ctx, K, B, T));
+    if (!A || !pif || !pib) return fail(ctx, HMCGPU_ERR_ARG, "NULL input");
+    if (precision != 32 && precision != 64) return fail(ctx, HMCGPU_ERR_ARG, "precision must be 32 or 64");
+    Xfer x{ctx};
+    double *dA, *dp, *db;
+    TRY(x.up(A, (size_t)B * K * K, &dA)); TRY(x.up(pif, (size_t)B * T * K, &dp)); TRY(x.up((double*)nullptr, (size_t)B * T * K, &db));
+    DISPATCH_K(K, {
+        if (precision == 32) smooth_kernel<float, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dA, dp, db);
+        else smooth_kernel<double, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dA, dp, db);
+    });
+    CU(ctx, cudaGetLastError());
+    TRY(x.down(pib, db, (size_t)B * T * K));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return HMCGPU_OK;
+}
+
+extern "C" int hmcgpu_sample_states(hmcgpu_ctx* ctx, int32_t K, int64_t B, int64_t T, const double* A, const double* pif,
+                                    const double* piN, const double* u, int64_t* X) {
+    TRY(check_common(ctx, K, B, T));
+    if (!A || !pif || !u || !X) return fail(ctx, HMCGPU_ERR_ARG, "NULL input");
+    Xfer x{ctx};
+    double *dA, *dp, *dn = nullptr, *du;
+    long long* dX;
+    TRY(x.up(A, (size_t)B * K * K, &dA)); TRY(x.up(pif, (size_t)B * T * K, &dp)); TRY(x.up(u, (size_t)B * T, &du));
+    if (piN) TRY(x.up(piN, (size_t)B * K, &dn));
+    TRY(x.up((long long*)nullptr, (size_t)B * T, &dX));
+    DISPATCH_K(K, { sample_states_kernel<KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dA, dp, dn, du, dX); });
+    CU(ctx, cudaGetLastError());
+    TRY(x.down(reinterpret_cast<long long*>(X), dX, (size_t)B * T));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return HMCGPU_OK;
+}
+
+extern "C" int hmcgpu_draw_params(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, const int64_t* Ni,
+                                  const double* S, const double* S2, const int64_t* trans, const double* xi,
+                                  const double* alpha, const double* nu, const double* beta, uint64_t seed,
+                                  uint32_t chain0, uint32_t sweep, double* sigma2, double* mu, double* rho, double* A) {
+    TRY(check_common(ctx, K, B, 1));
+    if (!Ni || !S || !S2 || !trans || !xi || !alpha || !nu || !beta || !sigma2 || !mu || !rho || !A)
+        return fail(ctx, HMCGPU_ERR_ARG, "NULL input");
+    if (precision != 32 && precision != 64) return fail(ctx, HMCGPU_ERR_ARG, "precision must be 32 or 64");
+    Xfer x{ctx};
+    long long *dN, *dT;
+    double *dS, *dS2, *dxi, *dal, *dnu, *dbe, *o1, *o2, *o3, *o4;
+    TRY(x.up(reinterpret_cast<const long long*>(Ni), (size_t)B * K, &dN));
+    TRY(x.up(reinterpret_cast<const long long*>(trans), (size_t)B * K * K, &dT));
+    TRY(x.up(S, (size_t)B * K, &dS)); TRY(x.up(S2, (size_t)B * K, &dS2));
+    TRY(x.up(xi, (size_t)K, &dxi)); TRY(x.up(alpha, (size_t)K, &dal)); TRY(x.up(nu, (size_t)K, &dnu)); TRY(x.up(beta, (size_t)K, &dbe));
+    TRY(x.up((double*)nullptr, (size_t)B * K, &o1)); TRY(x.up((double*)nullptr, (size_t)B * K, &o2));
+    TRY(x.up((double*)nullptr, (size_t)B * K, &o3)); TRY(x.up((double*)nullptr, (size_t)B * K * K, &o4));
+    const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+    DISPATCH_K(K, {
+        if (precision == 32) draw_params_kernel<float, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, dN, dS, dS2, dT, dxi, dal, dnu, dbe, k0, k1, chain0, sweep, o1, o2, o3, o4);
+        else draw_params_kernel<double, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, dN, dS, dS2, dT, dxi, dal, dnu, dbe, k0, k1, chain0, sweep, o1, o2, o3, o4);
+    });
+    CU(ctx, cudaGetLastError());
+    TRY(x.down(sigma2, o1, (size_t)B * K)); TRY(x.down(mu, o2, (size_t)B * K)); TRY(x.down(rho, o3, (size_t)B * K));
+    TRY(x.down(A, o4, (size_t)B * K * K));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return HMCGPU_OK;
+}
+
+extern "C" int hmcgpu_forecast(hmcgpu_ctx* ctx, int32_t K, int64_t B, const double* mu, const double* A, const double* pi,
+                               const int32_t* horizons, int32_t n_h, const double* yreal, double* out) {
+    TRY(check_common(ctx, K, B, 1));
+    if (!mu || !A || !pi || !horizons || !yreal || !out || n_h <= 0) return fail(ctx, HMCGPU_ERR_ARG, "NULL/empty input");
+    for (int j = 0; j < n_h; ++j) if (horizons[j] < 0) return fail(ctx, HMCGPU_ERR_ARG, "negative horizon");
+    Xfer x{ctx};
+    double *dm, *dA, *dp, *dy, *dout;
+    int* dh;
+    TRY(x.up(mu, (size_t)B * K, &dm)); TRY(x.up(A, (size_t)B * K * K, &dA)); TRY(x.up(pi, (size_t)B * K, &dp));
+    TRY(x.up(yreal, (size_t)n_h, &dy)); TRY(x.up(horizons, (size_t)n_h, &dh)); TRY(x.up((double*)nullptr, (size_t)B * 2 * n_h, &dout));
+    DISPATCH_K(K, { forecast_kernel<KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, dm, dA, dp, dh, n_h, dy, dout); });
+    CU(ctx, cudaGetLastError());
+    TRY(x.down(out, dout, (size_t)B * 2 * n_h));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return HMCGPU_OK;
+}
+
+extern "C" int hmcgpu_philox(hmcgpu_ctx* ctx, int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    if (!ctx || n <= 0 || !ctr || !key || !out) return fail(ctx, HMCGPU_ERR_ARG, "bad arguments");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Xfer x{ctx};
+    unsigned *dc, *dk, *dout;
+    TRY(x.up(ctr, (size_t)n * 4, &dc)); TRY(x.up(key, (size_t)n * 2, &dk)); TRY(x.up((unsigned*)nullptr, (size_t)n * 4, &dout));
+    philox_kernel<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, dc, dk, dout);
+    CU(ctx, cudaGetLastError());
+    TRY(x.down(out, dout, (size_t)n * 4));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return HMCGPU_OK;
+}
+
+// ============================================================================================ estimation plan
+// ---- window initialisation: HyperParams (:132-142) + makeParams (:161-195) + the statistics of X0, one block per window
+struct WinInit {          // per window, fp64
+    double mean;          // ξ default and the shift c
+    double cnt[8], Sd[8], Qd[8], trans[64];
+};
+
+__device__ __forceinline__ unsigned long long orderable(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double from_orderable(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+template <typename T, typename Op>
+__device__ T block_reduce(T v, T* sh, Op op) {   // deterministic tree, result broadcast
+    const int tid = threadIdx.x;
+    sh[tid] = v;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (tid < s) sh[tid] = op(sh[tid], sh[tid + s]);
+        __syncthreads();
+    }
+    T r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+// k-th smallest (0-based) by radix select on the order-preserving 64-bit image of the doubles
+__device__ double block_select(const double* y, size_t yld, int N, int k, unsigned long long* sh) {
+    unsigned long long prefix = 0, mask = 0;
+    for (int bit = 63; bit >= 0; --bit) {
+        const unsigned long long b = 1ull << bit;
+        unsigned long long c = 0;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const unsigned long long key = orderable(y[(size_t)i * yld]);
+            c += ((key & mask) == prefix && !(key & b)) ? 1ull : 0ull;
+        }
+        c = block_reduce<unsigned long long>(c, sh, [](unsigned long long a, unsigned long long b2) { return a + b2; });
+        if ((unsigned long long)k >= c) { prefix |= b; k -= (int)c; }
+        mask |= b;
+    }
+    return from_orderable(prefix);
+}
+
+__global__ void __launch_bounds__(256) window_init_kernel(int K, const double* __restrict__ y64, int yld,
+                                                          const long long* __restrict__ wbase, const int* __restrict__ wT,
+                                                          WinInit* __restrict__ out) {
+    extern __shared__ unsigned char x0[];                 // X0, one byte per time step
+    __shared__ double shd[256];
+    __shared__ unsigned long long shu[256];
+    __shared__ double mu0[8];
+    const int w = blockIdx.x;
+    const int N = wT[w];
+    const double* y = y64 + wbase[w];
+    const size_t ld = (size_t)yld;
+    auto add = [](double a, double b) { return a + b; };
+    double s = 0.0, mn = 1e300, mx = -1e300;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { const double v = y[i * ld]; s += v; mn = fmin(mn, v); mx = fmax(mx, v); }
+    const double mean = block_reduce<double>(s, shd, add) / N;
+    mn = block_reduce<double>(mn, shd, [](double a, double b) { return fmin(a, b); });
+    mx = block_reduce<double>(mx, shd, [](double a, double b) { return fmax(a, b); });
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { const double d = y[i * ld] - mean; ss += d * d; }
+    const double sd = sqrt(block_reduce<double>(ss, shd, add) / (N - 1));             // Statistics.std (:177)
+    double med = block_select(y, ld, N, N / 2, shu);
+    if (!(N & 1)) med = 0.5 * (block_select(y, ld, N, N / 2 - 1, shu) + med);
+    const double R = mx - mn, lo = med - 0.25 * R, hi = med + 0.25 * R;               // :175-176
+    if (threadIdx.x < K) mu0[threadIdx.x] = (K > 1) ? lo + (hi - lo) * ((double)threadIdx.x / (double)(K - 1)) : med;
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {                               // :185-187 findmax of the pdfs
+        const double v = y[i * ld];
+        int best = 0;
+        double z = (v - mu0[0]) / sd, bv = exp(-(z * z) / 2.0) * 0.3989422804014327 / sd;
+        for (int k = 1; k < K; ++k) {
+            z = (v - mu0[k]) / sd;
+            const double pv = exp(-(z * z) / 2.0) * 0.3989422804014327 / sd;
+            if (pv > bv) { bv = pv; best = k; }
+        }
+        x0[i] = (unsigned char)best;
+    }
+    __syncthreads();
+    // statistics of X0 in serial time order (deterministic): thread i < K -> state i, thread K+j -> transition pair j
+    const int tid = threadIdx.x;
+    if (tid < K) {
+        double c = 0.0, sdv = 0.0, qd = 0.0;
+        for (int i = 0; i < N; ++i)
+            if (x0[i] == tid) { const double d = y[i * ld] - mean; c += 1.0; sdv += d; qd += d * d; }
+        out[w].cnt[tid] = c; out[w].Sd[tid] = sdv; out[w].Qd[tid] = qd;
+    } else if (tid < K + K * K) {
+        const int j = tid - K, r = j / K, s2 = j % K;
+        double c = 0.0;
+        for (int i = 0; i + 1 < N; ++i) c += (x0[i] == r && x0[i + 1] == s2) ? 1.0 : 0.0;
+        out[w].trans[j] = c;
+    }
+    if (tid == 0) out[w].mean = mean;
+}
+
+template <typename R>
+__global__ void chain_init_kernel(int K, int n_slots, const int* __restrict__ slot_win, const WinInit* __restrict__ wi,
+                                  const double* __restrict__ xi_user, int* cnt, int* trans, R* Sd, R* Qd, R* cshift, R* xi,
+                                  int* events) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const int w = slot_win[slot];
+    events[slot] = 0;
+    for (int i = 0; i < K; ++i) {
+        cnt[i * n_slots + slot] = w < 0 ? 0 : (int)wi[w].cnt[i];
+        Sd[i * n_slots + slot] = w < 0 ? R(0) : (R)wi[w].Sd[i];
+        Qd[i * n_slots + slot] = w < 0 ? R(0) : (R)wi[w].Qd[i];
+        xi[i * n_slots + slot] = w < 0 ? R(0) : (R)(xi_user ? xi_user[i] : wi[w].mean);
+        for (int j = 0; j < K; ++j) trans[(i * K + j) * n_slots + slot] = w < 0 ? 0 : (int)wi[w].trans[i * K + j];
+    }
+    cshift[slot] = w < 0 ? R(0) : (R)wi[w].mean;
+}
+
+// y (fp64, series-major as the host gives it) -> time-major fp64 and R copies
+template <typename R>
+__global__ void y_layout_kernel(long long y_len, int n_series, const double* __restrict__ in, double* __restrict__ y64, R* __restrict__ yr) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= y_len * n_series) return;
+    const long long t = i / n_series;
+    const int s = (int)(i % n_series);
+    const double v = in[(long long)s * y_len + t];
+    y64[i] = v;
+    yr[i] = (R)v;
+}
+
+template <typename R>
+__global__ void yfut_kernel(int n_slots, int n_h, const int* __restrict__ slot_win, const double* __restrict__ yfut_w, R* __restrict__ out) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const int w = slot_win[slot];
+    for (int j = 0; j < n_h; ++j) out[(size_t)j * n_slots + slot] = w < 0 ? R(0) : (R)yfut_w[(size_t)w * n_h + j];
+}
+
+// ---- per-chunk post-processing
+// chunk buffer out[(f*chunk + i)*n_slots + slot]  ->  Julia column-major per-window draw arrays (fp64)
+template <typename R>
+__global__ void gather_draws_kernel(int K, int n_h, int n_slots, int chunk, int n_i, long long draw0, long long nrun, int n_chains,
+                                    const int* __restrict__ slot_win, const int* __restrict__ slot_chain,
+                                    const R* __restrict__ out, double* mu, double* sig2, double* A, double* pie, double* fc, double* ll) {
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots || i >= n_i) return;
+    const int w = slot_win[slot];
+    if (w < 0) return;
+    const long long Rr = (long long)n_chains * nrun;
+    const long long d = (long long)slot_chain[slot] * nrun + draw0 + i;
+    const size_t cs = (size_t)chunk * n_slots;
+    const R* o = out + (size_t)i * n_slots + slot;
+    int f = 0;
+    for (int k = 0; k < K; ++k, ++f) if (mu) mu[(size_t)w * Rr * K + (size_t)k * Rr + d] = (double)o[f * cs];
+    for (int k = 0; k < K; ++k, ++f) if (sig2) sig2[(size_t)w * Rr * K + (size_t)k * Rr + d] = (double)o[f * cs];
+    for (int k = 0; k < K * K; ++k, ++f) if (A) A[(size_t)w * Rr * K * K + (size_t)k * Rr + d] = (double)o[f * cs];
+    for (int k = 0; k < K; ++k, ++f) if (pie) pie[(size_t)w * Rr * K + (size_t)k * Rr + d] = (double)o[f * cs];
+    for (int k = 0; k < 2 * n_h; ++k, ++f) if (fc) fc[(size_t)w * Rr * 2 * n_h + (size_t)k * Rr + d] = (double)o[f * cs];
+    if (ll) ll[(size_t)w * Rr + d] = (double)o[f * cs];
+}
+
+// per (window, field): sum and sum of squares over the window's chains and the chunk's draws, accumulated in fp64
+template <typename R>
+__global__ void __launch_bounds__(128) summary_accum_kernel(int F, int n_slots, int chunk, int n_i, int n_chains,
+                                                            const int* __restrict__ win_slot0, const R* __restrict__ out,
+                                                            double* __restrict__ sum, double* __restrict__ sumsq) {
+    __shared__ double sh[128];
+    const int w = blockIdx.x, f = blockIdx.y;
+    const int s0 = win_slot0[w];
+    double a = 0.0, b = 0.0;
+    const long long n = (long long)n_chains * n_i;
+    for (long long j = threadIdx.x; j < n; j += blockDim.x) {
+        const int cidx = (int)(j % n_chains), i = (int)(j / n_chains);
+        const double v = (double)out[((size_t)f * chunk + i) * n_slots + s0 + cidx];
+        a += v; b += v * v;
+    }
+    auto add = [](double x, double y2) { return x + y2; };
+    a = block_reduce<double>(a, sh, add);
+    b = block_reduce<double>(b, sh, add);
+    if (threadIdx.x == 0) { sum[(size_t)w * F + f] += a; sumsq[(size_t)w * F + f] += b; }
+}
+
+// smoothed-probability sums of this chunk, pooled over the window's chains, added to the fp64 per-window accumulator
+template <typename R>
+__global__ void pib_reduce_kernel(int K, int n_chains, const int* __restrict__ win_slot0, const int* __restrict__ wT,
+                                  const long long* __restrict__ warp_pi_off, const long long* __restrict__ win_pib_off,
+                                  R* __restrict__ pacc, double* __restrict__ pib_sum) {
+    const int w = blockIdx.x;
+    const int N = wT[w];
+    const int s0 = win_slot0[w];
+    double* dst = pib_sum + win_pib_off[w];
+    for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
+        const int t = e / K, k = e % K;
+        double acc = 0.0;
+        for (int cidx = 0; cidx < n_chains; ++cidx) {
+            const int slot = s0 + cidx;
+            R* p = pacc + warp_pi_off[slot >> 5] + (size_t)(t * K + k) * 32 + (slot & 31);
+            acc += (double)*p;
+            *p = R(0);
+        }
+        dst[(size_t)k * N + t] += acc;                       // column-major N_w x K
+    }
+}
+
+struct hmcgpu_plan {
+    hmcgpu_ctx* ctx = nullptr;
+    // problem (host copies)
+    int K = 0, n_chains = 0, n_windows = 0, n_h = 0, precision = 32;
+    long long burnin = 0, nrun = 0;
+    unsigned flags = 0;
+    unsigned long long seed = 0;
+    int F = 0;
+    std::vector<int> wT;                 // per window (caller order)
+    std::vector<int> order;              // windows sorted by T descending: order[j] = caller index
+    std::vector<long long> pib_off;      // per window (caller order) offset in pib_mean
+    long long pib_total = 0;
+    long long state_steps = 0;
+    int n_slots = 0, n_warps = 0, chunk = 0, max_T = 0;
+    GibbsArgs args{};
+    // device buffers
+    DevBuf y64, yr, wbase, wTd, wi, slot_win, slot_chain, T, ybase, warp_T, warp_pi_off, pi, pacc, cnt, trans, Sd, Qd,
+        events, cshift, xi, xi_user, chain_id, out, yfut_w, yfut, win_slot0, win_pib_off;
+    DevBuf d_mu, d_sig2, d_A, d_pie, d_fc, d_ll, d_sum, d_sumsq, d_pibsum;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    double gpu_ms = 0.0, sweep_ms = 0.0;
+    long long n_launches = 0, n_sweep_launches = 0, h2d = 0, d2h = 0;
+    bool ran = false;
+    ~hmcgpu_plan() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (evk0) cudaEventDestroy(evk0);
+        if (evk1) cudaEventDestroy(evk1);
+    }
+};
+
+template <typename R, int K>
+static cudaError_t launch_gibbs(const hmcgpu_plan* pl, const GibbsArgs& a, cudaStream_t st) {
+    const unsigned grid = (unsigned)((a.n_slots + kGibbsThreads - 1) / kGibbsThreads);
+    const bool smooth = pl->flags & HMCGPU_FLAG_SMOOTHED_MEAN, ll = pl->flags & HMCGPU_FLAG_LOGLIK;
+    if (smooth && ll) gibbs_sweeps_kernel<R, K, true, true><<<grid, kGibbsThreads, 0, st>>>(a);
+    else if (smooth) gibbs_sweeps_kernel<R, K, true, false><<<grid, kGibbsThreads, 0, st>>>(a);
+    else if (ll) gibbs_sweeps_kernel<R, K, false, true><<<grid, kGibbsThreads, 0, st>>>(a);
+    else gibbs_sweeps_kernel<R, K, false, false><<<grid, kGibbsThreads, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+static int validate_problem(hmcgpu_ctx* ctx, const hmcgpu_problem* p) {
+    if (!ctx) return HMCGPU_ERR_ARG;
+    if (!p) return fail(ctx, HMCGPU_ERR_ARG, "problem is NULL");
+    if (!p->y || p->y_len < 2 || p->n_series < 1) return fail(ctx, HMCGPU_ERR_ARG, "empty series");
+    if (p->n_windows < 1 || !p->win_start || !p->win_end) return fail(ctx, HMCGPU_ERR_ARG, "no windows");
+    if (!k_supported(p->K)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "K=%d not supported (2..4)", p->K);
+    if (p->n_chains < 1) return fail(ctx, HMCGPU_ERR_ARG, "n_chains < 1");
+    if (p->burnin < 0 || p->nrun < 1) return fail(ctx, HMCGPU_ERR_ARG, "burnin < 0 or nrun < 1");
+    if (p->burnin + p->nrun > 0xffffffffLL) return fail(ctx, HMCGPU_ERR_ARG, "more than 2^32 sweeps");
+    if (p->precision != 32 && p->precision != 64) return fail(ctx, HMCGPU_ERR_ARG, "precision must be 32 or 64");
+    if (p->n_h < 0 || p->n_h > kMaxH || (p->n_h > 0 && !p->horizons)) return fail(ctx, HMCGPU_ERR_ARG, "0 <= n_h <= %d", kMaxH);
+    if (p->is_signal) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "is_signal: the signals tier is not implemented");
+    if (p->X0) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "X0: user initial states are not implemented");
+    for (int j = 0; j < p->n_h; ++j) if (p->horizons[j] < 1) return fail(ctx, HMCGPU_ERR_ARG, "horizons must be >= 1");
+    for (int w = 0; w < p->n_windows; ++w) {
+        const long long s = p->win_start[w], e = p->win_end[w];
+        if (s < 1 || e > p->y_len || e - s + 1 < 2) return fail(ctx, HMCGPU_ERR_ARG, "window %d: [%lld,%lld] outside 1..%lld or shorter than 2", w, s, e, (long long)p->y_len);
+        if (p->win_series && (p->win_series[w] < 0 || p->win_series[w] >= p->n_series)) return fail(ctx, HMCGPU_ERR_ARG, "window %d: bad series index", w);
+    }
+    return 0;
+}
+
+template <typename R>
+static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
+    hmcgpu_ctx* ctx = pl->ctx;
+    cudaStream_t st = ctx->stream;
+    const int K = p->K, nw = p->n_windows, nc = p->n_chains, nser = p->n_series;
+    pl->K = K; pl->n_chains = nc; pl->n_windows = nw; pl->n_h = p->n_h; pl->precision = p->precision;
+    pl->burnin = p->burnin; pl->nrun = p->nrun; pl->flags = p->flags; pl->seed = p->seed;
+    pl->F = 3 * K + K * K + 2 * p->n_h + 1;
+    pl->wT.resize(nw);
+    pl->order.resize(nw);
+    pl->pib_off.resize(nw);
+    long long sumT = 0, pib_total = 0;
+    for (int w = 0; w < nw; ++w) {
+        pl->wT[w] = p->win_end[w] - p->win_start[w] + 1;
+        pl->pib_off[w] = pib_total;
+        pib_total += (long long)pl->wT[w] * K;
+        sumT += pl->wT[w];
+        pl->max_T = std::max(pl->max_T, pl->wT[w]);
+    }
+    pl->pib_total = pib_total;
+    pl->state_steps = sumT * nc * (p->burnin + p->nrun);
+    std::iota(pl->order.begin(), pl->order.end(), 0);
+    std::stable_sort(pl->order.begin(), pl->order.end(), [&](int a, int b) { return pl->wT[a] > pl->wT[b]; });
+
+    // slots: windows by decreasing T, chains consecutive; padded to a multiple of 32
+    const long long n_real = (long long)nw * nc;
+    const int n_slots = (int)((n_real + 31) / 32 * 32);
+    const int n_warps = n_slots / 32;
+    pl->n_slots = n_slots; pl->n_warps = n_warps;
+    std::vector<int> slot_win(n_slots, -1), slot_chain(n_slots, 0), Ts(n_slots, 0), win_slot0(nw), warp_T(n_warps, 0);
+    std::vector<long long> ybase(n_slots, 0), warp_off(n_warps, 0), wbase(nw);
+    std::vector<unsigned> chain_id(n_slots, 0);
+    for (int w = 0; w < nw; ++w) {
+        const int ser = p->win_series ? p->win_series[w] : 0;
+        wbase[w] = (long long)(p->win_start[w] - 1) * nser + ser;       // time-major [y_len][n_series]
+    }
+    for (int j = 0; j < nw; ++j) {
+        const int w = pl->order[j];
+        win_slot0[w] = j * nc;
+        const unsigned long long wid = p->win_id ? (unsigned long long)p->win_id[w] : (unsigned long long)w;
+        for (int cidx = 0; cidx < nc; ++cidx) {
+            const int slot = j * nc + cidx;
+            slot_win[slot] = w; slot_chain[slot] = cidx; Ts[slot] = pl->wT[w]; ybase[slot] = wbase[w];
+            chain_id[slot] = (unsigned)(wid * (unsigned long long)nc + (unsigned long long)cidx);
+        }
+    }
+    long long pi_elems = 0;
+    for (int wp = 0; wp < n_warps; ++wp) {
+        int m = 0;
+        for (int l = 0; l < 32; ++l) m = std::max(m, Ts[wp * 32 + l]);
+        warp_T[wp] = m;
+        warp_off[wp] = pi_elems;
+        pi_elems += (long long)m * K * 32;
+    }
+    // forecasts: realised y at end+h per window (NaN outside the series), horizons sorted ascending
+    std::vector<double> yfut_w((size_t)nw * std::max(1, p->n_h), NAN);
+    std::vector<int> hs(p->n_h);
+    std::iota(hs.begin(), hs.end(), 0);
+    std::stable_sort(hs.begin(), hs.end(), [&](int a, int b) { return p->horizons[a] < p->horizons[b]; });
+    for (int w = 0; w < nw; ++w)
+        for (int j = 0; j < p->n_h; ++j) {
+            const long long idx = (long long)p->win_end[w] + p->horizons[j];   // 1-based
+            const int ser = p->win_series ? p->win_series[w] : 0;
+            if (idx <= p->y_len) yfut_w[(size_t)w * p->n_h + j] = p->y[(size_t)ser * p->y_len + idx - 1];
+        }
+
+    // chunk of draws per launch: bound the chunk buffer to ~1 GiB
+    const size_t per_draw = (size_t)pl->F * n_slots * sizeof(R);
+    long long chunk = std::max<long long>(1, (long long)((1ull << 30) / per_draw));
+    chunk = std::min<long long>(chunk, std::min<long long>(p->nrun, 1024));
+    pl->chunk = (int)chunk;
+
+    // ---- device allocation + upload
+    auto up = [&](DevBuf& b, const void* host, size_t bytes) -> cudaError_t {
+        cudaError_t e = b.alloc(bytes);
+        if (e != cudaSuccess) return e;
+        pl->h2d += (long long)bytes;
+        return cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, st);
+    };
+    DevBuf yin;
+    const size_t ny = (size_t)p->y_len * nser;
+    CU(ctx, up(yin, p->y, ny * sizeof(double)));
+    CU(ctx, pl->y64.alloc(ny * sizeof(double)));
+    CU(ctx, pl->yr.alloc(ny * sizeof(R)));
+    y_layout_kernel<R><<<grid_for((long long)ny, 256), 256, 0, st>>>(p->y_len, nser, yin.as<double>(), pl->y64.as<double>(), pl->yr.as<R>());
+    CU(ctx, cudaGetLastError());
+    CU(ctx, up(pl->wbase, wbase.data(), nw * sizeof(long long)));
+    CU(ctx, up(pl->wTd, pl->wT.data(), nw * sizeof(int)));
+    CU(ctx, up(pl->slot_win, slot_win.data(), n_slots * sizeof(int)));
+    CU(ctx, up(pl->slot_chain, slot_chain.data(), n_slots * sizeof(int)));
+    CU(ctx, up(pl->T, Ts.data(), n_slots * sizeof(int)));
+    CU(ctx, up(pl->ybase, ybase.data(), n_slots * sizeof(long long)));
+    CU(ctx, up(pl->warp_T, warp_T.data(), n_warps * sizeof(int)));
+    CU(ctx, up(pl->warp_pi_off, warp_off.data(), n_warps * sizeof(long long)));
+    CU(ctx, up(pl->chain_id, chain_id.data(), n_slots * sizeof(unsigned)));
+    CU(ctx, up(pl->win_slot0, win_slot0.data(), nw * sizeof(int)));
+    CU(ctx, up(pl->win_pib_off, pl->pib_off.data(), nw * sizeof(long long)));
+    CU(ctx, up(pl->yfut_w, yfut_w.data(), yfut_w.size() * sizeof(double)));
+    if (p->xi) CU(ctx, up(pl->xi_user, p->xi, K * sizeof(double)));
+    CU(ctx, pl->wi.alloc(nw * sizeof(WinInit)));
+    CU(ctx, pl->pi.alloc((size_t)pi_elems * sizeof(R)));
+    CU(ctx, pl->cnt.alloc((size_t)K * n_slots * sizeof(int)));
+    CU(ctx, pl->trans.alloc((size_t)K * K * n_slots * sizeof(int)));
+    CU(ctx, pl->Sd.alloc((size_t)K * n_slots * sizeof(R)));
+    CU(ctx, pl->Qd.alloc((size_t)K * n_slots * sizeof(R)));
+    CU(ctx, pl->events.alloc((size_t)n_slots * sizeof(int)));
+    CU(ctx, pl->cshift.alloc((size_t)n_slots * sizeof(R)));
+    CU(ctx, pl->xi.alloc((size_t)K * n_slots * sizeof(R)));
+    CU(ctx, pl->out.alloc(per_draw * (size_t)chunk));
+    CU(ctx, pl->yfut.alloc((size_t)std::max(1, p->n_h) * n_slots * sizeof(R)));
+    const size_t Rr = (size_t)nc * p->nrun;
+    if (p->flags & HMCGPU_FLAG_DRAWS) {
+        CU(ctx, pl->d_mu.alloc((size_t)nw * Rr * K * sizeof(double)));
+        CU(ctx, pl->d_sig2.alloc((size_t)nw * Rr * K * sizeof(double)));
+        CU(ctx, pl->d_A.alloc((size_t)nw * Rr * K * K * sizeof(double)));
+        CU(ctx, pl->d_pie.alloc((size_t)nw * Rr * K * sizeof(double)));
+        if (p->n_h > 0) CU(ctx, pl->d_fc.alloc((size_t)nw * Rr * 2 * p->n_h * sizeof(double)));
+        if (p->flags & HMCGPU_FLAG_LOGLIK) CU(ctx, pl->d_ll.alloc((size_t)nw * Rr * sizeof(double)));
+    }
+    if (p->flags & HMCGPU_FLAG_SUMMARY) {
+        CU(ctx, pl->d_sum.alloc((size_t)nw * pl->F * sizeof(double)));
+        CU(ctx, pl->d_sumsq.alloc((size_t)nw * pl->F * sizeof(double)));
+    }
+    if (p->flags & HMCGPU_FLAG_SMOOTHED_MEAN) {
+        CU(ctx, pl->pacc.alloc((size_t)pi_elems * sizeof(R)));
+        CU(ctx, pl->d_pibsum.alloc((size_t)pib_total * sizeof(double)));
+    }
+    // window statistics (once per plan)
+    const size_t smem = (size_t)pl->max_T;
+    if (smem > 200 * 1024) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "window longer than %d observations", 200 * 1024);
+    if (smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute(window_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    window_init_kernel<<<nw, 256, smem, st>>>(K, pl->y64.as<double>(), nser, pl->wbase.as<long long>(), pl->wTd.as<int>(), pl->wi.as<WinInit>());
+    CU(ctx, cudaGetLastError());
+    yfut_kernel<R><<<grid_for(n_slots, 128), 128, 0, st>>>(n_slots, p->n_h, pl->slot_win.as<int>(), pl->yfut_w.as<double>(), pl->yfut.as<R>());
+    CU(ctx, cudaGetLastError());
+
+    GibbsArgs& a = pl->args;
+    a.n_slots = n_slots; a.T = pl->T.as<int>(); a.ybase = pl->ybase.as<long long>(); a.yld = nser; a.y = pl->yr.p;
+    a.warp_T = pl->warp_T.as<int>(); a.warp_pi_off = pl->warp_pi_off.as<long long>(); a.pi = pl->pi.p; a.pib_acc = pl->pacc.p;
+    a.cnt = pl->cnt.as<int>(); a.trans = pl->trans.as<int>(); a.Sd = pl->Sd.p; a.Qd = pl->Qd.p; a.events = pl->events.as<int>();
+    a.cshift = pl->cshift.p; a.xi = pl->xi.p;
+    for (int i = 0; i < 8; ++i) {
+        a.alpha[i] = (p->alpha && i < K) ? p->alpha[i] : 1.0;      // :137
+        a.nu[i] = (p->nu && i < K) ? p->nu[i] : 1.0;               // :140
+        a.beta0[i] = (p->beta0 && i < K) ? p->beta0[i] : 1.0;      // :179
+        a.beta[i] = (p->beta && i < K) ? p->beta[i] : 2.0;         // :347
+    }
+    a.k0 = (unsigned)p->seed; a.k1 = (unsigned)(p->seed >> 32); a.chain_id = pl->chain_id.as<unsigned>();
+    a.burnin = p->burnin; a.out = pl->out.p; a.chunk = pl->chunk; a.n_h = p->n_h;
+    for (int j = 0; j < p->n_h; ++j) { a.h_sorted[j] = p->horizons[hs[j]]; a.h_slot[j] = hs[j]; }
+    a.yfut = pl->yfut.p; a.flags = p->flags;
+    CU(ctx, cudaEventCreate(&pl->ev0)); CU(ctx, cudaEventCreate(&pl->ev1));
+    CU(ctx, cudaEventCreate(&pl->evk0)); CU(ctx, cudaEventCreate(&pl->evk1));
+    CU(ctx, cudaStreamSynchronize(st));
+    return HMCGPU_OK;
+}
+
+template <typename R, int K>
+static int plan_run_t(hmcgpu_plan* pl) {
+    hmcgpu_ctx* ctx = pl->ctx;
+    cudaStream_t st = ctx->stream;
+    const int ns = pl->n_slots;
+    pl->n_launches = 0; pl->n_sweep_launches = 0; pl->sweep_ms = 0.0;
+    CU(ctx, cudaEventRecord(pl->ev0, st));
+    chain_init_kernel<R><<<grid_for(ns, 128), 128, 0, st>>>(K, ns, pl->slot_win.as<int>(), pl->wi.as<WinInit>(),
+                                                            pl->xi_user.as<double>(), pl->cnt.as<int>(), pl->trans.as<int>(),
+                                                            pl->Sd.as<R>(), pl->Qd.as<R>(), pl->cshift.as<R>(), pl->xi.as<R>(),
+                                                            pl->events.as<int>());
+    CU(ctx, cudaGetLastError());
+    ++pl->n_launches;
+    if (pl->d_sum.p) { CU(ctx, cudaMemsetAsync(pl->d_sum.p, 0, pl->d_sum.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_sumsq.p, 0, pl->d_sumsq.bytes, st)); }
+    if (pl->pacc.p) { CU(ctx, cudaMemsetAsync(pl->pacc.p, 0, pl->pacc.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_pibsum.p, 0, pl->d_pibsum.bytes, st)); }
+    GibbsArgs a = pl->args;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+    auto sweep_launch = [&](long long sweep0, int n, long long draw0) -> int {
+        a.sweep0 = sweep0; a.n_sweeps = n; a.draw0 = draw0;
+        cudaEvent_t e0, e1;
+        CU(ctx, cudaEventCreate(&e0)); CU(ctx, cudaEventCreate(&e1));
+        evs.emplace_back(e0, e1);
+        CU(ctx, cudaEventRecord(e0, st));
+        CU(ctx, (launch_gibbs<R, K>(pl, a, st)));
+        CU(ctx, cudaEventRecord(e1, st));
+        ++pl->n_launches; ++pl->n_sweep_launches;
+        return 0;
+    };
+    // burn-in (no outputs), in launches of at most 1024 sweeps
+    for (long long s = 0; s < pl->burnin; s += 1024) TRY(sweep_launch(s, (int)std::min<long long>(1024, pl->burnin - s), 0));
+    // saved draws, one chunk per launch, each followed by its post-processing kernels
+    for (long long d0 = 0; d0 < pl->nrun; d0 += pl->chunk) {
+        const int n = (int)std::min<long long>(pl->chunk, pl->nrun - d0);
+        TRY(sweep_launch(pl->burnin + d0, n, d0));
+        if (pl->flags & HMCGPU_FLAG_DRAWS) {
+            dim3 blk(32, 8), grd(grid_for(ns, 32), grid_for(n, 8));
+            gather_draws_kernel<R><<<grd, blk, 0, st>>>(K, pl->n_h, ns, pl->chunk, n, d0, pl->nrun, pl->n_chains, pl->slot_win.as<int>(),
+                                                         pl->slot_chain.as<int>(), pl->out.as<R>(), pl->d_mu.as<double>(),
+                                                         pl->d_sig2.as<double>(), pl->d_A.as<double>(), pl->d_pie.as<double>(),
+                                                         pl->d_fc.as<double>(), pl->d_ll.as<double>());
+            CU(ctx, cudaGetLastError());
+            ++pl->n_launches;
+        }
+        if (pl->flags & HMCGPU_FLAG_SUMMARY) {
+            dim3 grd(pl->n_windows, pl->F);
+            summary_accum_kernel<R><<<grd, 128, 0, st>>>(pl->F, ns, pl->chunk, n, pl->n_chains, pl->win_slot0.as<int>(), pl->out.as<R>(),
+                                                         pl->d_sum.as<double>(), pl->d_sumsq.as<double>());
+            CU(ctx, cudaGetLastError());
+            ++pl->n_launches;
+        }
+        if (pl->flags & HMCGPU_FLAG_SMOOTHED_MEAN) {
+            pib_reduce_kernel<R><<<pl->n_windows, 256, 0, st>>>(K, pl->n_chains, pl->win_slot0.as<int>(), pl->wTd.as<int>(),
+                                                                pl->warp_pi_off.as<long long>(), pl->win_pib_off.as<long long>(),
+                                                                pl->pacc.as<R>(), pl->d_pibsum.as<double>());
+            CU(ctx, cudaGetLastError());
+            ++pl->n_launches;
+        }
+    }
+    CU(ctx, cudaEventRecord(pl->ev1, st));
+    CU(ctx, cudaEventSynchronize(pl->ev1));
+    float ms = 0.f;
+    CU(ctx, cudaEventElapsedTime(&ms, pl->ev0, pl->ev1));
+    pl->gpu_ms = ms;
+    for (auto& e : evs) {
+        float k = 0.f;
+        cudaEventElapsedTime(&k, e.first, e.second);
+        pl->sweep_ms += k;
+        cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+    }
+    pl->ran = true;
+    return HMCGPU_OK;
+}
+
+extern "C" int hmcgpu_plan_create(hmcgpu_ctx* ctx, const hmcgpu_problem* p, hmcgpu_plan** out) {
+    if (!out) return fail(ctx, HMCGPU_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    TRY(validate_problem(ctx, p));
+    CU(ctx, cudaSetDevice(ctx->device));
+    hmcgpu_plan* pl = new hmcgpu_plan();
+    pl->ctx = ctx;
+    int rc = (p->precision == 32) ? plan_build<float>(pl, p) : plan_build<double>(pl, p);
+    if (rc != 0) { delete pl; return rc; }
+    *out = pl;
+    return HMCGPU_OK;
+}
+
+extern "C" int hmcgpu_plan_run(hmcgpu_plan* pl) {
+    if (!pl) return HMCGPU_ERR_ARG;
+    hmcgpu_ctx* ctx = pl->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = HMCGPU_ERR_UNSUPPORTED;
+    DISPATCH_K(pl->K, { rc = (pl->precision == 32) ? plan_run_t<float, KK>(pl) : plan_run_t<double, KK>(pl); });
+    return rc;
+}
+
+extern "C" int hmcgpu_plan_fetch(hmcgpu_plan* pl, hmcgpu_result* r) {
+    if (!pl || !r) return HMCGPU_ERR_ARG;
+    hmcgpu_ctx* ctx = pl->ctx;
+    if (!pl->ran) return fail(ctx, HMCGPU_ERR_ARG, "plan_fetch before plan_run");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int K = pl->K, nw = pl->n_windows;
+    const size_t Rr = (size_t)pl->n_chains * pl->nrun;
+    long long d2h = 0;
+    auto down = [&](void* host, const DevBuf& b, size_t bytes) -> cudaError_t {
+        if (!host || !b.p) return cudaSuccess;
+        d2h += (long long)bytes;
+        return cudaMemcpyAsync(host, b.p, bytes, cudaMemcpyDeviceToHost, st);
+    };
+    if ((r->mu || r->sigma2 || r->A || r->pi_end || r->forecasts || r->loglik) && !(pl->flags & HMCGPU_FLAG_DRAWS))
+        return fail(ctx, HMCGPU_ERR_ARG, "per-draw outputs requested without HMCGPU_FLAG_DRAWS");
+    if ((r->summary_mean || r->summary_var) && !(pl->flags & HMCGPU_FLAG_SUMMARY))
+        return fail(ctx, HMCGPU_ERR_ARG, "summary requested without HMCGPU_FLAG_SUMMARY");
+    if (r->pib_mean && !(pl->flags & HMCGPU_FLAG_SMOOTHED_MEAN))
+        return fail(ctx, HMCGPU_ERR_ARG, "pib_mean requested without HMCGPU_FLAG_SMOOTHED_MEAN");
+    if (r->loglik && !(pl->flags & HMCGPU_FLAG_LOGLIK)) return fail(ctx, HMCGPU_ERR_ARG, "loglik requested without HMCGPU_FLAG_LOGLIK");
+    CU(ctx, down(r->mu, pl->d_mu, nw * Rr * K * sizeof(double)));
+    CU(ctx, down(r->sigma2, pl->d_sig2, nw * Rr * K * sizeof(double)));
+    CU(ctx, down(r->A, pl->d_A, nw * Rr * K * K * sizeof(double)));
+    CU(ctx, down(r->pi_end, pl->d_pie, nw * Rr * K * sizeof(double)));
+    CU(ctx, down(r->forecasts, pl->d_fc, nw * Rr * 2 * pl->n_h * sizeof(double)));
+    CU(ctx, down(r->loglik, pl->d_ll, nw * Rr * sizeof(double)));
+    std::vector<double> sum, sumsq, pibsum;
+    std::vector<int> ev(pl->n_slots);
+    if (r->summary_mean || r->summary_var) {
+        sum.resize((size_t)nw * pl->F); sumsq.resize((size_t)nw * pl->F);
+        CU(ctx, down(sum.data(), pl->d_sum, sum.size() * sizeof(double)));
+        CU(ctx, down(sumsq.data(), pl->d_sumsq, sumsq.size() * sizeof(double)));
+    }
+    if (r->pib_mean) { pibsum.resize((size_t)pl->pib_total); CU(ctx, down(pibsum.data(), pl->d_pibsum, pibsum.size() * sizeof(double))); }
+    CU(ctx, down(ev.data(), pl->events, ev.size() * sizeof(int)));
+    CU(ctx, cudaStreamSynchronize(st));
+    const double n = (double)Rr;
+    for (size_t i = 0; i < sum.size(); ++i) {
+        const double m = sum[i] / n;
+        if (r->summary_mean) r->summary_mean[i] = m;
+        if (r->summary_var) r->summary_var[i] = std::max(0.0, sumsq[i] / n - m * m);
+    }
+    for (size_t i = 0; i < pibsum.size(); ++i) r->pib_mean[i] = pibsum[i] / n;
+    // slot order -> caller order
+    std::vector<int> slot_win(pl->n_slots), slot_chain(pl->n_slots);
+    int bad = 0;
+    for (int j = 0; j < nw; ++j) {
+        const int w = pl->order[j];
+        for (int c = 0; c < pl->n_chains; ++c) {
+            const int e = ev[(size_t)j * pl->n_chains + c];
+            if (r->status) r->status[(size_t)w * pl->n_chains + c] = e;
+            bad += e != 0;
+        }
+    }
+    r->gpu_ms = pl->gpu_ms; r->sweep_kernel_ms = pl->sweep_ms; r->n_launches = pl->n_launches;
+    r->n_sweep_launches = pl->n_sweep_launches; r->h2d_bytes = pl->h2d; r->d2h_bytes = d2h; r->state_steps = pl->state_steps;
+    return bad;
+}
+
+extern "C" void hmcgpu_plan_destroy(hmcgpu_plan* pl) {
+    if (!pl) return;
+    cudaSetDevice(pl->ctx->device);
+    delete pl;
+}
+
+extern "C" int hmcgpu_estimate(hmcgpu_ctx* ctx, const hmcgpu_problem* p, hmcgpu_result* r) {
+    if (!r) return fail(ctx, HMCGPU_ERR_ARG, "result is NULL");
+    hmcgpu_plan* pl = nullptr;
+    TRY(hmcgpu_plan_create(ctx, p, &pl));
+    int rc = hmcgpu_plan_run(pl);
+    if (rc == 0) rc = hmcgpu_plan_fetch(pl, r);
+    hmcgpu_plan_destroy(pl);
+    return rc;
+}
+
+// Windows sharded over devices by longest-processing-time-first on T_w; one host thread per device, no collectives.
+extern "C" int hmcgpu_estimate_multi(const int* devices, int n_dev, const hmcgpu_problem* p, hmcgpu_result* r) {
+    if (!devices || n_dev < 1 || !p || !r) return fail(nullptr, HMCGPU_ERR_ARG, "bad arguments");
+    if (p->n_windows < 1 || !p->win_start || !p->win_end) return fail(nullptr, HMCGPU_ERR_ARG, "no windows");
+    const int nw = p->n_windows, K = p->K, nh = p->n_h;
+    std::vector<int> ord(nw);
+    std::iota(ord.begin(), ord.end(), 0);
+    auto Tw = [&](int w) { return p->win_end[w] - p->win_start[w] + 1; };
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return Tw(a) > Tw(b); });
+    std::vector<std::vector<int>> shard(n_dev);
+    std::vector<long long> load(n_dev, 0);
+    for (int w : ord) {
+        const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        shard[d].push_back(w);
+        load[d] += Tw(w);
+    }
+    const size_t Rr = (size_t)p->n_chains * p->nrun;
+    const int F = 3 * K + K * K + 2 * nh + 1;
+    std::vector<long long> pib_off(nw);
+    long long acc = 0;
+    for (int w = 0; w < nw; ++w) { pib_off[w] = acc; acc += (long long)Tw(w) * K; }
+    std::vector<int> rcs(n_dev, 0);
+    std::vector<std::string> errs(n_dev);
+    std::vector<hmcgpu_result> parts(n_dev);
+    std::vector<std::thread> th;
+    for (int d = 0; d < n_dev; ++d) {
+        th.emplace_back([&, d]() {
+            const std::vector<int>& ws = shard[d];
+            const int n = (int)ws.size();
+            memset(&parts[d], 0, sizeof(hmcgpu_result));
+            if (n == 0) return;
+            hmcgpu_ctx* ctx = nullptr;
+            int rc = hmcgpu_ctx_create(devices[d], &ctx);
+            if (rc != 0) { rcs[d] = rc; errs[d] = hmcgpu_last_error(nullptr); return; }
+            std::vector<int32_t> ser(n), st(n), en(n);
+            std::vector<int64_t> id(n);
+            size_t pibn = 0;
+            for (int j = 0; j < n; ++j) {
+                const int w = ws[j];
+                ser[j] = p->win_series ? p->win_series[w] : 0; st[j] = p->win_start[w]; en[j] = p->win_end[w];
+                id[j] = p->win_id ? p->win_id[w] : w;
+                pibn += (size_t)Tw(w) * K;
+            }
+            hmcgpu_problem q = *p;
+            q.n_windows = n; q.win_series = ser.data(); q.win_start = st.data(); q.win_end = en.data(); q.win_id = id.data();
+            std::vector<double> mu, s2, A, pe, fc, ll, sm, sv, pb;
+            std::vector<int32_t> status;
+            hmcgpu_result& o = parts[d];
+            if (r->mu) { mu.resize(n * Rr * K); o.mu = mu.data(); }
+            if (r->sigma2) { s2.resize(n * Rr * K); o.sigma2 = s2.data(); }
+            if (r->A) { A.resize(n * Rr * K * K); o.A = A.data(); }
+            if (r->pi_end) { pe.resize(n * Rr * K); o.pi_end = pe.data(); }
+            if (r->forecasts) { fc.resize(n * Rr * 2 * nh); o.forecasts = fc.data(); }
+            if (r->loglik) { ll.resize(n * Rr); o.loglik = ll.data(); }
+            if (r->summary_mean) { sm.resize((size_t)n * F); o.summary_mean = sm.data(); }
+            if (r->summary_var) { sv.resize((size_t)n * F); o.summary_var = sv.data(); }
+            if (r->pib_mean) { pb.resize(pibn); o.pib_mean = pb.data(); }
+            if (r->status) { status.resize((size_t)n * p->n_chains); o.status = status.data(); }
+            rc = hmcgpu_estimate(ctx, &q, &o);
+            rcs[d] = rc;
+            if (rc < 0) errs[d] = hmcgpu_last_error(ctx);
+            if (rc >= 0) {   // scatter this shard's windows into the caller's arrays (host gather)
+                size_t po = 0;
+                for (int j = 0; j < n; ++j) {
+                    const size_t w = (size_t)ws[j];
+                    if (r->mu) memcpy(r->mu + w * Rr * K, mu.data() + j * Rr * K, Rr * K * sizeof(double));
+                    if (r->sigma2) memcpy(r->sigma2 + w * Rr * K, s2.data() + j * Rr * K, Rr * K * sizeof(double));
+                    if (r->A) memcpy(r->A + w * Rr * K * K, A.data() + j * Rr * K * K, Rr * K * K * sizeof(double));
+                    if (r->pi_end) memcpy(r->pi_end + w * Rr * K, pe.data() + j * Rr * K, Rr * K * sizeof(double));
+                    if (r->forecasts) memcpy(r->forecasts + w * Rr * 2 * nh, fc.data() + j * Rr * 2 * nh, Rr * 2 * nh * sizeof(double));
+                    if (r->loglik) memcpy(r->loglik + w * Rr, ll.data() + j * Rr, Rr * sizeof(double));
+                    if (r->summary_mean) memcpy(r->summary_mean + w * F, sm.data() + (size_t)j * F, F * sizeof(double));
+                    if (r->summary_var) memcpy(r->summary_var + w * F, sv.data() + (size_t)j * F, F * sizeof(double));
+                    if (r->pib_mean) { memcpy(r->pib_mean + pib_off[w], pb.data() + po, (size_t)Tw((int)w) * K * sizeof(double)); po += (size_t)Tw((int)w) * K; }
+                    if (r->status) memcpy(r->status + w * p->n_chains, status.data() + (size_t)j * p->n_chains, p->n_chains * sizeof(int32_t));
+                }
+            }
+            hmcgpu_ctx_destroy(ctx);
+        });
+    }
+    for (auto& t : th) t.join();
+    int bad = 0;
+    r->gpu_ms = 0; r->sweep_kernel_ms = 0; r->n_launches = 0; r->n_sweep_launches = 0; r->h2d_bytes = 0; r->d2h_bytes = 0; r->state_steps = 0;
+    for (int d = 0; d < n_dev; ++d) {
+        if (rcs[d] < 0) return fail(nullptr, rcs[d], "device %d: %s", devices[d], errs[d].c_str());
+        bad += rcs[d];
+        r->gpu_ms = std::max(r->gpu_ms, parts[d].gpu_ms);
+        r->sweep_kernel_ms = std::max(r->sweep_kernel_ms, parts[d].sweep_kernel_ms);
+        r->n_launches += parts[d].n_launches; r->n_sweep_launches += parts[d].n_sweep_launches;
+        r->h2d_bytes += parts[d].h2d_bytes; r->d2h_bytes += parts[d].d2h_bytes; r->state_steps += parts[d].state_steps;
+    }
+    return bad;
+}

@@ -1,0 +1,38 @@
+"""Regenerates the golden fixtures in this directory from the reference checkout (run in the build container only).
+
+Inputs  (read-only, /root/reference): data/processed/inflation.csv (the monthly series run_hmm.jl estimates on) and
+data/output/official/*_summary.csv (the reference's own posterior means over 250 000 draws per end date, produced by
+code/run_hmm.jl official <idx> + code/aggregate.jl).  Outputs: inflation_offic_inf.csv and official_summary_subset.json
+(every 27th end date, 18 windows) — small enough to commit; nothing at test time reads /root/reference.
+Header caveat: in the summary files column trans_a_b holds A[b,a].
+"""
+import csv
+import json
+import os
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+rows = list(csv.DictReader(open(f"{REF}/data/processed/inflation.csv")))
+with open(f"{HERE}/inflation_offic_inf.csv", "w") as f:
+    f.write("date,offic_inf\n")
+    for r in rows:
+        f.write(f"{r['date']},{r['offic_inf']}\n")
+dates = [r["date"] for r in rows]
+
+def load(name):
+    r = list(csv.reader(open(f"{REF}/data/output/official/{name}_summary.csv")))
+    return r[0][1:], {x[0]: [float(v) for v in x[1:]] for x in r[1:]}
+
+names = ["filtered_means", "filtered_variances", "filtered_state_probs", "filtered_trans_probs", "forecasts"]
+tabs = {n: load(n) for n in names}
+subset = {"source": "data/output/official/<name>_summary.csv", "burnin": 100000, "nrun": 250000, "K": 3,
+          "note": "trans_a_b column holds A[b,a]; per-draw values were rounded to 5 digits before averaging",
+          "windows": []}
+for idx in list(range(120, 580, 27)) + [579]:
+    d = dates[idx - 1]
+    if all(d in tabs[n][1] for n in names):
+        subset["windows"].append({"end_index": idx, "date": d, **{n: tabs[n][1][d] for n in names}})
+subset["columns"] = {n: tabs[n][0] for n in names}
+json.dump(subset, open(f"{HERE}/official_summary_subset.json", "w"), indent=1)
+print(len(subset["windows"]), "windows")

@@ -1,0 +1,331 @@
+"""GPU parity tests (run on the B200 box with -m gpu): every call goes through the C ABI (libhmcgpu.so via ctypes)
+and is checked against the CPU oracle on the same seeded inputs, against the reference's golden posterior
+summaries, or through size-independent properties at full size.
+
+Tolerances (north_star): deterministic pieces 1e-5 relative in fp64 and 1e-3 in fp32; state paths under injected
+uniforms bit-exact; full Gibbs posteriors within Monte-Carlo error.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, K3_TRUTH, load_inflation, random_params, synth_hmm
+
+pytestmark = pytest.mark.gpu
+
+RTOL64, RTOL32 = 1e-5, 1e-3
+
+
+def test_native_library_is_loaded(H, ctx):
+    assert os.path.samefile(H.lib_path(), os.path.join(os.path.dirname(H.__file__), "lib", "libhmcgpu.so"))
+    assert H.load().hmcgpu_device_count() >= 1
+
+
+def test_philox_known_answers_on_device(ctx, oracle):
+    ctr = np.array([[0, 0, 0, 0], [0xffffffff] * 4, [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]], dtype=np.uint32)
+    key = np.array([[0, 0], [0xffffffff] * 2, [0xa4093822, 0x299f31d0]], dtype=np.uint32)
+    out = ctx.philox(ctr, key)
+    assert out.tolist() == [[0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8], [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd],
+                            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]]
+    rng = np.random.default_rng(0)
+    ctr = rng.integers(0, 2**32, size=(1000, 4), dtype=np.uint64).astype(np.uint32)
+    key = rng.integers(0, 2**32, size=(1000, 2), dtype=np.uint64).astype(np.uint32)
+    out = ctx.philox(ctr, key)
+    for i in range(0, 1000, 37):
+        assert out[i].tolist() == oracle.philox(ctr[i], key[i])
+
+
+@pytest.mark.parametrize("K", [2, 3, 4])
+@pytest.mark.parametrize("precision,rtol", [(64, RTOL64), (32, RTOL32)])
+def test_filter_matches_oracle(ctx, oracle, K, precision, rtol):
+    rng = np.random.default_rng(100 + K)
+    B, T = 37, 700
+    A, mu, s2, rho = random_params(rng, B, K)
+    y = rng.normal(0, 3, size=(B, T))
+    g = ctx.filter(y, A, mu, s2, rho, precision=precision)
+    for b in range(B):
+        f = oracle.forward(y[b], A[b], mu[b], s2[b], rho[b], want_Pf=False)
+        # probabilities: relative on anything that matters, absolute floor for vanishing entries
+        np.testing.assert_allclose(g.pif[b], f.pif, rtol=rtol, atol=rtol * 1e-3)
+        assert abs(g.loglik[b] - f.loglik) <= rtol * abs(f.loglik)
+        np.testing.assert_allclose(np.log(g.totals[b]), np.log(f.totals), rtol=0, atol=10 * rtol)
+    if precision == 64:     # actual agreement is far tighter than the stated bar
+        f = oracle.forward(y[0], A[0], mu[0], s2[0], rho[0], want_Pf=False)
+        np.testing.assert_allclose(g.pif[0], f.pif, rtol=1e-10, atol=1e-200)
+
+
+def test_filter_shared_series_and_extreme_observations(ctx, oracle):
+    rng = np.random.default_rng(5)
+    K, B, T = 3, 5, 400
+    A, mu, s2, rho = random_params(rng, B, K)
+    y = rng.normal(0, 3, size=T)
+    y[50] = 40.0       # 13+ sigma from every state: the fp32 path must not underflow (hazard H1, scaled recursion)
+    y[200] = -35.0
+    for precision, rtol in ((64, RTOL64), (32, RTOL32)):
+        g = ctx.filter(y, A, mu, s2, rho, precision=precision)
+        assert np.isfinite(g.pif).all() and np.isfinite(g.loglik).all()
+        for b in range(B):
+            f = oracle.forward(y, A[b], mu[b], s2[b], rho[b], want_Pf=False)
+            np.testing.assert_allclose(g.pif[b], f.pif, rtol=rtol, atol=rtol * 1e-3)
+            assert abs(g.loglik[b] - f.loglik) <= rtol * abs(f.loglik)
+
+
+@pytest.mark.parametrize("precision,rtol", [(64, RTOL64), (32, RTOL32)])
+def test_smoother_matches_oracle(ctx, oracle, precision, rtol):
+    rng = np.random.default_rng(21)
+    K, B, T = 3, 9, 500
+    A, mu, s2, rho = random_params(rng, B, K)
+    y = rng.normal(0, 3, size=(B, T))
+    pif = np.stack([oracle.forward(y[b], A[b], mu[b], s2[b], rho[b]).pif for b in range(B)])
+    g = ctx.smooth(A, pif, precision=precision)
+    for b in range(B):
+        f = oracle.forward(y[b], A[b], mu[b], s2[b], rho[b])
+        _, pib = oracle.backward(f.Pf, f.pif)        # the reference's literal Pb recursion
+        np.testing.assert_allclose(g[b], pib, rtol=rtol, atol=rtol * 1e-3)
+
+
+@pytest.mark.parametrize("K", [2, 3, 4])
+def test_state_paths_bit_exact_under_injected_uniforms(ctx, oracle, K):
+    rng = np.random.default_rng(31 + K)
+    B, T = 64, 600
+    A, mu, s2, rho = random_params(rng, B, K)
+    y = rng.normal(0, 3, size=(B, T))
+    pif = np.stack([oracle.forward(y[b], A[b], mu[b], s2[b], rho[b], want_Pf=False).pif for b in range(B)])
+    u = rng.random((B, T))
+    X = ctx.sample_states(A, pif, u)
+    for b in range(B):
+        Xo = oracle.sample_states(pif[b], A[b], u[b], form=1)
+        np.testing.assert_array_equal(X[b], Xo)
+    # edge cases: u = 0, u just below 1, and an explicit piN (quirk Q1 path)
+    u0 = np.zeros((B, T)); u1 = np.full((B, T), np.nextafter(1.0, 0.0))
+    piN = rng.dirichlet(np.ones(K), size=B)
+    for uu in (u0, u1):
+        X = ctx.sample_states(A, pif, uu, piN=piN)
+        for b in range(0, B, 7):
+            np.testing.assert_array_equal(X[b], oracle.sample_states(pif[b], A[b], uu[b], piN=piN[b], form=1))
+
+
+def test_forecast_matches_oracle(ctx, oracle):
+    rng = np.random.default_rng(41)
+    K, B = 3, 50
+    A, mu, s2, rho = random_params(rng, B, K)
+    hs = list(range(1, 13))
+    yreal = rng.normal(size=len(hs))
+    g = ctx.forecast(mu, A, rho, hs, yreal)
+    for b in range(B):
+        for j, h in enumerate(hs):
+            f, e = oracle.forecast(mu[b], A[b], rho[b], h, yreal[j])
+            assert abs(g[b, j, 0] - f) <= 1e-12 * max(1, abs(f)) and abs(g[b, j, 1] - e) <= 1e-11 * max(1, abs(e))
+
+
+def test_conjugate_draws_match_oracle_streams(ctx, oracle):
+    """Same Philox streams on both sides: fp64 draws agree to rounding, fp32 to 1e-3 relative in distribution."""
+    rng = np.random.default_rng(51)
+    K, B = 3, 200
+    Ni = rng.integers(0, 300, size=(B, K))
+    ybar = rng.normal(3, 2, size=(B, K))
+    S = Ni * ybar
+    S2 = Ni * rng.uniform(0.3, 4.0, size=(B, K))
+    trans = rng.integers(0, 200, size=(B, K, K)) + 1
+    xi, one = np.full(K, 3.3), np.ones(K)
+    s2, mu, rho, A = ctx.draw_params(Ni, S, S2, trans, xi, one, one, 2 * one, seed=1234, chain0=1000, sweep=17, precision=64)
+    for b in range(B):
+        o = oracle.draw_params(Ni[b], S[b], S2[b], trans[b], xi, one, one, 2 * one, 1234, 1000 + b, 17)
+        np.testing.assert_allclose(s2[b], o[0], rtol=1e-9)
+        np.testing.assert_allclose(mu[b], o[1], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(rho[b], o[2], rtol=1e-9)
+        np.testing.assert_allclose(A[b], o[3], rtol=1e-9)
+    s2f, muf, rhof, Af = ctx.draw_params(Ni, S, S2, trans, xi, one, one, 2 * one, seed=1234, chain0=1000, sweep=17, precision=32)
+    # fp32 follows the same streams; a rejection decision can flip only on a measure-~1e-6 set
+    close = np.isclose(s2f, s2, rtol=2e-3).mean()
+    assert close > 0.99
+    assert np.isclose(Af, A, rtol=5e-3, atol=1e-5).mean() > 0.99
+
+
+def _run(H, ctx, y, ws, we, **kw):
+    spec = H.ProblemSpec(y, ws, we, **kw)
+    return H.estimate(ctx, spec)
+
+
+def test_gibbs_first_sweeps_follow_the_oracle_chain(H, ctx, oracle):
+    """fp64 device chain vs oracle chain on the same Philox streams: identical up to libm rounding for the first sweeps."""
+    y, _ = synth_hmm(260, **K3_TRUTH)
+    hs = (1, 12)
+    for (s, e) in ((1, 200), (20, 248)):
+        o = _run(H, ctx, y, [s], [e], K=3, n_chains=3, burnin=2, nrun=6, seed=77, horizons=hs, precision=64,
+                 flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_LOGLIK)
+        assert o.events == 0
+        for c in range(3):
+            yf = [y[e - 1 + h] for h in hs]
+            r = oracle.gibbs(y[s - 1:e], 3, 2, 6, seed=77, chain=c, horizons=hs, y_future=yf,
+                             flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM)
+            sl = slice(c * 6, (c + 1) * 6)
+            np.testing.assert_allclose(o.mu[0][:, sl].T, r.mu, rtol=1e-8)
+            np.testing.assert_allclose(o.sigma2[0][:, sl].T, r.sigma2, rtol=1e-8)
+            np.testing.assert_allclose(np.transpose(o.A[0][:, :, sl], (2, 1, 0)), r.A, rtol=1e-8)
+            np.testing.assert_allclose(o.pi_end[0][:, sl].T, r.pi_end, rtol=1e-7, atol=1e-12)
+            np.testing.assert_allclose(o.forecasts[0][:, sl].T, r.forecasts, rtol=1e-8, atol=1e-9)
+            np.testing.assert_allclose(o.loglik[0][sl], r.loglik, rtol=1e-9)
+
+
+def test_gibbs_reference_integration_test(H, ctx):
+    """The reference's only test (test/runtests.jl:20-57) through the estimatemodel mirror, fp64 and fp32."""
+    y, _ = synth_hmm(500, [[0.5, 0.5], [0.2, 0.8]], [-5.0, 4.0], [1.0, 0.5], seed=123)
+    for precision in (64, 32):
+        opt = H.EstOpt(y, list(range(500)), sampleRange=range(1, 477), endIndex=476, horizons=[12], D=2, burnin=3000,
+                       Nrun=1000, series="test", precision=precision)
+        s = H.estimatemodel(opt, ctx)
+        assert s.μ.shape == (1000, 2) and s.σ.shape == (1000, 2) and s.A.shape == (1000, 2, 2)
+        assert s.πb.shape == (1000, 1, 2) and s.forecasts.shape == (1000, 2) and len(s.obsdates) == 1000
+        assert np.all(np.abs(s.μ.mean(0) - [-5.0, 4.0]) < 0.3)          # runtests.jl:56
+        assert np.all(np.abs(s.σ.mean(0) - [1.0, 0.5]) < 0.5)           # runtests.jl:57
+        assert np.all(np.diff(s.μ, axis=1) > 0)
+        np.testing.assert_allclose(s.A.sum(2), 1.0, atol=1e-5)
+        np.testing.assert_allclose(s.πb[:, -1, :].sum(1), 1.0, atol=1e-5)
+        np.testing.assert_allclose(s.forecasts[:, 1], s.forecasts[:, 0] - y[476 + 11], atol=1e-4)
+        assert s.events == 0
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+def test_gibbs_posterior_matches_oracle_posterior(H, ctx, oracle, precision):
+    """Monte-Carlo parity on a synthetic series: pooled multi-chain posterior means/variances vs the oracle's."""
+    y, _ = synth_hmm(412, **K3_TRUTH)
+    hs = (1, 6, 12)
+    nch, burn, nrun = 64, 500, 500
+    o = _run(H, ctx, y, [1], [400], K=3, n_chains=nch, burnin=burn, nrun=nrun, seed=2024, horizons=hs, precision=precision,
+             flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_SUMMARY)
+    yf = [y[400 - 1 + h] for h in hs]
+    outs, _ = oracle.gibbs_batch([dict(y=y[:400], K=3, burnin=burn, nrun=nrun, seed=4048, chain=c, horizons=hs, y_future=yf)
+                                  for c in range(16)])
+    cat = lambda k: np.concatenate([getattr(r, k) for r in outs])
+    om, os2, oA, ope, ofc = cat("mu"), cat("sigma2"), cat("A"), cat("pi_end"), cat("forecasts")
+
+    def close(g, ref, name):
+        # standard error of the difference of two MC means; chains are autocorrelated -> inflate by 4, 5-sigma band
+        se = 4 * np.sqrt(ref.var(0) / len(ref) + g.var(0) / len(g))
+        d = np.abs(g.mean(0) - ref.mean(0))
+        assert np.all(d <= 5 * se + 1e-4), (name, d, se)
+        np.testing.assert_allclose(g.var(0), ref.var(0), rtol=0.35, atol=1e-5, err_msg=name)
+
+    close(o.mu[0].T, om, "mu")
+    close(o.sigma2[0].T, os2, "sigma2")
+    close(np.transpose(o.A[0], (2, 1, 0)).reshape(-1, 9), oA.reshape(-1, 9), "A")
+    close(o.pi_end[0].T, ope, "pi_end")
+    close(o.forecasts[0].T, ofc, "forecasts")
+    # device-side summary == moments of the returned draws
+    F = np.concatenate([o.mu[0], o.sigma2[0], o.A[0].reshape(9, -1), o.pi_end[0], o.forecasts[0]])
+    np.testing.assert_allclose(o.summary_mean[0][:-1], F.mean(1), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(o.summary_var[0][:-1], F.var(1), rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("which", [0, 9, 18])
+def test_gibbs_matches_reference_golden_summaries(H, ctx, which):
+    """Real series, real end dates: posterior means vs data/output/official/*_summary.csv (MC tolerance)."""
+    y, dates = load_inflation()
+    g = json.load(open(os.path.join(GOLDEN, "official_summary_subset.json")))["windows"][which]
+    idx = g["end_index"]
+    o = _run(H, ctx, y, [1], [idx], K=3, n_chains=64, burnin=2000, nrun=1000, seed=1234, horizons=(12,), precision=32,
+             flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY)
+    m = o.summary_mean[0]
+    np.testing.assert_allclose(m[0:3], g["filtered_means"], atol=0.08)
+    np.testing.assert_allclose(m[3:6], g["filtered_variances"], rtol=0.06)
+    np.testing.assert_allclose(m[6:15], g["filtered_trans_probs"], atol=0.01)     # summary A index s*K+r == trans_s_r column
+    np.testing.assert_allclose(m[15:18], g["filtered_state_probs"], atol=0.01)
+    if idx + 12 <= len(y):
+        np.testing.assert_allclose(m[18:20], g["forecasts"], atol=0.06)
+
+
+def test_smoothed_probability_means(H, ctx, oracle):
+    y, _ = synth_hmm(300, **K3_TRUTH)
+    o = _run(H, ctx, y, [1, 1], [300, 250], K=3, n_chains=32, burnin=300, nrun=300, seed=9, horizons=(), precision=32,
+             flags=H.FLAG_REF_Q1 | H.FLAG_SMOOTHED_MEAN | H.FLAG_SUMMARY)
+    for w, n in enumerate((300, 250)):
+        outs, _ = oracle.gibbs_batch([dict(y=y[:n], K=3, burnin=300, nrun=600, seed=10, chain=c, horizons=(), want_pib_mean=True)
+                                      for c in range(8)])
+        ref = np.mean([r.pib_mean for r in outs], axis=0)
+        pm = o.pib_mean[w]
+        assert pm.shape == (n, 3)
+        np.testing.assert_allclose(pm.sum(1), 1.0, atol=1e-4)
+        assert np.abs(pm - ref).max() < 0.06 and np.abs(pm - ref).mean() < 0.004
+        # last row = mean of pi_end
+        np.testing.assert_allclose(pm[-1], o.summary_mean[w][15:18], atol=1e-5)
+
+
+def test_expanding_windows_ragged_batch_and_sharding_invariance(H, ctx):
+    """Ragged windows in one launch; results must not depend on batching/sharding (counter-based RNG + win_id)."""
+    y, _ = synth_hmm(330, **K3_TRUTH)
+    ws, we = H.expanding_windows(101, 140)
+    kw = dict(K=3, n_chains=3, burnin=30, nrun=20, seed=5, horizons=(1, 12), precision=64, flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS)
+    full = _run(H, ctx, y, ws, we, **kw)
+    assert full.state_steps == int((we - ws + 1).sum()) * 3 * 50
+    for shard in H.shard_windows(we - ws + 1, 3):
+        part = _run(H, ctx, y, ws[shard], we[shard], win_id=shard, **kw)
+        np.testing.assert_array_equal(part.mu, full.mu[shard])
+        np.testing.assert_array_equal(part.A, full.A[shard])
+        np.testing.assert_array_equal(part.forecasts, full.forecasts[shard])
+    # a window estimated alone equals the same window inside the batch
+    one = _run(H, ctx, y, ws[7:8], we[7:8], win_id=[7], **kw)
+    np.testing.assert_array_equal(one.mu[0], full.mu[7])
+
+
+def test_multiple_series_time_major_layout(H, ctx):
+    rng = np.random.default_rng(3)
+    ys = np.stack([synth_hmm(150, seed=s, **K3_TRUTH)[0] for s in range(5)])
+    kw = dict(K=3, n_chains=2, burnin=20, nrun=10, seed=1, horizons=(3,), precision=64, flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS)
+    o = _run(H, ctx, ys, [1] * 5, [140] * 5, win_series=np.arange(5), **kw)
+    for s in (0, 3):
+        single = _run(H, ctx, ys[s], [1], [140], win_id=[s], **kw)
+        np.testing.assert_array_equal(single.mu[0], o.mu[s])
+        np.testing.assert_array_equal(single.forecasts[0], o.forecasts[s])
+
+
+def test_plan_run_is_repeatable_and_device_resident(H, ctx):
+    y, _ = synth_hmm(220, **K3_TRUTH)
+    spec = H.ProblemSpec(y, [1, 1], [200, 150], K=3, n_chains=40, burnin=20, nrun=30, seed=3, horizons=(12,), precision=32,
+                         flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_SUMMARY)
+    plan = H.Plan(ctx, spec)
+    plan.run(); a = plan.fetch()
+    plan.run(); b = plan.fetch()
+    plan.close()
+    np.testing.assert_array_equal(a.mu, b.mu)
+    np.testing.assert_array_equal(a.summary_mean, b.summary_mean)
+    assert a.n_sweep_launches >= 2 and a.gpu_ms > 0 and a.sweep_kernel_ms > 0
+    assert a.state_steps == (200 + 150) * 40 * 50
+
+
+def test_full_size_properties_fp32(H, ctx):
+    """BASELINE config 2 shape (500 expanding windows, T=101..600), reduced sweeps: size-independent properties."""
+    y, _ = synth_hmm(612, **K3_TRUTH)
+    ws, we = H.expanding_windows(101, 600)
+    o = _run(H, ctx, y, ws, we, K=3, n_chains=32, burnin=60, nrun=40, seed=1234, horizons=tuple(range(1, 13)), precision=32,
+             flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY)
+    m, v = o.summary_mean, o.summary_var
+    assert np.isfinite(m).all() and np.isfinite(v).all() and (v >= 0).all()
+    assert o.events == 0 and (o.status == 0).all()
+    assert np.all(np.diff(m[:, 0:3], axis=1) > 0)                                  # increasing-mu order
+    A = m[:, 6:15].reshape(-1, 3, 3)                                               # [s][r]
+    np.testing.assert_allclose(A.sum(1), 1.0, atol=1e-4)                           # rows of the mean A sum to 1
+    np.testing.assert_allclose(m[:, 15:18].sum(1), 1.0, atol=1e-4)                 # pi_end is a probability vector
+    fc = m[:, 18:42].reshape(-1, 12, 2)
+    yreal = np.array([[y[e - 1 + h] for h in range(1, 13)] for e in we])
+    np.testing.assert_allclose(fc[:, :, 0] - fc[:, :, 1], yreal, atol=2e-4)        # error = forecast - realised
+    assert (fc[:, :, 0] > m[:, 0:1] - 0.5).all() and (fc[:, :, 0] < m[:, 2:3] + 0.5).all()   # convex combination of mu
+    # long windows recover the generating parameters
+    big = we >= 500
+    assert np.abs(m[big, 0:3] - K3_TRUTH["mu"]).max() < 0.8
+
+
+def test_error_paths(H, ctx):
+    y = np.arange(50.0)
+    with pytest.raises(H.HmcGpuError) as e:
+        _run(H, ctx, y, [1], [60], K=3)
+    assert e.value.code == -1
+    with pytest.raises(H.HmcGpuError) as e:
+        _run(H, ctx, y, [1], [40], K=7)
+    assert e.value.code == -4
+    with pytest.raises(H.HmcGpuError):
+        _run(H, ctx, y, [10], [10], K=3)
+    with pytest.raises(H.HmcGpuError):
+        H.Context(99)

@@ -1,0 +1,197 @@
+"""CPU tests: the oracle (oracle/hmc_oracle.c) against known answers, an independent numpy/scipy restatement,
+the reference's own test tolerances (test/runtests.jl:56-57) and the reference's golden posterior summaries."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy.special import logsumexp
+from scipy.stats import norm
+
+from conftest import GOLDEN, K3_TRUTH, load_inflation, random_params, synth_hmm
+
+
+def test_philox_known_answers(oracle):
+    # Random123 kat_vectors for philox4x32-10
+    assert oracle.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert oracle.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert oracle.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def numpy_filter(y, A, mu, sigma2, rho):
+    """Independent log-space forward filter (scipy.stats.norm.logpdf + logsumexp)."""
+    T, K = len(y), len(mu)
+    logp = norm.logpdf(y[:, None], mu[None, :], np.sqrt(sigma2)[None, :])
+    la = np.log(A)
+    pif = np.zeros((T, K))
+    ll = 0.0
+    prev = np.log(rho)
+    for t in range(T):
+        joint = prev[:, None] + la + logp[t][None, :]
+        tot = logsumexp(joint)
+        ll += tot
+        prev = logsumexp(joint, axis=0) - tot
+        pif[t] = np.exp(prev)
+    return pif, ll
+
+
+@pytest.mark.parametrize("K", [2, 3, 4])
+def test_forward_matches_numpy(oracle, K):
+    rng = np.random.default_rng(7 + K)
+    A, mu, s2, rho = (v[0] for v in random_params(rng, 1, K))
+    y = rng.normal(0, 3, size=300)
+    f = oracle.forward(y, A, mu, s2, rho)
+    pif, ll = numpy_filter(y, A, mu, s2, rho)
+    np.testing.assert_allclose(f.pif, pif, rtol=1e-9, atol=1e-300)
+    assert abs(f.loglik - ll) < 1e-8 * abs(ll)
+    np.testing.assert_allclose(f.pif.sum(1), 1.0, atol=1e-12)
+    np.testing.assert_allclose(f.Pf.sum((1, 2)), 1.0, atol=1e-12)
+    assert abs(np.log(f.totals).sum() - f.loglik) < 1e-9
+
+
+def test_backward_forms_agree_and_match_numpy(oracle):
+    rng = np.random.default_rng(3)
+    K = 3
+    A, mu, s2, rho = (v[0] for v in random_params(rng, 1, K))
+    y = rng.normal(0, 3, size=200)
+    f = oracle.forward(y, A, mu, s2, rho)
+    Pb, pib = oracle.backward(f.Pf, f.pif)
+    pib2 = oracle.backward_pif(A, f.pif)
+    np.testing.assert_allclose(pib, pib2, rtol=1e-9, atol=1e-14)
+    # independent forward-backward: beta recursion
+    logp = norm.pdf(y[:, None], mu[None, :], np.sqrt(s2)[None, :])
+    T = len(y)
+    beta = np.ones((T, K))
+    for t in range(T - 2, -1, -1):
+        beta[t] = A @ (logp[t + 1] * beta[t + 1])
+        beta[t] /= beta[t].sum()
+    sm = f.pif * beta
+    sm /= sm.sum(1, keepdims=True)
+    np.testing.assert_allclose(pib, sm, rtol=1e-8, atol=1e-13)
+
+
+def test_sample_states_forms_give_same_paths(oracle):
+    rng = np.random.default_rng(5)
+    K = 3
+    A, mu, s2, rho = (v[0] for v in random_params(rng, 1, K))
+    y = rng.normal(0, 3, size=400)
+    f = oracle.forward(y, A, mu, s2, rho)
+    for rep in range(20):
+        u = rng.random(len(y))
+        X0 = oracle.sample_states(f.pif, A, u, Pf=f.Pf, form=0)
+        X1 = oracle.sample_states(f.pif, A, u, form=1)
+        assert X0.min() >= 1 and X0.max() <= K
+        assert (X0 == X1).all()
+
+
+def test_sample_states_distribution(oracle):
+    # the marginal of many sampled paths must equal the smoothed probabilities
+    rng = np.random.default_rng(11)
+    K = 3
+    A, mu, s2, rho = (v[0] for v in random_params(rng, 1, K))
+    y = rng.normal(0, 3, size=30)
+    f = oracle.forward(y, A, mu, s2, rho)
+    pib = oracle.backward_pif(A, f.pif)
+    n = 20000
+    counts = np.zeros((len(y), K))
+    for _ in range(n):
+        X = oracle.sample_states(f.pif, A, rng.random(len(y)), form=1)
+        counts[np.arange(len(y)), X - 1] += 1
+    assert np.abs(counts / n - pib).max() < 4 * 0.5 / np.sqrt(n)
+
+
+def test_forecast_matches_numpy(oracle):
+    rng = np.random.default_rng(13)
+    for K in (2, 3, 4):
+        A, mu, s2, rho = (v[0] for v in random_params(rng, 1, K))
+        for h in (1, 2, 5, 12, 13):
+            f, e = oracle.forecast(mu, A, rho, h, 1.25)
+            ref = rho @ np.linalg.matrix_power(A, h) @ mu
+            assert abs(f - ref) < 1e-12 * max(1, abs(ref)) and abs(e - (ref - 1.25)) < 1e-12 * max(1, abs(ref))
+
+
+def test_gamma_normal_moments(oracle):
+    for shape in (0.5, 1.0, 2.5, 50.0):
+        g = np.array([oracle.gamma(shape, 99, c, 3, (2 << 16)) for c in range(40000)])
+        assert abs(g.mean() - shape) < 5 * np.sqrt(shape / len(g))
+        assert abs(g.var() - shape) < 0.08 * shape
+
+
+def test_draw_params_moments(oracle):
+    K = 3
+    Ni, S, S2 = np.array([50, 100, 10]), np.array([80.0, 350.0, 83.0]), np.array([40.0, 55.0, 79.0])
+    trans = np.array([[45, 3, 2], [4, 90, 6], [2, 3, 5]]) + 1
+    xi, one = np.full(K, 3.2), np.ones(K)
+    n = 8000
+    out = [oracle.draw_params(Ni, S, S2, trans, xi, one, one, 2 * one, 1234, c, 7) for c in range(n)]
+    s2 = np.array([o[0] for o in out]); mu = np.array([o[1] for o in out]); rho = np.array([o[2] for o in out]); A = np.array([o[3] for o in out])
+    ybar = S / Ni
+    a = 1 + 0.5 * Ni
+    b = 2 + 0.5 * S2 + 0.5 * Ni / (Ni + 1) * (ybar - xi) ** 2
+    np.testing.assert_allclose(s2.mean(0), b / (a - 1), rtol=0.03)               # mean of InverseGamma(a,b)
+    np.testing.assert_allclose(mu.mean(0), (S + xi) / (Ni + 1), atol=0.02)
+    np.testing.assert_allclose(rho.mean(0), 1 / 3, atol=0.01)
+    np.testing.assert_allclose(A.mean(0), trans / trans.sum(1, keepdims=True), atol=0.01)
+    np.testing.assert_allclose(A.sum(2), 1.0, atol=1e-12)
+
+
+def test_make_params_rule(oracle):
+    y, _ = synth_hmm(300, **K3_TRUTH)
+    X, mu0, sd0 = oracle.make_params(y, 3)
+    R = y.max() - y.min()
+    np.testing.assert_allclose(mu0, np.linspace(np.median(y) - 0.25 * R, np.median(y) + 0.25 * R, 3))
+    assert abs(sd0 - y.std(ddof=1)) < 1e-12
+    np.testing.assert_array_equal(X, np.argmin(np.abs(y[:, None] - mu0[None, :]), axis=1) + 1)
+
+
+def test_reference_integration_test(oracle):
+    """test/runtests.jl:20-57: D=2, T=500, sampleRange=1:476, burnin 3000, Nrun 1000; atol 0.3 (mu), 0.5 (sigma)."""
+    y, _ = synth_hmm(500, [[0.5, 0.5], [0.2, 0.8]], [-5.0, 4.0], [1.0, 0.5], seed=123)
+    o = oracle.gibbs(y[:476], 2, 3000, 1000, seed=1234, horizons=(12,), y_future=[y[476 + 11]])
+    assert np.all(np.abs(o.mu.mean(0) - [-5.0, 4.0]) < 0.3)
+    assert np.all(np.abs(o.sigma2.mean(0) - [1.0, 0.5]) < 0.5)
+    assert o.n_events == 0
+    assert np.all(np.diff(o.mu, axis=1) > 0)                 # draws are emitted in increasing-mu order (:501-513)
+    np.testing.assert_allclose(o.A.sum(2), 1.0, atol=1e-12)
+    np.testing.assert_allclose(o.forecasts[:, 1], o.forecasts[:, 0] - y[476 + 11], atol=1e-12)
+
+
+def test_gibbs_deterministic_and_batch(oracle):
+    y, _ = synth_hmm(200, **K3_TRUTH)
+    a = oracle.gibbs(y, 3, 50, 50, seed=5, chain=3)
+    b = oracle.gibbs(y, 3, 50, 50, seed=5, chain=3)
+    c = oracle.gibbs(y, 3, 50, 50, seed=5, chain=4)
+    np.testing.assert_array_equal(a.mu, b.mu)
+    assert not np.array_equal(a.mu, c.mu)
+    outs, used = oracle.gibbs_batch([dict(y=y, K=3, burnin=50, nrun=50, seed=5, chain=ch) for ch in (3, 4)], n_threads=2)
+    np.testing.assert_array_equal(outs[0].mu, a.mu)
+    np.testing.assert_array_equal(outs[1].mu, c.mu)
+    assert used == 2
+    # the pif form of the backward sampler follows the same chain (identical paths up to measure-zero rounding ties)
+    d = oracle.gibbs(y, 3, 50, 50, seed=5, chain=3, flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM)
+    np.testing.assert_allclose(d.mu, a.mu, rtol=1e-9)
+
+
+@pytest.mark.parametrize("which", [0, 9, 18])
+def test_golden_posterior_summaries(oracle, which):
+    """The oracle reproduces the reference's own posterior means (data/output/official/*_summary.csv, 250k draws
+    after 100k burn-in) on the real series within Monte-Carlo tolerance."""
+    y, dates = load_inflation()
+    g = json.load(open(os.path.join(GOLDEN, "official_summary_subset.json")))["windows"][which]
+    idx = g["end_index"]
+    assert dates[idx - 1] == g["date"]
+    yf = [y[idx - 1 + 12]] if idx - 1 + 12 < len(y) else [np.nan]
+    outs, _ = oracle.gibbs_batch([dict(y=y[:idx], K=3, burnin=3000, nrun=6000, seed=1234, chain=c, horizons=(12,), y_future=yf)
+                                  for c in range(4)])
+    mu = np.concatenate([o.mu for o in outs]).mean(0)
+    s2 = np.concatenate([o.sigma2 for o in outs]).mean(0)
+    A = np.concatenate([o.A for o in outs]).mean(0)
+    pe = np.concatenate([o.pi_end for o in outs]).mean(0)
+    fc = np.concatenate([o.forecasts for o in outs]).mean(0)
+    np.testing.assert_allclose(mu, g["filtered_means"], atol=0.08)
+    np.testing.assert_allclose(s2, g["filtered_variances"], rtol=0.06)
+    np.testing.assert_allclose(A.T.ravel(), g["filtered_trans_probs"], atol=0.01)   # trans_a_b column = A[b,a]
+    np.testing.assert_allclose(pe, g["filtered_state_probs"], atol=0.01)
+    if np.isfinite(fc[1]):
+        np.testing.assert_allclose(fc, g["forecasts"], atol=0.06)
