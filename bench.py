@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — HMM state-steps/sec of the rolling-window Gibbs/FFBS estimation (BASELINE.json metric).
+
+One "step" = one whole estimation pass over the batch: every window x chain runs burnin + nrun Gibbs sweeps
+(draws, forward filter, backward sampling, forecasts h=1..12, per-window posterior summaries).
+Workload at N=1 = BASELINE.json configs[1] (SURVEY §8d "C2"): one synthetic K=3 series of length 612 (numpy
+default_rng(1234)), 500 expanding windows T_w = 101..600, 1000 burn-in + 1000 saved sweeps, 256 chains per window.
+N>1 (torchrun, one rank per GPU): end dates are sharded over the ranks (LPT on T_w) and the chains per window scale
+with N so per-GPU work is fixed (weak scaling); no data-path collective, only a final gather of per-window summaries.
+
+  value : state-steps / device time of the sweeps with inputs resident in HBM (hmcgpu_plan_run; CUDA events on the
+          library's stream, max over ranks).
+  e2e   : the same through the public call with HOST buffers (hmcgpu_estimate: H2D of the series, all sweeps, D2H of
+          the summaries, device allocation included), wall clock between barriers.
+  --impl reference : the CPU oracle (port of the reference's algorithm; Julia is not installed, so the reference's own
+          implementation cannot run) on all host threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "HMM state-steps/sec (windows x chains x T per Gibbs sweep)"
+UNIT = "state-steps/s"
+K = 3
+TRUTH = dict(A=np.array([[0.96, 0.02, 0.02], [0.02, 0.96, 0.02], [0.02, 0.02, 0.96]]),
+             mu=np.array([1.6, 3.5, 8.3]), sigma2=np.array([0.8, 0.55, 7.9]))
+HORIZONS = tuple(range(1, 13))
+
+
+def synth_series(T=612, seed=1234):
+    """generateData semantics (src/Hmc.jl:210-229) with numpy's default_rng(1234)."""
+    rng = np.random.default_rng(seed)
+    X = np.zeros(T, dtype=np.int64)
+    for t in range(1, T):
+        X[t] = rng.choice(K, p=TRUTH["A"][X[t - 1]])
+    return TRUTH["mu"][X] + np.sqrt(TRUTH["sigma2"][X]) * rng.standard_normal(T)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def barrier_sync(dist, local):
+    import torch
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(local)
+
+
+def all_max(dist, local, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def all_sum(dist, local, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def cpu_baseline(y, ws, we, target_seconds=15.0, threads=0):
+    """The oracle (kind "port") on all host cores over a bounded sample of the workload: every window, 1 chain,
+    as many sweeps as fit ~target_seconds (calibrated on a short run)."""
+    from oracle import oracle as O
+    cores = threads or os.cpu_count() or 1
+    T = (we - ws + 1).astype(np.int64)
+
+    def jobs(burn, nrun, idx):
+        out = []
+        for w in idx:
+            e = int(we[w])
+            yf = [y[e - 1 + h] if e - 1 + h < len(y) else np.nan for h in HORIZONS]
+            out.append(dict(y=y[int(ws[w]) - 1:e], K=K, burnin=burn, nrun=nrun, seed=1234, chain=int(w), horizons=HORIZONS,
+                            y_future=yf))
+        return out
+
+    idx = np.arange(len(T))
+    t0 = time.perf_counter()
+    O.gibbs_batch(jobs(2, 2, idx), n_threads=cores)
+    cal = max(time.perf_counter() - t0, 1e-3)
+    rate = T.sum() * 4 / cal
+    sweeps = int(max(8, min(2000, target_seconds * rate / T.sum())))
+    burn = sweeps // 2
+    t0 = time.perf_counter()
+    _, used = O.gibbs_batch(jobs(burn, sweeps - burn, idx), n_threads=cores)
+    dt = time.perf_counter() - t0
+    steps = int(T.sum()) * sweeps
+    return {"value": steps / dt, "unit": UNIT, "cores": used, "kind": "port",
+            "sample": f"all {len(T)} windows (T=101..600), 1 chain each, {burn}+{sweeps - burn} sweeps, h=1..12 forecasts; "
+                      f"{steps:.3e} state-steps in {dt:.1f}s; fp64 C port of src/Hmc.jl (Julia absent)"}, dt, steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    y = synth_series()
+    ws = np.ones(500, dtype=np.int32); we = np.arange(101, 601, dtype=np.int32)
+    per = []
+    base = None
+    target = max(3.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        b, dt, steps = cpu_baseline(y, ws, we, target_seconds=target)
+        if i >= args.warmup:
+            per.append((dt, steps))
+            base = b
+    dt = sum(p[0] for p in per); steps = sum(p[1] for p in per)
+    v = steps / dt
+    base["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / len(per), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.gpus) | {"note": "reference arm = CPU port of the reference on host cores; "
+                                                                   "Julia is not installed so the reference itself cannot run"},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "C2 rolling estimation: 500 expanding windows T=101..600 of one synthetic K=3 series (len 612, "
+                        "default_rng(1234)), burnin+nrun Gibbs sweeps, forecasts h=1..12, per-window posterior summaries",
+            "K": K, "windows": 500, "chains_per_window": args.chains * world, "burnin": args.burnin, "nrun": args.nrun,
+            "precision": f"fp{args.precision}", "sharding": f"end dates over {world} rank(s) (LPT on T_w), no collective",
+            "l2": "pif spill working set (sum_T*chains*12 B per rank) exceeds the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains", type=int, default=256, help="chains per window per GPU")
+    ap.add_argument("--burnin", type=int, default=1000)
+    ap.add_argument("--nrun", type=int, default=1000)
+    ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per sweep-kernel launch from an ncu capture")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import hmc_jl_b200 as H
+    rank, world, local, dist = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    torch.zeros(1, device=f"cuda:{local}")          # create the primary context torch.cuda.synchronize() needs
+
+    y = synth_series()
+    ws_all, we_all = H.expanding_windows(101, 600)
+    shard = H.shard_windows(we_all - ws_all + 1, world)[rank]
+    ws, we = ws_all[shard], we_all[shard]
+    n_chains = args.chains * world                  # weak scaling: per-GPU work fixed
+    spec = H.ProblemSpec(y, ws, we, K=K, n_chains=n_chains, burnin=args.burnin, nrun=args.nrun, seed=1234, horizons=HORIZONS,
+                         precision=args.precision, flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY, win_id=shard)
+    ctx = H.Context(local)
+    plan = H.Plan(ctx, spec)
+    for _ in range(args.warmup):
+        plan.run()
+    sampler = ClockSampler(local)
+    barrier_sync(dist, local)
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = sweep_ms = 0.0
+    launches = sweep_launches = 0
+    for _ in range(args.steps):
+        plan.run()
+        r = H.binding.Result()                      # timing fields only (no output pointers -> no D2H)
+        ctx._check(ctx.L.hmcgpu_plan_fetch(plan.h, ctypes.byref(r)))
+        dev_ms += r.gpu_ms; sweep_ms += r.sweep_kernel_ms
+        launches += r.n_launches; sweep_launches += r.n_sweep_launches
+        steps_per_run = r.state_steps
+    barrier_sync(dist, local)
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    res = plan.fetch()
+    plan.close()
+    dev_s = all_max(dist, local, dev_ms / 1e3)
+    total_steps = all_sum(dist, local, float(steps_per_run) * args.steps)
+    value = total_steps / dev_s
+
+    # ---- end to end through the public call with host buffers
+    H.estimate(ctx, spec)                            # warm the allocator path once
+    barrier_sync(dist, local)
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        o = H.estimate(ctx, spec)
+        h2d += o.h2d_bytes; d2h += o.d2h_bytes
+        if dist is not None:                         # final gather of per-window summaries on rank 0
+            t = torch.from_numpy(np.concatenate([o.summary_mean, o.summary_var], axis=1)).to(f"cuda:{local}")
+            pad = torch.zeros((max(len(s) for s in H.shard_windows(we_all - ws_all + 1, world)), t.shape[1]), dtype=t.dtype, device=t.device)
+            pad[: t.shape[0]] = t
+            outl = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+            dist.gather(pad, outl, dst=0)
+            if rank == 0:
+                _ = [x.cpu() for x in outl]
+    barrier_sync(dist, local)
+    e2e_s = all_max(dist, local, time.perf_counter() - t0)
+    e2e_value = total_steps / e2e_s
+
+    # ---- roofline of the dominant kernel (gibbs_sweeps_kernel): algorithmic bytes = (2K+2)*b per state-step
+    bpe = 4 if args.precision == 32 else 8
+    alg_bytes_per_step = (2 * K + 2) * bpe
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes_per_step * float(steps_per_run) * args.steps / (sweep_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": args.traffic, "kernel": "gibbs_sweeps_kernel", "peak_source": "MEASURED_PEAKS.json (measured copy)" if peaks else "fallback 6650",
+                "algorithmic_bytes_per_state_step": alg_bytes_per_step, "launches_timed": sweep_launches,
+                "avg_launch_ms": sweep_ms / max(1, sweep_launches),
+                "sweep_kernel_share_of_step": sweep_ms / dev_ms}
+
+    if rank == 0:
+        cb = None
+        if not args.no_cpu_baseline and world == 1:
+            cb, _, _ = cpu_baseline(y, ws_all, we_all)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic", "config": workload_config(args, world),
+                "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
+                        "ms_per_step": 1e3 * e2e_s / args.steps},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
+                "check": {"mu_mean_longest_window": res.summary_mean[int(np.argmax(we - ws))][0:3].tolist(), "events": int(res.events)}}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

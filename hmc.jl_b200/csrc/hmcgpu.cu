@@ -142,6 +142,10 @@ __global__ void filter_kernel(long long B, long long T, const double* __restrict
         const R m2 = em.eval((R)yb[t], e);
         bool ok;
         const R tot = forward_step<R, K>(a, e, pf, ok);
+        if (!ok) {
+#pragma unroll
+            for (int s = 0; s < K; ++s) pf[s] = R(1) / R(K);
+        }
         // natural-log normaliser of the unscaled recursion (what the reference's `total` is, :417/:430)
         const double lt = (sizeof(R) == 4) ? ((double)Real<float>::lg2((float)tot) + (double)m2) * 0.6931471805599453
                                            : log((double)tot);
@@ -442,6 +446,7 @@ extern "C" int hmcgpu_philox(hmcgpu_ctx* ctx, int64_t n, const uint32_t* ctr, co
 struct WinInit {          // per window, fp64
     double mean;          // ξ default and the shift c
     double cnt[8], Sd[8], Qd[8], trans[64];
+    double totS, totQ;    // sum over the window of (y-mean), (y-mean)^2
 };
 
 __device__ __forceinline__ unsigned long long orderable(double v) {
@@ -534,13 +539,18 @@ __global__ void __launch_bounds__(256) window_init_kernel(int K, const double* _
         for (int i = 0; i + 1 < N; ++i) c += (x0[i] == r && x0[i + 1] == s2) ? 1.0 : 0.0;
         out[w].trans[j] = c;
     }
-    if (tid == 0) out[w].mean = mean;
+    if (tid == 0) {
+        out[w].mean = mean;
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < N; ++i) { const double d = y[i * ld] - mean; a += d; b += d * d; }
+        out[w].totS = a; out[w].totQ = b;
+    }
 }
 
 template <typename R>
 __global__ void chain_init_kernel(int K, int n_slots, const int* __restrict__ slot_win, const WinInit* __restrict__ wi,
                                   const double* __restrict__ xi_user, int* cnt, int* trans, R* Sd, R* Qd, R* cshift, R* xi,
-                                  int* events) {
+                                  R* totS, R* totQ, int* events) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
     const int w = slot_win[slot];
@@ -553,6 +563,8 @@ __global__ void chain_init_kernel(int K, int n_slots, const int* __restrict__ sl
         for (int j = 0; j < K; ++j) trans[(i * K + j) * n_slots + slot] = w < 0 ? 0 : (int)wi[w].trans[i * K + j];
     }
     cshift[slot] = w < 0 ? R(0) : (R)wi[w].mean;
+    totS[slot] = w < 0 ? R(0) : (R)wi[w].totS;
+    totQ[slot] = w < 0 ? R(0) : (R)wi[w].totQ;
 }
 
 // y (fp64, series-major as the host gives it) -> time-major fp64 and R copies
@@ -659,7 +671,7 @@ struct hmcgpu_plan {
     GibbsArgs args{};
     // device buffers
     DevBuf y64, yr, wbase, wTd, wi, slot_win, slot_chain, T, ybase, warp_T, warp_pi_off, pi, pacc, cnt, trans, Sd, Qd,
-        events, cshift, xi, xi_user, chain_id, out, yfut_w, yfut, win_slot0, win_pib_off;
+        events, cshift, xi, xi_user, chain_id, out, yfut_w, yfut, win_slot0, win_pib_off, totS, totQ, task_counters;
     DevBuf d_mu, d_sig2, d_A, d_pie, d_fc, d_ll, d_sum, d_sumsq, d_pibsum;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     double gpu_ms = 0.0, sweep_ms = 0.0;
@@ -673,15 +685,30 @@ struct hmcgpu_plan {
     }
 };
 
+template <typename R, int K, bool WIDE>
+static cudaError_t launch_gibbs_w(const hmcgpu_plan* pl, const GibbsArgs& a, cudaStream_t st) {
+    const bool smooth = pl->flags & HMCGPU_FLAG_SMOOTHED_MEAN, ll = pl->flags & HMCGPU_FLAG_LOGLIK;
+    auto go = [&](auto kern) -> cudaError_t {
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGibbsThreads, 0);
+        if (e != cudaSuccess) return e;
+        // persistent warps pulling tasks: one resident wave, never more blocks than there are tasks
+        const long long want = ((long long)a.n_warps + (kGibbsThreads / 32) - 1) / (kGibbsThreads / 32);
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)per_sm * pl->ctx->sm_count));
+        kern<<<grid, kGibbsThreads, 0, st>>>(a);
+        return cudaGetLastError();
+    };
+    if (smooth && ll) return go(gibbs_sweeps_kernel<R, K, true, true, WIDE>);
+    if (smooth) return go(gibbs_sweeps_kernel<R, K, true, false, WIDE>);
+    if (ll) return go(gibbs_sweeps_kernel<R, K, false, true, WIDE>);
+    return go(gibbs_sweeps_kernel<R, K, false, false, WIDE>);
+}
+
 template <typename R, int K>
 static cudaError_t launch_gibbs(const hmcgpu_plan* pl, const GibbsArgs& a, cudaStream_t st) {
-    const unsigned grid = (unsigned)((a.n_slots + kGibbsThreads - 1) / kGibbsThreads);
-    const bool smooth = pl->flags & HMCGPU_FLAG_SMOOTHED_MEAN, ll = pl->flags & HMCGPU_FLAG_LOGLIK;
-    if (smooth && ll) gibbs_sweeps_kernel<R, K, true, true><<<grid, kGibbsThreads, 0, st>>>(a);
-    else if (smooth) gibbs_sweeps_kernel<R, K, true, false><<<grid, kGibbsThreads, 0, st>>>(a);
-    else if (ll) gibbs_sweeps_kernel<R, K, false, true><<<grid, kGibbsThreads, 0, st>>>(a);
-    else gibbs_sweeps_kernel<R, K, false, false><<<grid, kGibbsThreads, 0, st>>>(a);
-    return cudaGetLastError();
+    // packed transition counters: 32-bit rows hold fields of 32/K bits; longer windows use 64-bit rows
+    if ((long long)pl->max_T - 1 <= TransPack<K, false>::kMaxT) return launch_gibbs_w<R, K, false>(pl, a, st);
+    return launch_gibbs_w<R, K, true>(pl, a, st);
 }
 
 static int validate_problem(hmcgpu_ctx* ctx, const hmcgpu_problem* p) {
@@ -726,6 +753,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         pl->max_T = std::max(pl->max_T, pl->wT[w]);
     }
     pl->pib_total = pib_total;
+    if ((long long)pl->max_T - 1 > ((1ll << (64 / K)) - 1)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "window too long for K=%d", K);
     pl->state_steps = sumT * nc * (p->burnin + p->nrun);
     std::iota(pl->order.begin(), pl->order.end(), 0);
     std::stable_sort(pl->order.begin(), pl->order.end(), [&](int a, int b) { return pl->wT[a] > pl->wT[b]; });
@@ -814,6 +842,8 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     CU(ctx, pl->events.alloc((size_t)n_slots * sizeof(int)));
     CU(ctx, pl->cshift.alloc((size_t)n_slots * sizeof(R)));
     CU(ctx, pl->xi.alloc((size_t)K * n_slots * sizeof(R)));
+    CU(ctx, pl->totS.alloc((size_t)n_slots * sizeof(R)));
+    CU(ctx, pl->totQ.alloc((size_t)n_slots * sizeof(R)));
     CU(ctx, pl->out.alloc(per_draw * (size_t)chunk));
     CU(ctx, pl->yfut.alloc((size_t)std::max(1, p->n_h) * n_slots * sizeof(R)));
     const size_t Rr = (size_t)nc * p->nrun;
@@ -846,7 +876,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     a.n_slots = n_slots; a.T = pl->T.as<int>(); a.ybase = pl->ybase.as<long long>(); a.yld = nser; a.y = pl->yr.p;
     a.warp_T = pl->warp_T.as<int>(); a.warp_pi_off = pl->warp_pi_off.as<long long>(); a.pi = pl->pi.p; a.pib_acc = pl->pacc.p;
     a.cnt = pl->cnt.as<int>(); a.trans = pl->trans.as<int>(); a.Sd = pl->Sd.p; a.Qd = pl->Qd.p; a.events = pl->events.as<int>();
-    a.cshift = pl->cshift.p; a.xi = pl->xi.p;
+    a.cshift = pl->cshift.p; a.xi = pl->xi.p; a.totS = pl->totS.p; a.totQ = pl->totQ.p; a.n_warps = n_warps;
     for (int i = 0; i < 8; ++i) {
         a.alpha[i] = (p->alpha && i < K) ? p->alpha[i] : 1.0;      // :137
         a.nu[i] = (p->nu && i < K) ? p->nu[i] : 1.0;               // :140
@@ -873,15 +903,19 @@ static int plan_run_t(hmcgpu_plan* pl) {
     chain_init_kernel<R><<<grid_for(ns, 128), 128, 0, st>>>(K, ns, pl->slot_win.as<int>(), pl->wi.as<WinInit>(),
                                                             pl->xi_user.as<double>(), pl->cnt.as<int>(), pl->trans.as<int>(),
                                                             pl->Sd.as<R>(), pl->Qd.as<R>(), pl->cshift.as<R>(), pl->xi.as<R>(),
-                                                            pl->events.as<int>());
+                                                            pl->totS.as<R>(), pl->totQ.as<R>(), pl->events.as<int>());
     CU(ctx, cudaGetLastError());
     ++pl->n_launches;
     if (pl->d_sum.p) { CU(ctx, cudaMemsetAsync(pl->d_sum.p, 0, pl->d_sum.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_sumsq.p, 0, pl->d_sumsq.bytes, st)); }
     if (pl->pacc.p) { CU(ctx, cudaMemsetAsync(pl->pacc.p, 0, pl->pacc.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_pibsum.p, 0, pl->d_pibsum.bytes, st)); }
     GibbsArgs a = pl->args;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+    const long long n_sweep_launches = (pl->burnin + 1023) / 1024 + (pl->nrun + pl->chunk - 1) / pl->chunk;
+    if (pl->task_counters.bytes < (size_t)n_sweep_launches * sizeof(int)) CU(ctx, pl->task_counters.alloc((size_t)n_sweep_launches * sizeof(int)));
+    CU(ctx, cudaMemsetAsync(pl->task_counters.p, 0, pl->task_counters.bytes, st));
     auto sweep_launch = [&](long long sweep0, int n, long long draw0) -> int {
         a.sweep0 = sweep0; a.n_sweeps = n; a.draw0 = draw0;
+        a.task_counter = pl->task_counters.as<int>() + pl->n_sweep_launches;
         cudaEvent_t e0, e1;
         CU(ctx, cudaEventCreate(&e0)); CU(ctx, cudaEventCreate(&e1));
         evs.emplace_back(e0, e1);

@@ -71,19 +71,20 @@ template <int K> struct Emission<double, K> {
 template <typename R, int K>
 __device__ __forceinline__ R forward_step(const R (&A)[K][K], const R (&e)[K], R (&pi)[K], bool& ok) {
     R q[K];
-    R tot = R(0);
 #pragma unroll
     for (int s = 0; s < K; ++s) {
         R pred = pi[0] * A[0][s];
 #pragma unroll
         for (int r = 1; r < K; ++r) pred = fma(pi[r], A[r][s], pred);
         q[s] = pred * e[s];
-        tot += q[s];
     }
-    ok = (tot > R(0)) && (tot < R(3.0e38));
-    const R inv = ok ? Real<R>::rcp(tot) : R(0);
+    R tot = q[0];
 #pragma unroll
-    for (int s = 0; s < K; ++s) pi[s] = ok ? q[s] * inv : R(1) / R(K);
+    for (int s = 1; s < K; ++s) tot += q[s];
+    ok = (tot > R(0)) && (tot < R(3.0e38));
+    const R inv = Real<R>::rcp(tot);
+#pragma unroll
+    for (int s = 0; s < K; ++s) pi[s] = q[s] * inv;
     return tot;
 }
 

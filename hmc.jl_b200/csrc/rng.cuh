@@ -33,10 +33,11 @@ __device__ __forceinline__ uint4 rng_block(const RngKey& k, uint32_t sweep, uint
     return philox4x32_10(block, purpose, sweep, k.chain, k.k0, k.k1);
 }
 
-// uniform in (0,1): fp64 keeps all 32 bits, fp32 the top 24 (both exact in their type)
+// uniform in (0,1): fp64 = (w + 0.5) * 2^-32 exactly
 template <typename R> __device__ __forceinline__ R u01(uint32_t w);
 template <> __device__ __forceinline__ double u01<double>(uint32_t w) { return ((double)w + 0.5) * 2.3283064365386963e-10; }
-template <> __device__ __forceinline__ float u01<float>(uint32_t w) { return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-8f; }
+// fp32: the word rounded toward zero to 24 significant bits (one I2FP), offset by 2^-33 so that u > 0; u < 1 always
+template <> __device__ __forceinline__ float u01<float>(uint32_t w) { return fmaf(__uint2float_rz(w), 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
 
 template <typename R> struct M;
 template <> struct M<double> {
@@ -60,7 +61,7 @@ template <typename R> __device__ __forceinline__ R normal_from(uint32_t w0, uint
 
 // Marsaglia & Tsang gamma(shape, 1); attempt k = block k of the draw's own purpose stream:
 // words 0,1 -> normal, word 2 -> acceptance uniform, word 3 -> boost uniform (shape < 1).
-template <typename R> __device__ R gamma_mt(R shape, const RngKey& key, uint32_t sweep, uint32_t purpose) {
+template <typename R> __device__ __noinline__ R gamma_mt(R shape, const RngKey key, uint32_t sweep, uint32_t purpose) {
     const R a = shape < R(1) ? shape + R(1) : shape;
     const R d = a - R(1) / R(3), c = R(1) / M<R>::sqrt(R(9) * d);
     R g = d;

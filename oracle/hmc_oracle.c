@@ -396,11 +396,12 @@ int orc_gibbs(const orc_problem* p, orc_result* res) {
             for (int k = 0; k < K; ++k) tmpv[k] = row[order[k]];
             memcpy(row, tmpv, sizeof(double) * (size_t)K);
         }
-        /* --- update_X! (:514): one uniform per t from the STATES stream; time t uses word t&3 of block t>>2 */
-        for (int t = 0; t < N; t += 4) {
+        /* --- update_X! (:514): one uniform per t from the STATES stream, indexed in consumption order:
+         *     the i-th uniform drawn (i = 0 for X[N], i = N-1-t for X[t]) is word i&3 of block i>>2 */
+        for (int i = 0; i < N; i += 4) {
             uint32_t w[4];
-            orc_block(p->seed, p->chain, sweep, (ORC_KIND_STATES << 16), (uint32_t)(t >> 2), w);
-            for (int j = 0; j < 4 && t + j < N; ++j) u[t + j] = orc_u01(w[j]);
+            orc_block(p->seed, p->chain, sweep, (ORC_KIND_STATES << 16), (uint32_t)(i >> 2), w);
+            for (int j = 0; j < 4 && i + j < N; ++j) u[N - 1 - (i + j)] = orc_u01(w[j]);
         }
         /* chain-label A for the pif form (Atmp is the un-permuted matrix) */
         orc_sample_states(N, K, Pf, pif, Atmp, piN, u, (p->flags & ORC_FLAG_PIF_FORM) ? 1 : 0, X);
