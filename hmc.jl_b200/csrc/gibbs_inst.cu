@@ -1,0 +1,46 @@
+// gibbs_inst.cu — one explicit instantiation of the Gibbs sweep kernel family per translation unit:
+// compiled with -DHMC_R=<float|double> -DHMC_K=<2|3|4> (hmc.jl_b200/build.py builds the six units in parallel).
+#include <algorithm>
+#include "gibbs_kernel.cuh"
+
+namespace hmc {
+
+// calls f(kernel) with the variant the flags / window length select
+template <typename R, int K, bool WIDE, typename F> static auto with_variant(const GibbsLaunch& cfg, F f) {
+    const bool smooth = cfg.flags & 8u /*HMCGPU_FLAG_SMOOTHED_MEAN*/, ll = cfg.flags & 16u /*HMCGPU_FLAG_LOGLIK*/;
+    if (smooth && ll) return f(gibbs_sweeps_kernel<R, K, true, true, WIDE>);
+    if (smooth) return f(gibbs_sweeps_kernel<R, K, true, false, WIDE>);
+    if (ll) return f(gibbs_sweeps_kernel<R, K, false, true, WIDE>);
+    return f(gibbs_sweeps_kernel<R, K, false, false, WIDE>);
+}
+// packed transition counters: 32-bit rows hold fields of 32/K bits; longer windows use 64-bit rows
+template <int K> static bool wide_rows(const GibbsLaunch& cfg) { return (long long)cfg.max_T - 1 > TransPack<K, false>::kMaxT; }
+
+template <typename R, int K> cudaError_t launch_gibbs(const GibbsLaunch& cfg, const GibbsArgs& a, cudaStream_t st) {
+    const unsigned grid = (unsigned)((a.n_tasks + kGibbsThreads / 32 - 1) / (kGibbsThreads / 32));
+    auto go = [&](auto kern, size_t smem) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, kGibbsThreads, smem, st>>>(a);
+        return cudaGetLastError();
+    };
+    if (wide_rows<K>(cfg)) return with_variant<R, K, true>(cfg, [&](auto kern) { return go(kern, kGibbsSmemBytes<R, K, true>()); });
+    return with_variant<R, K, false>(cfg, [&](auto kern) { return go(kern, kGibbsSmemBytes<R, K, false>()); });
+}
+
+template <typename R, int K> int gibbs_capacity_warps(const GibbsLaunch& cfg) {
+    auto q = [&](auto kern, size_t smem) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGibbsThreads, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
+        return per_sm * cfg.sm_count * (kGibbsThreads / 32);
+    };
+    if (wide_rows<K>(cfg)) return with_variant<R, K, true>(cfg, [&](auto kern) { return q(kern, kGibbsSmemBytes<R, K, true>()); });
+    return with_variant<R, K, false>(cfg, [&](auto kern) { return q(kern, kGibbsSmemBytes<R, K, false>()); });
+}
+
+template cudaError_t launch_gibbs<HMC_R, HMC_K>(const GibbsLaunch&, const GibbsArgs&, cudaStream_t);
+template int gibbs_capacity_warps<HMC_R, HMC_K>(const GibbsLaunch&);
+
+}  // namespace hmc

@@ -5,9 +5,11 @@
 //   optional backward smoother accumulation.
 //
 // Mapping.  A warp = 32 chains in lockstep ("warp task"); lanes of a warp share one contiguous pif tile so every
-// global access is a full 128-byte (fp32) / 256-byte (fp64) line.  Warp tasks are sorted by window length
-// (longest first) and handed out dynamically through one atomic counter per launch, so the 148 SMs stay balanced
-// although T_w varies 6x across the expanding windows.  Windows inside a warp are right-aligned in time: loop row j
+// global access is a full 128-byte (fp32) / 256-byte (fp64) line.  The cost of a warp task is its window length, which
+// varies 6x across the expanding windows, and the SM warp arbiter is priority-based (starved warps finish late), so
+// balance comes from the launch structure (hmcgpu.cu): tasks are sorted longest-first, split into interleaved groups,
+// and each group runs short launches (a few sweeps) on its own stream — while one group's launch drains, the block
+// scheduler backfills the freed SM slots with the pending blocks of the other groups' launches.  Windows inside a warp are right-aligned in time: loop row j
 // holds t = j - (T_warp - T_lane), which keeps the first backward step and every Philox block warp-uniform.
 #pragma once
 #include <type_traits>
@@ -15,13 +17,47 @@
 
 namespace hmc {
 
+// experiment knobs (defaults = the measured best; see profiles/ for the A/B runs)
+#ifndef HMC_SEL_LDS
+#define HMC_SEL_LDS 1      // 1: A[:,x] and the counter increment come from a per-thread shared-memory table; 0: register selects
+#endif
+
+#ifndef HMC_ASYNC
+#define HMC_ASYNC 1        // 1: backward rows are staged through a per-warp shared-memory ring with cp.async (LDGSTS)
+#endif
+#ifndef HMC_RING_STAGES
+#define HMC_RING_STAGES 4  // groups of 4 rows in flight per warp
+#endif
+
 constexpr int kMaxH = 16;
+constexpr int kRing = HMC_RING_STAGES;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// The passes are out-of-line functions, where pointers arriving through their by-value arguments would be generic
+// (LD.E/ST.E).  Shared memory is therefore always re-derived from the kernel's dynamic shared array, and global memory
+// goes through the explicit-space intrinsics below (LDG/STG in SASS).
+__device__ __forceinline__ unsigned char* smem_base() {
+    extern __shared__ __align__(16) unsigned char hmc_smem[];
+    return hmc_smem;
+}
+template <typename T> __device__ __forceinline__ T ld_stream(const T* p) { return __ldcg(p); }     // pif rows: L2 only
+template <typename T> __device__ __forceinline__ T ld_ro(const T* p) { return __ldg(p); }          // y: read-only, L1
+template <typename T> __device__ __forceinline__ void st_stream(T* p, T v) { __stcg(p, v); }
 constexpr int kGibbsThreads = 128;
+#ifndef HMC_MINBLOCKS
+#define HMC_MINBLOCKS 5
+#endif
+constexpr int kGibbsMinBlocks = HMC_MINBLOCKS;   // 5 blocks x 128 threads per SM -> register cap 102, 20 resident warps
 
 struct GibbsArgs {
     int n_slots;                 // chains incl. padding, multiple of 32
     int n_warps;                 // warp tasks = n_slots/32
-    int* task_counter;           // zeroed before the launch
+    // this launch covers the warp tasks task0, task0 + task_stride, ... (n_tasks of them): one task group
+    int task0, task_stride, n_tasks;
     const int* T;                // [n_slots] window length (0 = padding lane)
     const long long* ybase;      // [n_slots] element offset of the window's first observation in y
     int yld;                     // stride between consecutive time steps in y (= n_series, time-major)
@@ -80,22 +116,31 @@ struct GibbsWarp {
     using Pack = TransPack<K, WIDE>;
     using Row = typename Pack::Row;
 
+    // What the backward step needs once X_{t+1} = x is known, fetched with one (fp32, K<=3) vector load from shared
+    // memory instead of K+1 register selects: column x of A and the packed-counter increment of destination x.
+    struct alignas(16) Entry {
+        R a[K];
+        Row inc;
+    };
+
     // per-sweep constants of one chain
     struct Chain {
         R A[K][K];
         R c;                      // shift of the sufficient statistics
         int rank[K];              // position of each chain label in increasing-mu order
         int T, Tw, off;           // window length, warp length, right-alignment offset (row j <-> t = j - off)
+        bool ragged;              // some lane of the warp has a shorter window (or is padding): steps are guarded
         long long yld;
         const R* y0;              // row j -> y0[j*yld]
         R* pi0;                   // row j, state k -> pi0[(j*K + k)*32]
         R* pacc0;
+        unsigned tab_off;         // shared memory (bytes): tab[x*kGibbsThreads] = {A[:,x], 1 << (kBits*x)} of this thread's chain
+        unsigned ring_off;        // shared memory (bytes): this warp's ring of kRing groups x 4 rows x K x 32 lanes (HMC_ASYNC)
     };
 
     // state carried by the backward pass; the sampled state of the later time step is kept one-hot in (lt[])
     struct Back {
         R Sd[K - 1], Qd[K - 1];   // statistics of states 0..K-2 (the last one follows from the window totals)
-        int n[K - 1];
         Pack tr;
         Row inc;                  // Row(1) << (kBits * x_{t+1})
         R Acol[K];                // A[:, x_{t+1}]
@@ -136,39 +181,50 @@ struct GibbsWarp {
         const R d = yt - ch.c, dd = d * d;
 #pragma unroll
         for (int i = 0; i < K - 1; ++i)
-            if (is_state(lt, i)) { b.Sd[i] += d; b.Qd[i] += dd; b.n[i] += 1; }
+            if (is_state(lt, i)) { b.Sd[i] += d; b.Qd[i] += dd; }
+#if HMC_SEL_LDS
+        const Entry* e = reinterpret_cast<const Entry*>(smem_base() + ch.tab_off);
+#pragma unroll
+        for (int i = 1; i < K; ++i) if (lt[i - 1]) e += kGibbsThreads;
+        const Entry en = *e;
+        b.inc = en.inc;
+#pragma unroll
+        for (int r = 0; r < K; ++r) b.Acol[r] = en.a[r];
+#else
         Row incs[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) incs[i] = (Row)1 << (Pack::kBits * i);
         b.inc = pick<Row>(lt, incs);
-        b.gate = pick<R>(lt, pt);
 #pragma unroll
         for (int r = 0; r < K; ++r) b.Acol[r] = pick<R>(lt, ch.A[r]);
+#endif
+        b.gate = pick<R>(lt, pt);
     }
 
-    // one backward step at loop row j: draw X_t | X_{t+1} (src/Hmc.jl:466-481 in the pif form), update the statistics
-    static __device__ __forceinline__ void back_step(Back& b, const Chain& ch, const R* __restrict__ pip, R* __restrict__ pap,
-                                                      const R* __restrict__ yp, uint32_t word, bool save) {
-        R pt[K];
-#pragma unroll
-        for (int s = 0; s < K; ++s) pt[s] = pip[s * 32];
-        const R yt = *yp;
+    // one backward step at loop row j: draw X_t | X_{t+1} (src/Hmc.jl:466-481 in the pif form), update the statistics.
+    // Quirk Q5 (:472-480: p = 1/D when total = pif[t+1, x_{t+1}] <= eps()) practically never fires.  GATED = handle it
+    // in place; otherwise only record it in `bad` and let the caller redo the pass gated (counter-based RNG: same draws).
+    template <bool GATED>
+    static __device__ __forceinline__ void back_step(Back& b, const Chain& ch, const R (&pt)[K], R* __restrict__ pap,
+                                                      R yt, uint32_t word, bool save, bool& bad) {
         R p[K];
 #pragma unroll
         for (int r = 0; r < K; ++r) p[r] = pt[r] * b.Acol[r];
-        const R u = u01<R>(word);
-        bool lt[K - 1];
-        draw(p, u, lt);
-        if (__builtin_expect(!(b.gate > Real<R>::eps()), 0)) {   // reference: uniform p when total <= eps() (:472-480)
+        if (GATED) {
+            if (!(b.gate > Real<R>::eps())) {
 #pragma unroll
-            for (int r = 0; r < K; ++r) p[r] = R(1);
-            draw(p, u, lt);
+                for (int r = 0; r < K; ++r) p[r] = R(1);
+            }
+        } else {
+            bad = bad || !(b.gate > Real<R>::eps());
         }
+        bool lt[K - 1];
+        draw(p, u01<R>(word), lt);
         if (SMOOTH) {
             smooth_step<R, K>(ch.A, pt, b.pb);
             if (save) {
 #pragma unroll
-                for (int s = 0; s < K; ++s) pap[ch.rank[s] * 32] += b.pb[s];
+                for (int s = 0; s < K; ++s) st_stream(pap + ch.rank[s] * 32, ld_stream(pap + ch.rank[s] * 32) + b.pb[s]);
             }
         }
         commit(b, ch, lt, pt, yt, false);
@@ -177,8 +233,18 @@ struct GibbsWarp {
     // forward filter (forwardupdate_P! :371-440); pif rows stored for the backward pass.  CHECKED = per-step handling
     // of a zero / non-finite normaliser (the reference only warns, :435); the hot path runs unchecked and is re-run
     // checked when the final row is not finite (a NaN, once produced, propagates to the last row).
+    // The two passes are separate out-of-line functions (arguments and results by value): each gets its own register
+    // allocation, and the per-sweep state of the caller is saved around the call instead of squeezing the hot loops.
+    struct Vec { R v[K]; };
+    struct FwdOut { Vec pf; R ll; int events; };
     template <bool RAGGED, bool CHECKED>
-    static __device__ __forceinline__ int forward(const Chain& ch, const Emission<R, K>& em, const R (&rho)[K], R (&pf)[K], R& ll) {
+    static __device__ __noinline__ FwdOut forward_pass(const Chain ch, const Emission<R, K> em, const Vec rho_in) {
+        FwdOut o;
+        R (&pf)[K] = o.pf.v;
+        R& ll = o.ll;
+        const R (&rho)[K] = rho_in.v;
+        const long long yld = ch.yld;
+        constexpr bool ragged = RAGGED;
         int events = 0;
 #pragma unroll
         for (int s = 0; s < K; ++s) pf[s] = rho[s];                  // t = 1 uses ρ (:390)
@@ -186,8 +252,8 @@ struct GibbsWarp {
         const R* yp = ch.y0;
         R* pip = ch.pi0;
         auto step = [&](int j, int u) {
-            if (!RAGGED || j >= ch.off) {
-                const R yt = yp[u * ch.yld];
+            if (!ragged || j >= ch.off) {
+                const R yt = ld_ro(yp + u * yld);
                 R e[K];
                 const R m2 = em.eval(yt, e);
                 bool ok;
@@ -202,26 +268,37 @@ struct GibbsWarp {
                     else ll += (R)log((double)tot);
                 }
 #pragma unroll
-                for (int s = 0; s < K; ++s) pip[(u * K + s) * 32] = pf[s];
+                for (int s = 0; s < K; ++s) st_stream(pip + (u * K + s) * 32, pf[s]);
             }
         };
         int j = 0;
-        for (; j + 3 < ch.Tw; j += 4, yp += 4 * ch.yld, pip += 4 * K * 32) { step(j, 0); step(j + 1, 1); step(j + 2, 2); step(j + 3, 3); }
-        for (; j < ch.Tw; ++j, yp += ch.yld, pip += K * 32) step(j, 0);
-        return events;
+        for (; j + 3 < ch.Tw; j += 4, yp += 4 * yld, pip += 4 * K * 32) { step(j, 0); step(j + 1, 1); step(j + 2, 2); step(j + 3, 3); }
+        for (; j < ch.Tw; ++j, yp += yld, pip += K * 32) step(j, 0);
+        o.events = events;
+        return o;
     }
-    static __device__ __noinline__ int forward_checked(const Chain& ch, const Emission<R, K>& em, const R (&rho)[K], R (&pf)[K], R& ll) {
-        return forward<true, true>(ch, em, rho, pf, ll);
-    }
-
     // backward state sampling (update_X! :459-484) fused with the next sweep's statistics (update_μσ! :254-258/:291-294,
     // update_A! :362-365) and, optionally, backwardupdate_P! (:442-457).
     // The i-th uniform consumed (i = 0 for X[N]) is word i&3 of Philox block i>>2 of this sweep.
-    template <bool RAGGED>
-    static __device__ __forceinline__ void backward(Back& b, const Chain& ch, const R (&pf)[K], const RngKey& key, uint32_t sweep,
-                                                    unsigned flags, bool save) {
+    struct BackOut { Back b; int xN; bool bad; };
+    template <bool RAGGED, bool GATED>
+    static __device__ __noinline__ BackOut backward_pass(const Chain ch, const Vec pf_in, const RngKey key, const uint32_t sweep,
+                                                         const unsigned flags, const bool save) {
+        BackOut o;
+        Back& b = o.b;
+        const R (&pf)[K] = pf_in.v;
+        bool bad = false;
+        int xN = 0;
         const int Tw = ch.Tw, T = ch.T;
-        const R* yp = ch.y0 + (long long)(Tw - 1) * ch.yld;
+        const long long ys = ch.yld;
+        constexpr bool ragged = RAGGED;
+#pragma unroll
+        for (int i = 0; i < K - 1; ++i) { b.Sd[i] = R(0); b.Qd[i] = R(0); }
+        b.tr.clear();
+        b.inc = 0; b.gate = R(1);
+#pragma unroll
+        for (int s = 0; s < K; ++s) { b.Acol[s] = R(0); b.pb[s] = R(0); }
+        const R* yp = ch.y0 + (long long)(Tw - 1) * ys;
         const R* pip = ch.pi0 + (size_t)(Tw - 1) * K * 32;
         R* pap = SMOOTH ? ch.pacc0 + (size_t)(Tw - 1) * K * 32 : nullptr;
         uint4 w = rng_block(key, sweep, (KIND_STATES << 16), 0u);
@@ -242,39 +319,107 @@ struct GibbsWarp {
             }
             bool lt[K - 1];
             draw(pN, u01<R>(w.x), lt);
+#pragma unroll
+            for (int i = 0; i < K - 1; ++i) xN += lt[i] ? 1 : 0;
             if (SMOOTH) {
 #pragma unroll
                 for (int s = 0; s < K; ++s) b.pb[s] = pf[s];           // pib[N,:] = pif[N,:]
                 if (save) {
 #pragma unroll
-                    for (int s = 0; s < K; ++s) pap[ch.rank[s] * 32] += pf[s];
+                    for (int s = 0; s < K; ++s) st_stream(pap + ch.rank[s] * 32, ld_stream(pap + ch.rank[s] * 32) + pf[s]);
                 }
             }
-            commit(b, ch, lt, pf, *yp, true);
+            commit(b, ch, lt, pf, ld_ro(yp), true);
         }
         int i = 1;
-        const long long ys = ch.yld;
-#define HMC_BACK(word)                                                                   \
-    yp -= ys; pip -= K * 32; if (SMOOTH) pap -= K * 32;                                  \
-    if (!RAGGED || i < T) back_step(b, ch, pip, pap, yp, (word), save);                  \
-    ++i;
-        if (Tw > 1) { HMC_BACK(w.y) }
-        if (Tw > 2) { HMC_BACK(w.z) }
-        if (Tw > 3) { HMC_BACK(w.w) }
-        for (; i + 3 < Tw;) {
-            w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
-            HMC_BACK(w.x) HMC_BACK(w.y) HMC_BACK(w.z) HMC_BACK(w.w)
+        // one step; u = position inside the current group of 4 (pointers move once per group).  The filtered rows and
+        // observations of a group are loaded into registers one whole group ahead (they do not depend on the sampled
+        // states), so the HBM/L2 latency of group g+1 hides behind the dependent chain of group g.
+        auto load_row = [&](int u, R (&pt)[K], R& yt) {
+#pragma unroll
+            for (int s = 0; s < K; ++s) pt[s] = ld_stream(pip + (s - (u + 1) * K) * 32);
+            yt = (!ragged || i + u < T) ? ld_ro(yp - (u + 1) * ys) : R(0);
+        };
+#define HMC_BACK(u, word, PT, YT)                                                                                      \
+    if (!ragged || i + (u) < T) back_step<GATED>(b, ch, PT, SMOOTH ? pap - ((u) + 1) * K * 32 : nullptr, YT, (word), save, bad);
+        {
+            R p0[K], p1[K], p2[K], y0, y1, y2;
+            if (Tw > 1) load_row(0, p0, y0);
+            if (Tw > 2) load_row(1, p1, y1);
+            if (Tw > 3) load_row(2, p2, y2);
+            if (Tw > 1) { HMC_BACK(0, w.y, p0, y0) }
+            if (Tw > 2) { HMC_BACK(1, w.z, p1, y1) }
+            if (Tw > 3) { HMC_BACK(2, w.w, p2, y2) }
+            const int done = Tw > 3 ? 3 : Tw - 1;
+            i += done; yp -= done * ys; pip -= (size_t)done * K * 32; if (SMOOTH) pap -= (size_t)done * K * 32;
         }
+#if HMC_ASYNC
+        {
+            // Groups of 4 rows are contiguous in the warp's tile (4*K*32 elements).  They are copied global -> shared
+            // kRing-1 groups ahead with 16-byte cp.async (every lane moves K*sizeof(R)/4 chunks per group), so the HBM/L2
+            // latency never sits in the dependent chain of the sampler; the rows are then read back with conflict-free LDS.
+            constexpr int kGroupElems = 4 * K * 32;
+            constexpr int kChunksPerLane = (int)(kGroupElems * sizeof(R) / 16 / 32);
+            const int lane = threadIdx.x & 31;
+            R* const ring = reinterpret_cast<R*>(smem_base() + ch.ring_off);
+            const int n_groups = (Tw - i) / 4;                          // full groups (i == 4 here when there are any)
+            // group g (0-based) holds rows [jlo, jlo+3], jlo = Tw - 8 - 4g  (the rows of steps i = 4+4g .. 7+4g, highest first)
+            const R* gsrc = ch.pi0 - lane + (long long)(Tw - 8) * K * 32;   // row block of group 0, lane 0
+            auto issue = [&](int g) {
+                if (g < n_groups) {
+                    const char* src = reinterpret_cast<const char*>(gsrc - (long long)g * kGroupElems);
+                    char* dst = reinterpret_cast<char*>(ring + (g % kRing) * kGroupElems);
+#pragma unroll
+                    for (int m = 0; m < kChunksPerLane; ++m) cp_async16(dst + (lane + 32 * m) * 16, src + (lane + 32 * m) * 16);
+                }
+                cp_async_commit();                                       // (possibly empty) keeps the group count uniform
+            };
+#pragma unroll
+            for (int g = 0; g < kRing - 1; ++g) issue(g);
+            for (int g = 0; g < n_groups; ++g, i += 4, yp -= 4 * ys, pip -= 4 * K * 32, pap -= SMOOTH ? 4 * K * 32 : 0) {
+                issue(g + kRing - 1);                                    // overwrites the stage consumed in iteration g-1
+                cp_async_wait<kRing - 1>();                              // group g has landed (for this lane's chunks)
+                __syncwarp();                                            // ... and for every other lane's
+                const R* st = ring + (g % kRing) * kGroupElems + lane;
+                R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3;
+#pragma unroll
+                for (int s = 0; s < K; ++s) {
+                    c0[s] = st[(3 * K + s) * 32]; c1[s] = st[(2 * K + s) * 32]; c2[s] = st[(1 * K + s) * 32]; c3[s] = st[s * 32];
+                }
+                y0 = (!ragged || i + 0 < T) ? ld_ro(yp - 1 * ys) : R(0);
+                y1 = (!ragged || i + 1 < T) ? ld_ro(yp - 2 * ys) : R(0);
+                y2 = (!ragged || i + 2 < T) ? ld_ro(yp - 3 * ys) : R(0);
+                y3 = (!ragged || i + 3 < T) ? ld_ro(yp - 4 * ys) : R(0);
+                w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
+                HMC_BACK(0, w.x, c0, y0) HMC_BACK(1, w.y, c1, y1) HMC_BACK(2, w.z, c2, y2) HMC_BACK(3, w.w, c3, y3)
+                __syncwarp();                                            // all lanes are done with this stage
+            }
+            cp_async_wait<0>();
+        }
+#else
+        for (; i + 3 < Tw; i += 4, yp -= 4 * ys, pip -= 4 * K * 32, pap -= SMOOTH ? 4 * K * 32 : 0) {
+            R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3;
+            load_row(0, c0, y0); load_row(1, c1, y1); load_row(2, c2, y2); load_row(3, c3, y3);
+            w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
+            HMC_BACK(0, w.x, c0, y0) HMC_BACK(1, w.y, c1, y1) HMC_BACK(2, w.z, c2, y2) HMC_BACK(3, w.w, c3, y3)
+        }
+#endif
         if (i < Tw) {
             w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
-            HMC_BACK(w.x)
-            if (i < Tw) { HMC_BACK(w.y) }
-            if (i < Tw) { HMC_BACK(w.z) }
+            R p0[K], p1[K], p2[K], y0 = R(0), y1 = R(0), y2 = R(0);
+            load_row(0, p0, y0);
+            if (i + 1 < Tw) load_row(1, p1, y1);
+            if (i + 2 < Tw) load_row(2, p2, y2);
+            HMC_BACK(0, w.x, p0, y0)
+            if (i + 1 < Tw) { HMC_BACK(1, w.y, p1, y1) }
+            if (i + 2 < Tw) { HMC_BACK(2, w.z, p2, y2) }
         }
 #undef HMC_BACK
+        o.xN = xN;
+        o.bad = bad;
+        return o;
     }
-
-    static __device__ void run(const GibbsArgs& a, const int warp, const int lane) {
+    static __device__ void run(const GibbsArgs& a, const int warp, const int lane, Entry* smem_tab) {
         const int slot = warp * 32 + lane;
         const int ns = a.n_slots;
         Chain ch;
@@ -286,9 +431,11 @@ struct GibbsWarp {
         ch.pacc0 = SMOOTH ? reinterpret_cast<R*>(a.pib_acc) + a.warp_pi_off[warp] + lane : nullptr;
         ch.y0 = reinterpret_cast<const R*>(a.y) + a.ybase[slot] - (long long)ch.off * ch.yld;
         ch.c = reinterpret_cast<const R*>(a.cshift)[slot];
+        ch.tab_off = (unsigned)(threadIdx.x * sizeof(Entry));
+        ch.ring_off = (unsigned)(sizeof(Entry) * K * kGibbsThreads + sizeof(R) * (threadIdx.x >> 5) * (kRing * 4 * K * 32));
         const int T = ch.T;
         // padding lanes (T = 0) only exist in the last warp, which therefore counts as ragged
-        const bool ragged = __any_sync(0xffffffffu, ch.off != 0);
+        ch.ragged = __any_sync(0xffffffffu, ch.off != 0);
         const R totS = reinterpret_cast<const R*>(a.totS)[slot], totQ = reinterpret_cast<const R*>(a.totQ)[slot];
         const RngKey key{a.k0, a.k1, a.chain_id[slot]};
         R* __restrict__ const out = reinterpret_cast<R*>(a.out);
@@ -322,13 +469,20 @@ struct GibbsWarp {
             Emission<R, K> em;
             em.prepare(mu, sig2);
             R pf[K], ll;
-            if (ragged) forward<true, false>(ch, em, rho, pf, ll);
-            else forward<false, false>(ch, em, rho, pf, ll);
             {
-                R chk = pf[0];
+                Vec rv;
 #pragma unroll
-                for (int s = 1; s < K; ++s) chk += pf[s];
-                if (__builtin_expect(T > 0 && !(chk > R(0.5) && chk < R(2)), 0)) events += forward_checked(ch, em, rho, pf, ll);
+                for (int s = 0; s < K; ++s) rv.v[s] = rho[s];
+                FwdOut fo = ch.ragged ? forward_pass<true, false>(ch, em, rv) : forward_pass<false, false>(ch, em, rv);
+                R chk = fo.pf.v[0];
+#pragma unroll
+                for (int s = 1; s < K; ++s) chk += fo.pf.v[s];
+                // a zero / non-finite normaliser anywhere leaves a NaN in the last row: redo the pass with per-step handling
+                if (__builtin_expect(T > 0 && !(chk > R(0.5) && chk < R(2)), 0)) fo = forward_pass<true, true>(ch, em, rv);
+#pragma unroll
+                for (int s = 0; s < K; ++s) pf[s] = fo.pf.v[s];
+                ll = fo.ll;
+                events += fo.events;
             }
             // pf now holds pif[T,:] in chain labels
 
@@ -380,13 +534,30 @@ struct GibbsWarp {
             // ---- 4. backward pass
             Back b;
 #pragma unroll
-            for (int i = 0; i < K - 1; ++i) { b.Sd[i] = R(0); b.Qd[i] = R(0); b.n[i] = 0; }
-            b.tr.clear();
-            b.inc = 0; b.gate = R(1);
+            for (int x = 0; x < K; ++x) {                           // this thread's private selection table
+                Entry en;
 #pragma unroll
-            for (int s = 0; s < K; ++s) { b.Acol[s] = R(0); b.pb[s] = R(0); }
-            if (ragged) backward<true>(b, ch, pf, key, sweep, a.flags, save);
-            else backward<false>(b, ch, pf, key, sweep, a.flags, save);
+                for (int r = 0; r < K; ++r) en.a[r] = ch.A[r][x];
+                en.inc = (Row)1 << (Pack::kBits * x);
+                smem_tab[x * kGibbsThreads + threadIdx.x] = en;
+            }
+            int xN;
+            {
+                Vec pv;
+#pragma unroll
+                for (int s = 0; s < K; ++s) pv.v[s] = pf[s];
+                BackOut bo;
+                if (SMOOTH) {                                        // accumulates into memory: run gated in place
+                    bo = backward_pass<true, true>(ch, pv, key, sweep, a.flags, save);
+                } else {
+                    bo = ch.ragged ? backward_pass<true, false>(ch, pv, key, sweep, a.flags, save)
+                                   : backward_pass<false, false>(ch, pv, key, sweep, a.flags, save);
+                    // quirk Q5 fired somewhere: redo the pass exactly (counter-based RNG: identical draws otherwise)
+                    if (__builtin_expect(bo.bad, 0)) bo = backward_pass<true, true>(ch, pv, key, sweep, a.flags, save);
+                }
+                b = bo.b;
+                xN = bo.xN;
+            }
 
             // ---- unpack the statistics for the next sweep's draws
 #pragma unroll
@@ -394,11 +565,18 @@ struct GibbsWarp {
 #pragma unroll
                 for (int j = 0; j < K; ++j) trans[i][j] = b.tr.get(i, j);
             {
+                // occupation counts from the transition counts: n_i = sum_j n_ij + [X_N = i]
                 R sS = R(0), sQ = R(0);
-                int sn = 0;
 #pragma unroll
-                for (int i = 0; i < K - 1; ++i) { Sd[i] = b.Sd[i]; Qd[i] = b.Qd[i]; cnt[i] = b.n[i]; sS += b.Sd[i]; sQ += b.Qd[i]; sn += b.n[i]; }
-                Sd[K - 1] = totS - sS; Qd[K - 1] = totQ - sQ; cnt[K - 1] = T - sn;
+                for (int i = 0; i < K; ++i) {
+                    int n = (T > 0 && xN == i) ? 1 : 0;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) n += trans[i][j];
+                    cnt[i] = n;
+                }
+#pragma unroll
+                for (int i = 0; i < K - 1; ++i) { Sd[i] = b.Sd[i]; Qd[i] = b.Qd[i]; sS += b.Sd[i]; sQ += b.Qd[i]; }
+                Sd[K - 1] = totS - sS; Qd[K - 1] = totQ - sQ;
                 if (cnt[K - 1] == 0) { Sd[K - 1] = R(0); Qd[K - 1] = R(0); }
             }
         }
@@ -416,16 +594,26 @@ struct GibbsWarp {
     }
 };
 
-template <typename R, int K, bool SMOOTH, bool LOGLIK, bool WIDE>
-__global__ void __launch_bounds__(kGibbsThreads) gibbs_sweeps_kernel(const GibbsArgs a) {
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        int task = 0;
-        if (lane == 0) task = atomicAdd(a.task_counter, 1);
-        task = __shfl_sync(0xffffffffu, task, 0);
-        if (task >= a.n_warps) break;
-        GibbsWarp<R, K, SMOOTH, LOGLIK, WIDE>::run(a, task, lane);
-    }
+template <typename R, int K, bool WIDE> constexpr size_t kGibbsSmemBytes() {
+    return sizeof(typename GibbsWarp<R, K, false, false, WIDE>::Entry) * K * kGibbsThreads      // selection tables
+           + (HMC_ASYNC ? sizeof(R) * (size_t)(kGibbsThreads / 32) * kRing * 4 * K * 32 : 0);    // cp.async rings
 }
+
+template <typename R, int K, bool SMOOTH, bool LOGLIK, bool WIDE>
+__global__ void __launch_bounds__(kGibbsThreads, kGibbsMinBlocks) gibbs_sweeps_kernel(const GibbsArgs a) {
+    using W = GibbsWarp<R, K, SMOOTH, LOGLIK, WIDE>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename W::Entry* tab = reinterpret_cast<typename W::Entry*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (kGibbsThreads / 32) + (threadIdx.x >> 5);
+    if (g >= a.n_tasks) return;
+    W::run(a, a.task0 + g * a.task_stride, lane, tab);
+}
+
+// host-side launcher, instantiated once per (R, K) in gibbs_inst.cu (one translation unit each, built in parallel)
+struct GibbsLaunch { unsigned flags; int max_T; int sm_count; };
+template <typename R, int K> cudaError_t launch_gibbs(const GibbsLaunch& cfg, const GibbsArgs& a, cudaStream_t st);
+// how many persistent warps of this kernel variant fit on the device at once
+template <typename R, int K> int gibbs_capacity_warps(const GibbsLaunch& cfg);
 
 }  // namespace hmc

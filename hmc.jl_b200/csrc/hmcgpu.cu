@@ -7,7 +7,11 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -16,11 +20,13 @@
 using namespace hmc;
 
 // ============================================================================================ context
+struct DevPool;
 struct hmcgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
     int sm_count = 0;
+    std::shared_ptr<DevPool> pool;      // recycled device buffers (see DevPool)
 };
 
 static thread_local std::string g_create_err;
@@ -43,19 +49,63 @@ static int fail(hmcgpu_ctx* ctx, int code, const char* fmt, ...) {
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);   \
     } while (0)
 
+// Device memory is recycled per context: repeated estimations of the same shape (the rolling-window driver calls
+// hmcgpu_estimate once per batch) reuse their multi-GB buffers instead of paying cudaMalloc/cudaFree every call.
+struct DevPool {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;
+    size_t pooled = 0;
+    static constexpr size_t kMaxPooled = 64ull << 30;
+    cudaError_t get(size_t n, void** out) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = free_blocks.find(n);
+            if (it != free_blocks.end()) { *out = it->second; pooled -= n; free_blocks.erase(it); return cudaSuccess; }
+        }
+        cudaError_t e = cudaMalloc(out, n);
+        if (e == cudaErrorMemoryAllocation) {                     // make room and retry once
+            cudaGetLastError();
+            release_all();
+            e = cudaMalloc(out, n);
+        }
+        return e;
+    }
+    void put(size_t n, void* p) {
+        std::lock_guard<std::mutex> g(mu);
+        if (pooled + n > kMaxPooled || free_blocks.size() >= 256) { cudaFree(p); return; }
+        free_blocks.emplace(n, p);
+        pooled += n;
+    }
+    void release_all() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        pooled = 0;
+    }
+    ~DevPool() { release_all(); }
+};
+static thread_local std::shared_ptr<DevPool> tl_pool;     // set by the API entry points for the context they run on
+
 // RAII device buffer
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    std::shared_ptr<DevPool> pool;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { release(); }
+    void release() {
+        if (!p) return;
+        if (pool) pool->put(bytes, p); else cudaFree(p);
+        p = nullptr;
+    }
     cudaError_t alloc(size_t n) {
-        if (p) { cudaFree(p); p = nullptr; }
+        release();
         bytes = n;
         if (n == 0) return cudaSuccess;
-        return cudaMalloc(&p, n);
+        pool = tl_pool;
+        return pool ? pool->get(n, &p) : cudaMalloc(&p, n);
     }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
@@ -86,6 +136,7 @@ extern "C" int hmcgpu_ctx_create(int device, hmcgpu_ctx** out) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->pool = std::make_shared<DevPool>();
     *out = ctx;
     return HMCGPU_OK;
 }
@@ -93,6 +144,9 @@ extern "C" int hmcgpu_ctx_create(int device, hmcgpu_ctx** out) {
 extern "C" void hmcgpu_ctx_destroy(hmcgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (tl_pool == ctx->pool) tl_pool.reset();
+    if (ctx->pool) ctx->pool->release_all();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -115,6 +169,11 @@ static bool k_supported(int K) { return K == 2 || K == 3 || K == 4; }
         case 4: { constexpr int KK = 4; __VA_ARGS__; } break; \
         default: break;                             \
     }
+#ifdef HMC_DEV_F3   /* experiment builds: only the fp32 K=3 sweep kernels are linked */
+#define DISPATCH_RUN(pl, rc) do { if ((pl)->K == 3 && (pl)->precision == 32) rc = plan_run_t<float, 3>(pl); } while (0)
+#else
+#define DISPATCH_RUN(pl, rc) DISPATCH_K((pl)->K, { rc = ((pl)->precision == 32) ? plan_run_t<float, KK>(pl) : plan_run_t<double, KK>(pl); })
+#endif
 
 // ============================================================================================ deterministic entry points
 // One thread per batch element; host arrays are fp64 row-major and are converted on the fly.
@@ -317,6 +376,7 @@ static int check_common(hmcgpu_ctx* ctx, int K, long long B, long long T) {
     if (!k_supported(K)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "K=%d not supported (2..4)", K);
     if (B <= 0 || T <= 0) return fail(ctx, HMCGPU_ERR_ARG, "empty batch (B=%lld, T=%lld)", B, T);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, HMCGPU_ERR_CUDA, "cudaSetDevice failed");
+    tl_pool = ctx->pool;
     return 0;
 }
 
@@ -431,6 +491,7 @@ extern "C" int hmcgpu_forecast(hmcgpu_ctx* ctx, int32_t K, int64_t B, const doub
 extern "C" int hmcgpu_philox(hmcgpu_ctx* ctx, int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
     if (!ctx || n <= 0 || !ctr || !key || !out) return fail(ctx, HMCGPU_ERR_ARG, "bad arguments");
     CU(ctx, cudaSetDevice(ctx->device));
+    tl_pool = ctx->pool;
     Xfer x{ctx};
     unsigned *dc, *dk, *dout;
     TRY(x.up(ctr, (size_t)n * 4, &dc)); TRY(x.up(key, (size_t)n * 2, &dk)); TRY(x.up((unsigned*)nullptr, (size_t)n * 4, &dout));
@@ -671,45 +732,24 @@ struct hmcgpu_plan {
     GibbsArgs args{};
     // device buffers
     DevBuf y64, yr, wbase, wTd, wi, slot_win, slot_chain, T, ybase, warp_T, warp_pi_off, pi, pacc, cnt, trans, Sd, Qd,
-        events, cshift, xi, xi_user, chain_id, out, yfut_w, yfut, win_slot0, win_pib_off, totS, totQ, task_counters;
+        events, cshift, xi, xi_user, chain_id, out, yfut_w, yfut, win_slot0, win_pib_off, totS, totQ;
+    int n_groups = 1, n_bufs = 1;
+    std::vector<cudaStream_t> gstreams;
+    std::vector<cudaEvent_t> pool_events;
     DevBuf d_mu, d_sig2, d_A, d_pie, d_fc, d_ll, d_sum, d_sumsq, d_pibsum;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     double gpu_ms = 0.0, sweep_ms = 0.0;
     long long n_launches = 0, n_sweep_launches = 0, h2d = 0, d2h = 0;
     bool ran = false;
     ~hmcgpu_plan() {
+        for (auto s2 : gstreams) cudaStreamDestroy(s2);
+        for (auto e : pool_events) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (evk0) cudaEventDestroy(evk0);
         if (evk1) cudaEventDestroy(evk1);
     }
 };
-
-template <typename R, int K, bool WIDE>
-static cudaError_t launch_gibbs_w(const hmcgpu_plan* pl, const GibbsArgs& a, cudaStream_t st) {
-    const bool smooth = pl->flags & HMCGPU_FLAG_SMOOTHED_MEAN, ll = pl->flags & HMCGPU_FLAG_LOGLIK;
-    auto go = [&](auto kern) -> cudaError_t {
-        int per_sm = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGibbsThreads, 0);
-        if (e != cudaSuccess) return e;
-        // persistent warps pulling tasks: one resident wave, never more blocks than there are tasks
-        const long long want = ((long long)a.n_warps + (kGibbsThreads / 32) - 1) / (kGibbsThreads / 32);
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)per_sm * pl->ctx->sm_count));
-        kern<<<grid, kGibbsThreads, 0, st>>>(a);
-        return cudaGetLastError();
-    };
-    if (smooth && ll) return go(gibbs_sweeps_kernel<R, K, true, true, WIDE>);
-    if (smooth) return go(gibbs_sweeps_kernel<R, K, true, false, WIDE>);
-    if (ll) return go(gibbs_sweeps_kernel<R, K, false, true, WIDE>);
-    return go(gibbs_sweeps_kernel<R, K, false, false, WIDE>);
-}
-
-template <typename R, int K>
-static cudaError_t launch_gibbs(const hmcgpu_plan* pl, const GibbsArgs& a, cudaStream_t st) {
-    // packed transition counters: 32-bit rows hold fields of 32/K bits; longer windows use 64-bit rows
-    if ((long long)pl->max_T - 1 <= TransPack<K, false>::kMaxT) return launch_gibbs_w<R, K, false>(pl, a, st);
-    return launch_gibbs_w<R, K, true>(pl, a, st);
-}
 
 static int validate_problem(hmcgpu_ctx* ctx, const hmcgpu_problem* p) {
     if (!ctx) return HMCGPU_ERR_ARG;
@@ -800,9 +840,15 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
             if (idx <= p->y_len) yfut_w[(size_t)w * p->n_h + j] = p->y[(size_t)ser * p->y_len + idx - 1];
         }
 
-    // chunk of draws per launch: bound the chunk buffer to ~1 GiB
+    // task groups: interleaved subsets of the (longest-first) warp tasks, each driven through its own stream
+    pl->n_groups = n_warps >= 1024 ? 4 : (n_warps >= 256 ? 2 : 1);
+    if (const char* e = getenv("HMCGPU_GROUPS")) pl->n_groups = std::max(1, std::min(8, atoi(e)));
+    pl->n_groups = std::min(pl->n_groups, n_warps);
+    // double-buffered draw chunks let the groups drift apart (not with the smoothing accumulators, which are shared)
+    pl->n_bufs = (pl->n_groups > 1 && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN)) ? 2 : 1;
+    // chunk of draws per buffer: bound the chunk buffers to ~2 GiB in total
     const size_t per_draw = (size_t)pl->F * n_slots * sizeof(R);
-    long long chunk = std::max<long long>(1, (long long)((1ull << 30) / per_draw));
+    long long chunk = std::max<long long>(1, (long long)((2ull << 30) / pl->n_bufs / per_draw));
     chunk = std::min<long long>(chunk, std::min<long long>(p->nrun, 1024));
     pl->chunk = (int)chunk;
 
@@ -844,7 +890,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     CU(ctx, pl->xi.alloc((size_t)K * n_slots * sizeof(R)));
     CU(ctx, pl->totS.alloc((size_t)n_slots * sizeof(R)));
     CU(ctx, pl->totQ.alloc((size_t)n_slots * sizeof(R)));
-    CU(ctx, pl->out.alloc(per_draw * (size_t)chunk));
+    CU(ctx, pl->out.alloc(per_draw * (size_t)chunk * pl->n_bufs));
     CU(ctx, pl->yfut.alloc((size_t)std::max(1, p->n_h) * n_slots * sizeof(R)));
     const size_t Rr = (size_t)nc * p->nrun;
     if (p->flags & HMCGPU_FLAG_DRAWS) {
@@ -887,18 +933,41 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     a.burnin = p->burnin; a.out = pl->out.p; a.chunk = pl->chunk; a.n_h = p->n_h;
     for (int j = 0; j < p->n_h; ++j) { a.h_sorted[j] = p->horizons[hs[j]]; a.h_slot[j] = hs[j]; }
     a.yfut = pl->yfut.p; a.flags = p->flags;
+    for (int g = 0; g < pl->n_groups; ++g) {
+        cudaStream_t s2;
+        CU(ctx, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        pl->gstreams.push_back(s2);
+    }
     CU(ctx, cudaEventCreate(&pl->ev0)); CU(ctx, cudaEventCreate(&pl->ev1));
     CU(ctx, cudaEventCreate(&pl->evk0)); CU(ctx, cudaEventCreate(&pl->evk1));
     CU(ctx, cudaStreamSynchronize(st));
     return HMCGPU_OK;
 }
 
+// Sweeps per launch.  Short launches bound the damage of the priority-based warp arbiter (a starved warp can only fall
+// behind by one launch) and give the block scheduler a steady supply of pending blocks from the other groups.
+static int sweeps_per_launch() {
+    if (const char* e = getenv("HMCGPU_SWEEPS_PER_LAUNCH")) return std::max(1, atoi(e));
+    return 16;
+}
+
 template <typename R, int K>
 static int plan_run_t(hmcgpu_plan* pl) {
     hmcgpu_ctx* ctx = pl->ctx;
     cudaStream_t st = ctx->stream;
-    const int ns = pl->n_slots;
+    const int ns = pl->n_slots, G = pl->n_groups, L = sweeps_per_launch();
     pl->n_launches = 0; pl->n_sweep_launches = 0; pl->sweep_ms = 0.0;
+    size_t ev_used = 0;
+    auto new_event = [&](cudaEvent_t* e) -> cudaError_t {
+        if (ev_used == pl->pool_events.size()) {
+            cudaEvent_t x;
+            cudaError_t rc = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+            if (rc != cudaSuccess) return rc;
+            pl->pool_events.push_back(x);
+        }
+        *e = pl->pool_events[ev_used++];
+        return cudaSuccess;
+    };
     CU(ctx, cudaEventRecord(pl->ev0, st));
     chain_init_kernel<R><<<grid_for(ns, 128), 128, 0, st>>>(K, ns, pl->slot_win.as<int>(), pl->wi.as<WinInit>(),
                                                             pl->xi_user.as<double>(), pl->cnt.as<int>(), pl->trans.as<int>(),
@@ -908,41 +977,35 @@ static int plan_run_t(hmcgpu_plan* pl) {
     ++pl->n_launches;
     if (pl->d_sum.p) { CU(ctx, cudaMemsetAsync(pl->d_sum.p, 0, pl->d_sum.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_sumsq.p, 0, pl->d_sumsq.bytes, st)); }
     if (pl->pacc.p) { CU(ctx, cudaMemsetAsync(pl->pacc.p, 0, pl->pacc.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_pibsum.p, 0, pl->d_pibsum.bytes, st)); }
-    GibbsArgs a = pl->args;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
-    const long long n_sweep_launches = (pl->burnin + 1023) / 1024 + (pl->nrun + pl->chunk - 1) / pl->chunk;
-    if (pl->task_counters.bytes < (size_t)n_sweep_launches * sizeof(int)) CU(ctx, pl->task_counters.alloc((size_t)n_sweep_launches * sizeof(int)));
-    CU(ctx, cudaMemsetAsync(pl->task_counters.p, 0, pl->task_counters.bytes, st));
-    auto sweep_launch = [&](long long sweep0, int n, long long draw0) -> int {
-        a.sweep0 = sweep0; a.n_sweeps = n; a.draw0 = draw0;
-        a.task_counter = pl->task_counters.as<int>() + pl->n_sweep_launches;
-        cudaEvent_t e0, e1;
-        CU(ctx, cudaEventCreate(&e0)); CU(ctx, cudaEventCreate(&e1));
-        evs.emplace_back(e0, e1);
-        CU(ctx, cudaEventRecord(e0, st));
-        CU(ctx, (launch_gibbs<R, K>(pl, a, st)));
-        CU(ctx, cudaEventRecord(e1, st));
-        ++pl->n_launches; ++pl->n_sweep_launches;
-        return 0;
-    };
-    // burn-in (no outputs), in launches of at most 1024 sweeps
-    for (long long s = 0; s < pl->burnin; s += 1024) TRY(sweep_launch(s, (int)std::min<long long>(1024, pl->burnin - s), 0));
-    // saved draws, one chunk per launch, each followed by its post-processing kernels
-    for (long long d0 = 0; d0 < pl->nrun; d0 += pl->chunk) {
+    cudaEvent_t ev_init;
+    CU(ctx, new_event(&ev_init));
+    CU(ctx, cudaEventRecord(ev_init, st));
+    for (int g = 0; g < G; ++g) CU(ctx, cudaStreamWaitEvent(pl->gstreams[g], ev_init, 0));
+
+    const GibbsLaunch cfg{pl->flags, pl->max_T, ctx->sm_count};
+    const long long S = pl->burnin + pl->nrun;
+    const long long n_chunks = (pl->nrun + pl->chunk - 1) / pl->chunk;
+    const size_t buf_elems = (size_t)pl->F * pl->chunk * ns;
+    std::vector<long long> next(G, 0);                       // next sweep of each group
+    std::vector<cudaEvent_t> post_done(n_chunks, nullptr);   // post-processing of chunk k finished
+    std::vector<std::vector<cudaEvent_t>> chunk_done(n_chunks, std::vector<cudaEvent_t>(G, nullptr));
+    long long posted = 0;                                    // chunks whose post-processing has been enqueued
+    auto enqueue_post = [&](long long k) -> int {
+        for (int g = 0; g < G; ++g) CU(ctx, cudaStreamWaitEvent(st, chunk_done[k][g], 0));
+        const long long d0 = k * pl->chunk;
         const int n = (int)std::min<long long>(pl->chunk, pl->nrun - d0);
-        TRY(sweep_launch(pl->burnin + d0, n, d0));
+        const R* buf = pl->out.as<R>() + (size_t)(k % pl->n_bufs) * buf_elems;
         if (pl->flags & HMCGPU_FLAG_DRAWS) {
             dim3 blk(32, 8), grd(grid_for(ns, 32), grid_for(n, 8));
             gather_draws_kernel<R><<<grd, blk, 0, st>>>(K, pl->n_h, ns, pl->chunk, n, d0, pl->nrun, pl->n_chains, pl->slot_win.as<int>(),
-                                                         pl->slot_chain.as<int>(), pl->out.as<R>(), pl->d_mu.as<double>(),
-                                                         pl->d_sig2.as<double>(), pl->d_A.as<double>(), pl->d_pie.as<double>(),
-                                                         pl->d_fc.as<double>(), pl->d_ll.as<double>());
+                                                         pl->slot_chain.as<int>(), buf, pl->d_mu.as<double>(), pl->d_sig2.as<double>(),
+                                                         pl->d_A.as<double>(), pl->d_pie.as<double>(), pl->d_fc.as<double>(), pl->d_ll.as<double>());
             CU(ctx, cudaGetLastError());
             ++pl->n_launches;
         }
         if (pl->flags & HMCGPU_FLAG_SUMMARY) {
             dim3 grd(pl->n_windows, pl->F);
-            summary_accum_kernel<R><<<grd, 128, 0, st>>>(pl->F, ns, pl->chunk, n, pl->n_chains, pl->win_slot0.as<int>(), pl->out.as<R>(),
+            summary_accum_kernel<R><<<grd, 128, 0, st>>>(pl->F, ns, pl->chunk, n, pl->n_chains, pl->win_slot0.as<int>(), buf,
                                                          pl->d_sum.as<double>(), pl->d_sumsq.as<double>());
             CU(ctx, cudaGetLastError());
             ++pl->n_launches;
@@ -954,18 +1017,70 @@ static int plan_run_t(hmcgpu_plan* pl) {
             CU(ctx, cudaGetLastError());
             ++pl->n_launches;
         }
+        CU(ctx, new_event(&post_done[k]));
+        CU(ctx, cudaEventRecord(post_done[k], st));
+        return 0;
+    };
+    GibbsArgs a = pl->args;
+    // launches are enqueued round-robin over the groups; a launch never crosses the end of burn-in or of a draw chunk
+    bool more = true;
+    for (long long round = 0; more; ++round) {
+        more = false;
+        std::vector<int> gorder(G);
+        std::iota(gorder.begin(), gorder.end(), 0);
+        std::stable_sort(gorder.begin(), gorder.end(), [&](int x, int y2) { return next[x] < next[y2]; });   // laggards first
+        for (int g : gorder) {
+            const long long s0 = next[g];
+            if (s0 >= S) continue;
+            more = true;
+            if (s0 >= pl->burnin && (s0 - pl->burnin) % pl->chunk == 0) {
+                const long long k0 = (s0 - pl->burnin) / pl->chunk;
+                if (k0 >= pl->n_bufs && post_done[k0 - pl->n_bufs] == nullptr) continue;   // buffer not released yet: next round
+            }
+            // stagger: the first launch of group g is (g+1)/G of a normal one, so the groups' launch boundaries interleave
+            long long n = (round == 0 && G > 1) ? std::max<long long>(1, (long long)L * (g + 1) / G) : L;
+            long long limit = S;
+            if (s0 < pl->burnin) limit = pl->burnin;
+            else limit = pl->burnin + std::min<long long>(pl->nrun, ((s0 - pl->burnin) / pl->chunk + 1) * pl->chunk);
+            n = std::min(n, limit - s0);
+            cudaStream_t gs = pl->gstreams[g];
+            long long k = -1;
+            if (s0 >= pl->burnin) {
+                k = (s0 - pl->burnin) / pl->chunk;
+                // the chunk's buffer must have been consumed by the post-processing of chunk k - n_bufs
+                if ((s0 - pl->burnin) % pl->chunk == 0 && k >= pl->n_bufs) CU(ctx, cudaStreamWaitEvent(gs, post_done[k - pl->n_bufs], 0));
+                a.draw0 = k * pl->chunk;
+                a.out = pl->out.as<R>() + (size_t)(k % pl->n_bufs) * buf_elems;
+            } else {
+                a.draw0 = 0;
+                a.out = pl->out.p;
+            }
+            a.sweep0 = s0; a.n_sweeps = (int)n;
+            a.task0 = g; a.task_stride = G; a.n_tasks = (pl->n_warps - g + G - 1) / G;
+            CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
+            ++pl->n_launches; ++pl->n_sweep_launches;
+            next[g] = s0 + n;
+            if (k >= 0 && next[g] == pl->burnin + std::min<long long>(pl->nrun, (k + 1) * pl->chunk)) {
+                CU(ctx, new_event(&chunk_done[k][g]));
+                CU(ctx, cudaEventRecord(chunk_done[k][g], gs));
+            }
+            // post-process every chunk all groups have finished enqueuing
+            while (posted < n_chunks) {
+                bool ready = true;
+                for (int g2 = 0; g2 < G; ++g2) ready = ready && chunk_done[posted][g2] != nullptr;
+                if (!ready) break;
+                TRY(enqueue_post(posted));
+                ++posted;
+            }
+        }
     }
-    CU(ctx, cudaEventRecord(pl->ev1, st));
+    CU(ctx, cudaEventRecord(pl->ev1, st));                   // st has waited for every group through the last chunk's post
     CU(ctx, cudaEventSynchronize(pl->ev1));
+    for (int g = 0; g < G; ++g) CU(ctx, cudaStreamSynchronize(pl->gstreams[g]));
     float ms = 0.f;
     CU(ctx, cudaEventElapsedTime(&ms, pl->ev0, pl->ev1));
     pl->gpu_ms = ms;
-    for (auto& e : evs) {
-        float k = 0.f;
-        cudaEventElapsedTime(&k, e.first, e.second);
-        pl->sweep_ms += k;
-        cudaEventDestroy(e.first); cudaEventDestroy(e.second);
-    }
+    pl->sweep_ms = ms;                                       // launches of different groups overlap: report the enclosing time
     pl->ran = true;
     return HMCGPU_OK;
 }
@@ -975,6 +1090,7 @@ extern "C" int hmcgpu_plan_create(hmcgpu_ctx* ctx, const hmcgpu_problem* p, hmcg
     *out = nullptr;
     TRY(validate_problem(ctx, p));
     CU(ctx, cudaSetDevice(ctx->device));
+    tl_pool = ctx->pool;
     hmcgpu_plan* pl = new hmcgpu_plan();
     pl->ctx = ctx;
     int rc = (p->precision == 32) ? plan_build<float>(pl, p) : plan_build<double>(pl, p);
@@ -988,7 +1104,7 @@ extern "C" int hmcgpu_plan_run(hmcgpu_plan* pl) {
     hmcgpu_ctx* ctx = pl->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     int rc = HMCGPU_ERR_UNSUPPORTED;
-    DISPATCH_K(pl->K, { rc = (pl->precision == 32) ? plan_run_t<float, KK>(pl) : plan_run_t<double, KK>(pl); });
+    DISPATCH_RUN(pl, rc);
     return rc;
 }
 
@@ -1055,6 +1171,8 @@ extern "C" int hmcgpu_plan_fetch(hmcgpu_plan* pl, hmcgpu_result* r) {
 extern "C" void hmcgpu_plan_destroy(hmcgpu_plan* pl) {
     if (!pl) return;
     cudaSetDevice(pl->ctx->device);
+    cudaStreamSynchronize(pl->ctx->stream);            // nothing may still be using the buffers that go back to the pool
+    for (auto s2 : pl->gstreams) cudaStreamSynchronize(s2);
     delete pl;
 }
 
