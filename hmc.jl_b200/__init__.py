@@ -5,6 +5,7 @@ Layout: csrc/ (CUDA kernels + C ABI), lib/ (built libhmcgpu.so), binding.py (cty
 api.py (mirror of Hmc.estopt / Hmc.estimatemodel), julia/HmcGPU.jl (the ccall binding a Julia user loads).
 """
 from . import build  # noqa: F401
-from .api import EstOpt, estimatemodel, estimate_windows, shard_windows, expanding_windows  # noqa: F401
+from .api import (EstOpt, estimatemodel, estimate_windows, shard_windows, expanding_windows,  # noqa: F401
+                  gather_window_summaries)
 from .binding import (Context, HmcGpuError, Plan, ProblemSpec, estimate, estimate_multi, load, lib_path,  # noqa: F401
                       FLAG_REF_Q1, FLAG_DRAWS, FLAG_SUMMARY, FLAG_SMOOTHED_MEAN, FLAG_LOGLIK, SYMBOLS)

@@ -118,3 +118,35 @@ def estimate_windows(y, win_start, win_end, *, K=3, n_chains=1, burnin=1000, nru
     finally:
         if own:
             ctx.close()
+
+
+def gather_window_summaries(local: np.ndarray, shard: np.ndarray, n_windows: int, dist=None, device=None):
+    """Final host gather of per-window summaries (the only cross-rank step of the path; no data-path collective).
+
+    `local` [len(shard), F] holds this rank's windows, `shard` their global indices.  Returns the full
+    [n_windows, F] table on rank 0 (None elsewhere).  `dist` is torch.distributed (initialised: nccl on the
+    GPU box, gloo in the CPU tests) or None for a single process."""
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    if dist is None or dist.get_world_size() == 1:
+        out = np.empty((n_windows, local.shape[1]))
+        out[np.asarray(shard)] = local
+        return out
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    max_rows = (n_windows + world - 1) // world + 1
+    # payload rows: [global index, F values]; padded with index -1
+    pad = torch.full((max_rows, local.shape[1] + 1), -1.0, dtype=torch.float64)
+    pad[: len(shard), 0] = torch.as_tensor(np.asarray(shard), dtype=torch.float64)
+    pad[: len(shard), 1:] = torch.from_numpy(local)
+    if device is not None:
+        pad = pad.to(device)
+    parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, parts, dst=0)
+    if rank != 0:
+        return None
+    out = np.full((n_windows, local.shape[1]), np.nan)
+    for t in parts:
+        t = t.cpu().numpy()
+        keep = t[:, 0] >= 0
+        out[t[keep, 0].astype(np.int64)] = t[keep, 1:]
+    return out
