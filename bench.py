@@ -196,6 +196,10 @@ def run_reference(args):
 
 
 def workload_config(args, world):
+    if getattr(args, "workload", "c2") != "c2":
+        return {"workload": {"c1": "C1: one window T=600, K=3, one chain (latency-bound by construction)",
+                             "c4": "C4: independent series of T=2000, K=3, one chain each (wide batch)"}[args.workload],
+                "K": K, "chains": args.chains, "burnin": args.burnin, "nrun": args.nrun, "precision": f"fp{args.precision}"}
     return {"workload": "C2 rolling estimation: 500 expanding windows T=101..600 of one synthetic K=3 series (len 612, "
                         "default_rng(1234)), burnin+nrun Gibbs sweeps, forecasts h=1..12, per-window posterior summaries",
             "K": K, "windows": 500, "chains_per_window": args.chains * world, "burnin": args.burnin, "nrun": args.nrun,
@@ -210,6 +214,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=256, help="chains per window per GPU")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c1", "c4"],
+                    help="c2 (default, BASELINE configs[1]): 500 expanding windows; c1: one window T=600, one chain; "
+                         "c4: --chains independent series (default 65536) of T=2000, K=3")
     ap.add_argument("--burnin", type=int, default=1000)
     ap.add_argument("--nrun", type=int, default=1000)
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
@@ -227,13 +234,32 @@ def main():
     torch.cuda.set_device(local)
     torch.zeros(1, device=f"cuda:{local}")          # create the primary context torch.cuda.synchronize() needs
 
-    y = synth_series()
-    ws_all, we_all = H.expanding_windows(101, 600)
+    win_series = None
+    if args.workload == "c2":
+        y = synth_series()
+        ws_all, we_all = H.expanding_windows(101, 600)
+        n_chains = args.chains * world              # weak scaling: per-GPU work fixed
+    elif args.workload == "c1":
+        y = synth_series()
+        ws_all, we_all = np.array([1], dtype=np.int32), np.array([600], dtype=np.int32)
+        n_chains = 1
+    else:                                           # c4: wide batch of independent series (SURVEY section 8d "C4")
+        n_ser = (args.chains if args.chains != 256 else 65536) * world
+        rng = np.random.default_rng(1234)
+        X = np.zeros((n_ser, 2012), dtype=np.int64)
+        u = rng.random((n_ser, 2012))
+        cum = np.cumsum(TRUTH["A"], axis=1)
+        for t in range(1, 2012):
+            X[:, t] = (u[:, t, None] > cum[X[:, t - 1]]).sum(1)
+        y = TRUTH["mu"][X] + np.sqrt(TRUTH["sigma2"][X]) * rng.standard_normal((n_ser, 2012))
+        ws_all, we_all = np.ones(n_ser, dtype=np.int32), np.full(n_ser, 2000, dtype=np.int32)
+        win_series = np.arange(n_ser, dtype=np.int32)
+        n_chains = 1
     shard = H.shard_windows(we_all - ws_all + 1, world)[rank]
     ws, we = ws_all[shard], we_all[shard]
-    n_chains = args.chains * world                  # weak scaling: per-GPU work fixed
     spec = H.ProblemSpec(y, ws, we, K=K, n_chains=n_chains, burnin=args.burnin, nrun=args.nrun, seed=1234, horizons=HORIZONS,
-                         precision=args.precision, flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY, win_id=shard)
+                         precision=args.precision, flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY, win_id=shard,
+                         win_series=None if win_series is None else win_series[shard])
     ctx = H.Context(local)
     plan = H.Plan(ctx, spec)
     for _ in range(args.warmup):
@@ -296,7 +322,7 @@ def main():
 
     if rank == 0:
         cb = None
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.workload == "c2":
             cb, _, _ = cpu_baseline(y, ws_all, we_all, burnin=args.burnin, nrun=args.nrun)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

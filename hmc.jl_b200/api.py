@@ -150,3 +150,71 @@ def gather_window_summaries(local: np.ndarray, shard: np.ndarray, n_windows: int
         keep = t[:, 0] >= 0
         out[t[keep, 0].astype(np.int64)] = t[keep, 1:]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Output layer: the reference's per-end-date CSVs and the per-date means of code/aggregate.jl
+
+def _fmt(v, digits=5):
+    return repr(round(float(v), digits))
+
+
+def saveresults(samples, opt: EstOpt, directory: str, precision: int = 5):
+    """Mirror of Hmc.saveresults(samples, opt, dir; hassignals=false) (src/Hmc.jl:724-748 -> basicsave :707-722):
+    five CSVs per end date, one row per draw, values rounded to `precision` digits (:719).  Headers as the current
+    reference code builds them: state_i; trans_i_j in column-major order of (i, j) with column trans_i_j = A[i, j]
+    (:727, :745); forecast_h, forecast_error_h (:729-732)."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    D = opt.D
+    date = str(opt.dates[opt.endIndex - 1])
+    h1 = [f"state_{i}" for i in range(1, D + 1)]
+    h2 = [f"trans_{i}_{j}" for j in range(1, D + 1) for i in range(1, D + 1)]
+    h3 = []
+    for h in opt.horizons:
+        h3 += [f"forecast_{h}", f"forecast_error_{h}"]
+    R = samples.μ.shape[0]
+    tables = {
+        "filtered_means": (h1, samples.μ),
+        "filtered_variances": (h1, samples.σ),
+        "filtered_state_probs": (h1, samples.πb[:, -1, :]),                                  # :744
+        "filtered_trans_probs": (h2, np.transpose(samples.A, (0, 2, 1)).reshape(R, D * D)),  # reshape(A, Nrun, :) column-major
+        "forecasts": (h3, samples.forecasts),
+    }
+    paths = {}
+    for name, (hdr, data) in tables.items():
+        path = os.path.join(directory, f"{name}_{date}.csv")
+        with open(path, "w") as f:
+            f.write(",".join(["date"] + hdr) + "\n")
+            for row in np.asarray(data):
+                f.write(",".join([date] + [_fmt(v, precision) for v in row]) + "\n")
+        paths[name] = path
+    return paths
+
+
+def write_summaries(out, K: int, horizons: Sequence[int], dates: Sequence, directory: str):
+    """Per-date posterior means in the layout of the reference's `<var>_summary.csv` (Hmc.runaggregate,
+    src/Hmc.jl:1025-1051: group by date, mean -> columns `<col>_mean`), computed on the device
+    (HMCGPU_FLAG_SUMMARY) instead of from 250 000-row draw files.  One row per window, in caller order."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    m = np.asarray(out.summary_mean)
+    nh = len(horizons)
+    cols = {
+        "filtered_means": ([f"state_{i}_mean" for i in range(1, K + 1)], m[:, 0:K]),
+        "filtered_variances": ([f"state_{i}_mean" for i in range(1, K + 1)], m[:, K:2 * K]),
+        # summary A index s*K + r = A[r, s]  ->  column-major (i, j) order with trans_i_j = A[i, j]
+        "filtered_trans_probs": ([f"trans_{i}_{j}_mean" for j in range(1, K + 1) for i in range(1, K + 1)], m[:, 2 * K:2 * K + K * K]),
+        "filtered_state_probs": ([f"state_{i}_mean" for i in range(1, K + 1)], m[:, 2 * K + K * K:3 * K + K * K]),
+        "forecasts": (sum([[f"forecast_{h}_mean", f"forecast_error_{h}_mean"] for h in horizons], []),
+                      m[:, 3 * K + K * K:3 * K + K * K + 2 * nh]),
+    }
+    paths = {}
+    for name, (hdr, data) in cols.items():
+        path = os.path.join(directory, f"{name}_summary.csv")
+        with open(path, "w") as f:
+            f.write(",".join(["date"] + hdr) + "\n")
+            for d, row in zip(dates, data):
+                f.write(",".join([str(d)] + [repr(float(v)) for v in row]) + "\n")
+        paths[name] = path
+    return paths

@@ -46,11 +46,13 @@ template <> struct M<double> {
     static __device__ __forceinline__ double cos2pi(double u) { return ::cos(6.283185307179586 * u); }
     static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
 };
+// fp32 draws use the SFU approximations (lg2/ex2/sin-cos/rsqrt, ~1e-6 relative): the conjugate draws are ~10 % of the
+// sweep kernel's instructions with the libm versions, and draw-level accuracy is far inside the fp32 path's tolerance.
 template <> struct M<float> {
-    static __device__ __forceinline__ float log(float x) { return ::logf(x); }
-    static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
-    static __device__ __forceinline__ float cos2pi(float u) { return ::cospif(2.0f * u); }
-    static __device__ __forceinline__ float pow(float x, float y) { return ::powf(x, y); }
+    static __device__ __forceinline__ float log(float x) { return __logf(x); }
+    static __device__ __forceinline__ float sqrt(float x) { return __fsqrt_rn(x); }
+    static __device__ __forceinline__ float cos2pi(float u) { return __cosf(6.283185307179586f * u); }
+    static __device__ __forceinline__ float pow(float x, float y) { return __powf(x, y); }
 };
 
 // Box-Muller, cos branch, from two words

@@ -78,3 +78,42 @@ def test_problem_spec_layouts(H):
     assert o.pib_mean.size == (40 + 46) * 3
     st = spec.struct()
     assert st.y_len == 50 and st.n_series == 3 and st.n_windows == 2 and st.n_h == 2
+
+
+def test_saveresults_csv_layout(H, tmp_path):
+    """src/Hmc.jl:707-748: headers, 5-digit rounding, trans_i_j column order, piB[:, end, :]."""
+    from types import SimpleNamespace
+    rng = np.random.default_rng(0)
+    R, D = 4, 3
+    A = rng.dirichlet(np.ones(D), size=(R, D))
+    s = SimpleNamespace(μ=rng.normal(size=(R, D)), σ=rng.uniform(1, 2, size=(R, D)), A=A,
+                        πb=rng.dirichlet(np.ones(D), size=R)[:, None, :], forecasts=rng.normal(size=(R, 2)))
+    dates = [f"2000-{m:02d}-01" for m in range(1, 13)]
+    opt = H.EstOpt(np.arange(12.0), dates, sampleRange=range(1, 11), endIndex=10, horizons=[12], D=D)
+    paths = H.saveresults(s, opt, str(tmp_path))
+    lines = open(paths["filtered_trans_probs"]).read().splitlines()
+    assert lines[0] == "date,trans_1_1,trans_2_1,trans_3_1,trans_1_2,trans_2_2,trans_3_2,trans_1_3,trans_2_3,trans_3_3"
+    row = lines[1].split(",")
+    assert row[0] == "2000-10-01" and len(lines) == R + 1
+    np.testing.assert_allclose([float(v) for v in row[1:]], np.round(A[0].T.ravel(), 5))     # trans_i_j = A[i, j]
+    assert open(paths["forecasts"]).readline().strip() == "date,forecast_12,forecast_error_12"
+    assert open(paths["filtered_means"]).readline().strip() == "date,state_1,state_2,state_3"
+    got = np.loadtxt(paths["filtered_state_probs"], delimiter=",", skiprows=1, usecols=(1, 2, 3))
+    np.testing.assert_allclose(got, np.round(s.πb[:, -1, :], 5))
+
+
+def test_write_summaries_matches_reference_summary_columns(H, tmp_path):
+    import json
+    from types import SimpleNamespace
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "official_summary_subset.json")))
+    K, hs = 3, [12]
+    F = 3 * K + K * K + 2 * len(hs) + 1
+    m = np.arange(2 * F, dtype=float).reshape(2, F)
+    paths = H.write_summaries(SimpleNamespace(summary_mean=m), K, hs, ["1979-12-01", "1980-01-01"], str(tmp_path))
+    for name in ("filtered_means", "filtered_variances", "filtered_state_probs", "forecasts"):
+        hdr = open(paths[name]).readline().strip().split(",")[1:]
+        assert hdr == g["columns"][name], name
+    hdr = open(paths["filtered_trans_probs"]).readline().strip().split(",")[1:]
+    assert sorted(hdr) == sorted(g["columns"]["filtered_trans_probs"])          # same names (the goldens predate the :727 order)
+    row = open(paths["filtered_means"]).read().splitlines()[2].split(",")
+    assert row[0] == "1980-01-01" and [float(v) for v in row[1:]] == m[1, 0:3].tolist()
