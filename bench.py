@@ -198,8 +198,9 @@ def run_reference(args):
 def workload_config(args, world):
     if getattr(args, "workload", "c2") != "c2":
         return {"workload": {"c1": "C1: one window T=600, K=3, one chain (latency-bound by construction)",
-                             "c4": "C4: independent series of T=2000, K=3, one chain each (wide batch)"}[args.workload],
-                "K": K, "chains": args.chains, "burnin": args.burnin, "nrun": args.nrun, "precision": f"fp{args.precision}"}
+                             "c4": "C4: independent series of T=2000, K=3, one chain each (wide batch)",
+                             "c5": f"C5: independent series of T={args.length}, K={args.states}, one chain each"}[args.workload],
+                "K": getattr(args, "K_run", K), "chains": args.chains, "burnin": args.burnin, "nrun": args.nrun, "precision": f"fp{args.precision}"}
     return {"workload": "C2 rolling estimation: 500 expanding windows T=101..600 of one synthetic K=3 series (len 612, "
                         "default_rng(1234)), burnin+nrun Gibbs sweeps, forecasts h=1..12, per-window posterior summaries",
             "K": K, "windows": 500, "chains_per_window": args.chains * world, "burnin": args.burnin, "nrun": args.nrun,
@@ -214,7 +215,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=256, help="chains per window per GPU")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c1", "c4"],
+    ap.add_argument("--states", type=int, default=3, help="K for --workload c5 (K=3: SURVEY truth; otherwise mu_k=2k, sigma2=0.5)")
+    ap.add_argument("--length", type=int, default=2000, help="T for --workload c4/c5")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c1", "c4", "c5"],
                     help="c2 (default, BASELINE configs[1]): 500 expanding windows; c1: one window T=600, one chain; "
                          "c4: --chains independent series (default 65536) of T=2000, K=3")
     ap.add_argument("--burnin", type=int, default=1000)
@@ -243,21 +246,28 @@ def main():
         y = synth_series()
         ws_all, we_all = np.array([1], dtype=np.int32), np.array([600], dtype=np.int32)
         n_chains = 1
-    else:                                           # c4: wide batch of independent series (SURVEY section 8d "C4")
+    else:                                           # c4 / c5: wide batch of independent series
+        Kw = args.states if args.workload == "c5" else 3
+        truth = TRUTH if Kw == 3 else dict(A=np.full((Kw, Kw), 0.1 / (Kw - 1)) + np.eye(Kw) * (0.9 - 0.1 / (Kw - 1)),
+                                           mu=2.0 * np.arange(Kw), sigma2=np.full(Kw, 0.5))
         n_ser = (args.chains if args.chains != 256 else 65536) * world
+        n_gen = min(n_ser, 2048)                    # distinct series generated; tiled to n_ser (device work is unaffected)
+        L = args.length + 12
         rng = np.random.default_rng(1234)
-        X = np.zeros((n_ser, 2012), dtype=np.int64)
-        u = rng.random((n_ser, 2012))
-        cum = np.cumsum(TRUTH["A"], axis=1)
-        for t in range(1, 2012):
-            X[:, t] = (u[:, t, None] > cum[X[:, t - 1]]).sum(1)
-        y = TRUTH["mu"][X] + np.sqrt(TRUTH["sigma2"][X]) * rng.standard_normal((n_ser, 2012))
-        ws_all, we_all = np.ones(n_ser, dtype=np.int32), np.full(n_ser, 2000, dtype=np.int32)
+        X = np.zeros((n_gen, L), dtype=np.int64)
+        u = rng.random((n_gen, L))
+        cum = np.cumsum(truth["A"], axis=1)
+        for t in range(1, L):
+            X[:, t] = np.minimum((u[:, t, None] > cum[X[:, t - 1]]).sum(1), Kw - 1)
+        y = truth["mu"][X] + np.sqrt(truth["sigma2"][X]) * rng.standard_normal((n_gen, L))
+        y = np.tile(y, ((n_ser + n_gen - 1) // n_gen, 1))[:n_ser]
+        ws_all, we_all = np.ones(n_ser, dtype=np.int32), np.full(n_ser, args.length, dtype=np.int32)
         win_series = np.arange(n_ser, dtype=np.int32)
         n_chains = 1
+        args.K_run = Kw
     shard = H.shard_windows(we_all - ws_all + 1, world)[rank]
     ws, we = ws_all[shard], we_all[shard]
-    spec = H.ProblemSpec(y, ws, we, K=K, n_chains=n_chains, burnin=args.burnin, nrun=args.nrun, seed=1234, horizons=HORIZONS,
+    spec = H.ProblemSpec(y, ws, we, K=getattr(args, "K_run", K), n_chains=n_chains, burnin=args.burnin, nrun=args.nrun, seed=1234, horizons=HORIZONS,
                          precision=args.precision, flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY, win_id=shard,
                          win_series=None if win_series is None else win_series[shard])
     ctx = H.Context(local)
@@ -303,7 +313,7 @@ def main():
 
     # ---- roofline of the dominant kernel (gibbs_sweeps_kernel): algorithmic bytes = (2K+2)*b per state-step
     bpe = 4 if args.precision == 32 else 8
-    alg_bytes_per_step = (2 * K + 2) * bpe
+    alg_bytes_per_step = (2 * getattr(args, "K_run", K) + 2) * bpe
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -331,7 +341,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                         "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
-                "check": {"mu_mean_longest_window": res.summary_mean[int(np.argmax(we - ws))][0:3].tolist(), "events": int(res.events)}}
+                "check": {"mu_mean_longest_window": res.summary_mean[int(np.argmax(we - ws))][0:getattr(args, "K_run", K)].tolist(),
+                          "events": int(res.events)}}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-HEADERS = [os.path.join(CSRC, f) for f in ("gibbs_kernel.cuh", "hmm_device.cuh", "rng.cuh")] + [
+HEADERS = [os.path.join(CSRC, f) for f in ("gibbs_kernel.cuh", "gibbs_wide_kernel.cuh", "hmm_device.cuh", "rng.cuh")] + [
     os.path.join(HERE, "..", "include", "hmcgpu.h")]
 LIB = os.path.join(HERE, "lib", "libhmcgpu.so")
 TAG = os.environ.get("HMC_TAG")             # experiment knob: build/load a side library lib/libhmcgpu_<tag>.so ...
@@ -21,7 +21,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O2",
          "-Xptxas", "-v", "--fmad=true"]
 UNITS = [("hmcgpu", "hmcgpu.cu", [])] + [
-    (f"gibbs_{r}_{k}", "gibbs_inst.cu", [f"-DHMC_R={r}", f"-DHMC_K={k}"]) for r in ("float", "double") for k in (2, 3, 4)]
+    (f"gibbs_{r}_{k}", "gibbs_inst.cu", [f"-DHMC_R={r}", f"-DHMC_K={k}"]) for r in ("float", "double") for k in (2, 3, 4)] + [
+    (f"gibbs_wide_{r}", "gibbs_wide_inst.cu", [f"-DHMC_R={r}"]) for r in ("float", "double")]
 
 
 def _compile(unit):
@@ -46,8 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if os.path.exists(LIB) and not force:
             return LIB                          # side libraries are never rebuilt implicitly
         if "-DHMC_DEV_F3" in DEFS:              # fp32, K=3 only: the bench path, for quick A/B builds
-            units = [u for u in UNITS if u[0] in ("hmcgpu", "gibbs_float_3")]
-    sources = [os.path.join(CSRC, "hmcgpu.cu"), os.path.join(CSRC, "gibbs_inst.cu")] + HEADERS
+            units = [u for u in UNITS if u[0] in ("hmcgpu", "gibbs_float_3", "gibbs_wide_float")]
+    sources = [os.path.join(CSRC, f) for f in ("hmcgpu.cu", "gibbs_inst.cu", "gibbs_wide_inst.cu")] + HEADERS
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in sources):
         return LIB                              # e.g. on the GPU box: the prebuilt library travels, the objects do not
     os.makedirs(OBJ, exist_ok=True)

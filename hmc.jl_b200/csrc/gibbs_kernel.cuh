@@ -76,7 +76,7 @@ struct GibbsArgs {
     const void* totS;            // R* [n_slots]  sum over the window of (y-c)
     const void* totQ;            // R* [n_slots]  sum over the window of (y-c)^2
     const void* xi;              // R* [K][n_slots]
-    double alpha[8], nu[8], beta0[8], beta[8];
+    double alpha[32], nu[32], beta0[32], beta[32];
     unsigned k0, k1;
     const unsigned* chain_id;    // [n_slots]
     long long sweep0;            // global index of the first sweep of this launch

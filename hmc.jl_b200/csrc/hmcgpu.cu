@@ -1,7 +1,7 @@
 // hmcgpu.cu — C ABI (include/hmcgpu.h) and kernels of the B200 Gibbs/FFBS path.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --shared (see hmc.jl_b200/build.py).
 #include "../../include/hmcgpu.h"
-#include "gibbs_kernel.cuh"
+#include "gibbs_wide_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -160,7 +160,8 @@ extern "C" int hmcgpu_ctx_sync(hmcgpu_ctx* ctx) {
     return HMCGPU_OK;
 }
 
-static bool k_supported(int K) { return K == 2 || K == 3 || K == 4; }
+static bool k_supported(int K) { return K >= 2 && K <= 32; }   // 2..4: thread-per-chain kernels; 5..32: lane-per-state kernel
+static bool k_thread(int K) { return K >= 2 && K <= 4; }
 
 #define DISPATCH_K(K, ...)                          \
     switch (K) {                                    \
@@ -170,9 +171,13 @@ static bool k_supported(int K) { return K == 2 || K == 3 || K == 4; }
         default: break;                             \
     }
 #ifdef HMC_DEV_F3   /* experiment builds: only the fp32 K=3 sweep kernels are linked */
-#define DISPATCH_RUN(pl, rc) do { if ((pl)->K == 3 && (pl)->precision == 32) rc = plan_run_t<float, 3>(pl); } while (0)
+#define DISPATCH_RUN(pl, rc) do { if ((pl)->precision == 32) { if ((pl)->wide) rc = plan_run_t<float, 0>(pl); else if ((pl)->K == 3) rc = plan_run_t<float, 3>(pl); } } while (0)
 #else
-#define DISPATCH_RUN(pl, rc) DISPATCH_K((pl)->K, { rc = ((pl)->precision == 32) ? plan_run_t<float, KK>(pl) : plan_run_t<double, KK>(pl); })
+#define DISPATCH_RUN(pl, rc)                                                                                          \
+    do {                                                                                                            \
+        if ((pl)->wide) rc = ((pl)->precision == 32) ? plan_run_t<float, 0>(pl) : plan_run_t<double, 0>(pl);       \
+        else DISPATCH_K((pl)->K, { rc = ((pl)->precision == 32) ? plan_run_t<float, KK>(pl) : plan_run_t<double, KK>(pl); }) \
+    } while (0)
 #endif
 
 // ============================================================================================ deterministic entry points
@@ -343,6 +348,155 @@ __global__ void forecast_kernel(long long B, const double* __restrict__ mu, cons
     }
 }
 
+
+// ---- runtime-K (5..32) versions of the deterministic entry points: same arithmetic, small local arrays, A read from
+//      global memory.  These are checking utilities, not hot paths.
+constexpr int kMaxK = 32;
+
+template <typename R>
+__global__ void filter_kernel_generic(int K, long long B, long long T, const double* __restrict__ y, long long ystride,
+                                      const double* __restrict__ A, const double* __restrict__ mu, const double* __restrict__ sig2,
+                                      const double* __restrict__ rho, double* __restrict__ pif, double* __restrict__ totals,
+                                      double* __restrict__ loglik) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    R pf[kMaxK], q[kMaxK], m[kMaxK], c0[kMaxK], c1[kMaxK];
+    for (int s = 0; s < K; ++s) {
+        pf[s] = (R)rho[b * K + s]; m[s] = (R)mu[b * K + s];
+        const R v = (R)sig2[b * K + s];
+        if (sizeof(R) == 4) { c0[s] = (R)(-0.72134752044448170368) / v; c1[s] = (R)(-0.5f * Real<float>::lg2(6.283185307179586f * (float)v)); }
+        else { const R sd = (R)sqrt((double)v); c0[s] = R(1) / sd; c1[s] = (R)0.3989422804014327 / sd; }
+    }
+    const double* Ab = A + b * K * K;
+    const double* yb = y + b * ystride;
+    double ll = 0.0;
+    for (long long t = 0; t < T; ++t) {
+        const R yt = (R)yb[t];
+        R mx = (R)(-3.0e38);
+        if (sizeof(R) == 4) for (int s = 0; s < K; ++s) { const R d = yt - m[s]; q[s] = fma(d * d, c0[s], c1[s]); mx = q[s] > mx ? q[s] : mx; }
+        R tot = R(0);
+        for (int s = 0; s < K; ++s) {
+            R e;
+            if (sizeof(R) == 4) e = (R)Real<float>::ex2((float)(q[s] - mx));
+            else { const R z = (yt - m[s]) * c0[s]; e = (R)exp(-0.5 * (double)(z * z)) * c1[s]; }
+            R pred = R(0);
+            for (int r = 0; r < K; ++r) pred = fma(pf[r], (R)Ab[r * K + s], pred);
+            q[s] = pred * e;
+            tot += q[s];
+        }
+        const bool ok = (tot > R(0)) && (tot < R(3.0e38));
+        for (int s = 0; s < K; ++s) pf[s] = ok ? q[s] / tot : R(1) / R(K);
+        const double lt = (sizeof(R) == 4) ? ((double)Real<float>::lg2((float)tot) + (double)mx) * 0.6931471805599453 : log((double)tot);
+        ll += lt;
+        if (totals) totals[b * T + t] = (sizeof(R) == 4) ? exp(lt) : (double)tot;
+        for (int s = 0; s < K; ++s) pif[(b * T + t) * K + s] = (double)pf[s];
+    }
+    if (loglik) loglik[b] = ll;
+}
+
+template <typename R>
+__global__ void smooth_kernel_generic(int K, long long B, long long T, const double* __restrict__ A, const double* __restrict__ pif,
+                                      double* __restrict__ pib) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    R pb[kMaxK], w[kMaxK];
+    const double* Ab = A + b * K * K;
+    for (int s = 0; s < K; ++s) { pb[s] = (R)pif[(b * T + T - 1) * K + s]; pib[(b * T + T - 1) * K + s] = (double)pb[s]; }
+    for (long long t = T - 2; t >= 0; --t) {
+        const double* f = pif + (b * T + t) * K;
+        for (int s = 0; s < K; ++s) {
+            R pred = R(0);
+            for (int r = 0; r < K; ++r) pred = fma((R)f[r], (R)Ab[r * K + s], pred);
+            w[s] = pred > R(0) ? pb[s] / pred : R(0);
+        }
+        for (int r = 0; r < K; ++r) {
+            R acc = R(0);
+            for (int s2 = 0; s2 < K; ++s2) acc = fma((R)Ab[r * K + s2], w[s2], acc);
+            pb[r] = (R)f[r] * acc;
+        }
+        for (int s = 0; s < K; ++s) pib[(b * T + t) * K + s] = (double)pb[s];
+    }
+}
+
+__global__ void sample_states_kernel_generic(int K, long long B, long long T, const double* __restrict__ A, const double* __restrict__ pif,
+                                             const double* __restrict__ piN, const double* __restrict__ u, long long* __restrict__ X) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double p[kMaxK];
+    const double* Ab = A + b * K * K;
+    auto cat = [&](double uu) { int i = 0; double c = p[0]; while (c < uu && i < K - 1) { ++i; c = __dadd_rn(c, p[i]); } return i; };
+    for (int s = 0; s < K; ++s) p[s] = piN ? piN[b * K + s] : pif[(b * T + T - 1) * K + s];
+    int x = cat(u[b * T + T - 1]);
+    X[b * T + T - 1] = x + 1;
+    for (long long k = T - 2; k >= 0; --k) {
+        double total = 0.0;
+        for (int r = 0; r < K; ++r) { p[r] = __dmul_rn(pif[(b * T + k) * K + r], Ab[r * K + x]); total = __dadd_rn(total, p[r]); }
+        const double gate = pif[(b * T + k + 1) * K + x];
+        if (gate > 2.220446049250313e-16 && total > 0.0) { for (int r = 0; r < K; ++r) p[r] = __ddiv_rn(p[r], total); }
+        else { for (int r = 0; r < K; ++r) p[r] = 1.0 / K; }
+        x = cat(u[b * T + k]);
+        X[b * T + k] = x + 1;
+    }
+}
+
+__global__ void forecast_kernel_generic(int K, long long B, const double* __restrict__ mu, const double* __restrict__ A,
+                                        const double* __restrict__ pi, const int* __restrict__ horizons, int n_h,
+                                        const double* __restrict__ yreal, double* __restrict__ out) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double v[kMaxK], nv[kMaxK];
+    const double* Ab = A + b * K * K;
+    for (int j = 0; j < n_h; ++j) {
+        for (int s = 0; s < K; ++s) v[s] = pi[b * K + s];
+        for (int h = 0; h < horizons[j]; ++h) {
+            for (int s = 0; s < K; ++s) { double acc = 0.0; for (int r = 0; r < K; ++r) acc = fma(v[r], Ab[r * K + s], acc); nv[s] = acc; }
+            for (int s = 0; s < K; ++s) v[s] = nv[s];
+        }
+        double f = 0.0;
+        for (int s = 0; s < K; ++s) f = fma(v[s], mu[b * K + s], f);
+        out[(b * n_h + j) * 2] = f;
+        out[(b * n_h + j) * 2 + 1] = f - yreal[j];
+    }
+}
+
+template <typename R>
+__global__ void draw_params_kernel_generic(int K, long long B, const long long* __restrict__ Ni, const double* __restrict__ S,
+                                           const double* __restrict__ S2, const long long* __restrict__ trans,
+                                           const double* __restrict__ xi, const double* __restrict__ alpha, const double* __restrict__ nu,
+                                           const double* __restrict__ beta, unsigned k0, unsigned k1, unsigned chain0, unsigned sweep,
+                                           double* __restrict__ sig2o, double* __restrict__ muo, double* __restrict__ rhoo,
+                                           double* __restrict__ Ao) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const RngKey key{k0, k1, chain0 + (unsigned)b};
+    R rsum = R(0);
+    for (int i = 0; i < K; ++i) {
+        const R n = (R)Ni[b * K + i];
+        const R ybar = n > R(0) ? (R)S[b * K + i] / n : R(0);
+        const R dev = ybar - (R)xi[i];
+        const R a = (R)alpha[i] + R(0.5) * n;
+        const R bb = (R)beta[i] + R(0.5) * (R)S2[b * K + i] + R(0.5) * n * (R)nu[i] / (n + (R)nu[i]) * (dev * dev);
+        R v = R(1);
+        if (a > R(0) && bb > R(0)) v = bb / gamma_mt<R>(a, key, sweep, (KIND_SIGMA << 16) | (uint32_t)i);
+        sig2o[b * K + i] = (double)v;
+        const R m = ((R)S[b * K + i] + (R)nu[i] * (R)xi[i]) / (n + (R)nu[i]);
+        const R sd = M<R>::sqrt(v / (n + (R)nu[i]));
+        const uint4 w = rng_block(key, sweep, (KIND_MU << 16), (uint32_t)(i >> 1));
+        muo[b * K + i] = (double)(m + sd * ((i & 1) ? normal_from<R>(w.z, w.w) : normal_from<R>(w.x, w.y)));
+        const R g = gamma_mt<R>(R(1), key, sweep, (KIND_RHO << 16) | (uint32_t)i);
+        rhoo[b * K + i] = (double)g;
+        rsum += g;
+        R tot = R(0);
+        for (int j = 0; j < K; ++j) {
+            const R ga = gamma_mt<R>((R)trans[(b * K + i) * K + j], key, sweep, (KIND_A << 16) | (uint32_t)(i * K + j));
+            Ao[(b * K + i) * K + j] = (double)ga;
+            tot += ga;
+        }
+        for (int j = 0; j < K; ++j) Ao[(b * K + i) * K + j] = (double)((R)Ao[(b * K + i) * K + j] / tot);
+    }
+    for (int i = 0; i < K; ++i) rhoo[b * K + i] = (double)((R)rhoo[b * K + i] / rsum);
+}
+
 __global__ void philox_kernel(long long n, const unsigned* __restrict__ ctr, const unsigned* __restrict__ key, unsigned* __restrict__ out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -373,7 +527,7 @@ struct Xfer {
 
 static int check_common(hmcgpu_ctx* ctx, int K, long long B, long long T) {
     if (!ctx) return HMCGPU_ERR_ARG;
-    if (!k_supported(K)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "K=%d not supported (2..4)", K);
+    if (!k_supported(K)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "K=%d not supported (2..32)", K);
     if (B <= 0 || T <= 0) return fail(ctx, HMCGPU_ERR_ARG, "empty batch (B=%lld, T=%lld)", B, T);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, HMCGPU_ERR_CUDA, "cudaSetDevice failed");
     tl_pool = ctx->pool;
@@ -397,6 +551,10 @@ extern "C" int hmcgpu_filter(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int6
     TRY(x.up((double*)nullptr, (size_t)B * T * K, &dp));
     if (totals) TRY(x.up((double*)nullptr, (size_t)B * T, &dt));
     if (loglik) TRY(x.up((double*)nullptr, (size_t)B, &dl));
+    if (!k_thread(K)) {
+        if (precision == 32) filter_kernel_generic<float><<<grid_for(B, 64), 64, 0, ctx->stream>>>(K, B, T, dy, ystride, dA, dmu, ds, dr, dp, dt, dl);
+        else filter_kernel_generic<double><<<grid_for(B, 64), 64, 0, ctx->stream>>>(K, B, T, dy, ystride, dA, dmu, ds, dr, dp, dt, dl);
+    }
     DISPATCH_K(K, {
         if (precision == 32) filter_kernel<float, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dy, ystride, dA, dmu, ds, dr, dp, dt, dl);
         else filter_kernel<double, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dy, ystride, dA, dmu, ds, dr, dp, dt, dl);
@@ -415,6 +573,10 @@ extern "C" int hmcgpu_smooth(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int6
     Xfer x{ctx};
     double *dA, *dp, *db;
     TRY(x.up(A, (size_t)B * K * K, &dA)); TRY(x.up(pif, (size_t)B * T * K, &dp)); TRY(x.up((double*)nullptr, (size_t)B * T * K, &db));
+    if (!k_thread(K)) {
+        if (precision == 32) smooth_kernel_generic<float><<<grid_for(B, 64), 64, 0, ctx->stream>>>(K, B, T, dA, dp, db);
+        else smooth_kernel_generic<double><<<grid_for(B, 64), 64, 0, ctx->stream>>>(K, B, T, dA, dp, db);
+    }
     DISPATCH_K(K, {
         if (precision == 32) smooth_kernel<float, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dA, dp, db);
         else smooth_kernel<double, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dA, dp, db);
@@ -435,6 +597,7 @@ extern "C" int hmcgpu_sample_states(hmcgpu_ctx* ctx, int32_t K, int64_t B, int64
     TRY(x.up(A, (size_t)B * K * K, &dA)); TRY(x.up(pif, (size_t)B * T * K, &dp)); TRY(x.up(u, (size_t)B * T, &du));
     if (piN) TRY(x.up(piN, (size_t)B * K, &dn));
     TRY(x.up((long long*)nullptr, (size_t)B * T, &dX));
+    if (!k_thread(K)) sample_states_kernel_generic<<<grid_for(B, 64), 64, 0, ctx->stream>>>(K, B, T, dA, dp, dn, du, dX);
     DISPATCH_K(K, { sample_states_kernel<KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dA, dp, dn, du, dX); });
     CU(ctx, cudaGetLastError());
     TRY(x.down(reinterpret_cast<long long*>(X), dX, (size_t)B * T));
@@ -460,6 +623,10 @@ extern "C" int hmcgpu_draw_params(hmcgpu_ctx* ctx, int32_t precision, int32_t K,
     TRY(x.up((double*)nullptr, (size_t)B * K, &o1)); TRY(x.up((double*)nullptr, (size_t)B * K, &o2));
     TRY(x.up((double*)nullptr, (size_t)B * K, &o3)); TRY(x.up((double*)nullptr, (size_t)B * K * K, &o4));
     const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+    if (!k_thread(K)) {
+        if (precision == 32) draw_params_kernel_generic<float><<<grid_for(B, 64), 64, 0, ctx->stream>>>(K, B, dN, dS, dS2, dT, dxi, dal, dnu, dbe, k0, k1, chain0, sweep, o1, o2, o3, o4);
+        else draw_params_kernel_generic<double><<<grid_for(B, 64), 64, 0, ctx->stream>>>(K, B, dN, dS, dS2, dT, dxi, dal, dnu, dbe, k0, k1, chain0, sweep, o1, o2, o3, o4);
+    }
     DISPATCH_K(K, {
         if (precision == 32) draw_params_kernel<float, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, dN, dS, dS2, dT, dxi, dal, dnu, dbe, k0, k1, chain0, sweep, o1, o2, o3, o4);
         else draw_params_kernel<double, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, dN, dS, dS2, dT, dxi, dal, dnu, dbe, k0, k1, chain0, sweep, o1, o2, o3, o4);
@@ -481,6 +648,7 @@ extern "C" int hmcgpu_forecast(hmcgpu_ctx* ctx, int32_t K, int64_t B, const doub
     int* dh;
     TRY(x.up(mu, (size_t)B * K, &dm)); TRY(x.up(A, (size_t)B * K * K, &dA)); TRY(x.up(pi, (size_t)B * K, &dp));
     TRY(x.up(yreal, (size_t)n_h, &dy)); TRY(x.up(horizons, (size_t)n_h, &dh)); TRY(x.up((double*)nullptr, (size_t)B * 2 * n_h, &dout));
+    if (!k_thread(K)) forecast_kernel_generic<<<grid_for(B, 64), 64, 0, ctx->stream>>>(K, B, dm, dA, dp, dh, n_h, dy, dout);
     DISPATCH_K(K, { forecast_kernel<KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, dm, dA, dp, dh, n_h, dy, dout); });
     CU(ctx, cudaGetLastError());
     TRY(x.down(out, dout, (size_t)B * 2 * n_h));
@@ -506,7 +674,7 @@ extern "C" int hmcgpu_philox(hmcgpu_ctx* ctx, int64_t n, const uint32_t* ctr, co
 // ---- window initialisation: HyperParams (:132-142) + makeParams (:161-195) + the statistics of X0, one block per window
 struct WinInit {          // per window, fp64
     double mean;          // ξ default and the shift c
-    double cnt[8], Sd[8], Qd[8], trans[64];
+    double cnt[32], Sd[32], Qd[32], trans[1024];
     double totS, totQ;    // sum over the window of (y-mean), (y-mean)^2
 };
 
@@ -556,7 +724,7 @@ __global__ void __launch_bounds__(256) window_init_kernel(int K, const double* _
     extern __shared__ unsigned char x0[];                 // X0, one byte per time step
     __shared__ double shd[256];
     __shared__ unsigned long long shu[256];
-    __shared__ double mu0[8];
+    __shared__ double mu0[32];
     const int w = blockIdx.x;
     const int N = wT[w];
     const double* y = y64 + wbase[w];
@@ -573,7 +741,7 @@ __global__ void __launch_bounds__(256) window_init_kernel(int K, const double* _
     double med = block_select(y, ld, N, N / 2, shu);
     if (!(N & 1)) med = 0.5 * (block_select(y, ld, N, N / 2 - 1, shu) + med);
     const double R = mx - mn, lo = med - 0.25 * R, hi = med + 0.25 * R;               // :175-176
-    if (threadIdx.x < K) mu0[threadIdx.x] = (K > 1) ? lo + (hi - lo) * ((double)threadIdx.x / (double)(K - 1)) : med;
+    if ((int)threadIdx.x < K) mu0[threadIdx.x] = (K > 1) ? lo + (hi - lo) * ((double)threadIdx.x / (double)(K - 1)) : med;
     __syncthreads();
     for (int i = threadIdx.x; i < N; i += blockDim.x) {                               // :185-187 findmax of the pdfs
         const double v = y[i * ld];
@@ -589,16 +757,18 @@ __global__ void __launch_bounds__(256) window_init_kernel(int K, const double* _
     __syncthreads();
     // statistics of X0 in serial time order (deterministic): thread i < K -> state i, thread K+j -> transition pair j
     const int tid = threadIdx.x;
-    if (tid < K) {
-        double c = 0.0, sdv = 0.0, qd = 0.0;
-        for (int i = 0; i < N; ++i)
-            if (x0[i] == tid) { const double d = y[i * ld] - mean; c += 1.0; sdv += d; qd += d * d; }
-        out[w].cnt[tid] = c; out[w].Sd[tid] = sdv; out[w].Qd[tid] = qd;
-    } else if (tid < K + K * K) {
-        const int j = tid - K, r = j / K, s2 = j % K;
-        double c = 0.0;
-        for (int i = 0; i + 1 < N; ++i) c += (x0[i] == r && x0[i + 1] == s2) ? 1.0 : 0.0;
-        out[w].trans[j] = c;
+    for (int q = tid; q < K + K * K; q += blockDim.x) {
+        if (q < K) {
+            double c = 0.0, sdv = 0.0, qd = 0.0;
+            for (int i = 0; i < N; ++i)
+                if (x0[i] == q) { const double d = y[i * ld] - mean; c += 1.0; sdv += d; qd += d * d; }
+            out[w].cnt[q] = c; out[w].Sd[q] = sdv; out[w].Qd[q] = qd;
+        } else {
+            const int j = q - K, r = j / K, s2 = j % K;
+            double c = 0.0;
+            for (int i = 0; i + 1 < N; ++i) c += (x0[i] == r && x0[i + 1] == s2) ? 1.0 : 0.0;
+            out[w].trans[j] = c;
+        }
     }
     if (tid == 0) {
         out[w].mean = mean;
@@ -732,7 +902,8 @@ struct hmcgpu_plan {
     GibbsArgs args{};
     // device buffers
     DevBuf y64, yr, wbase, wTd, wi, slot_win, slot_chain, T, ybase, warp_T, warp_pi_off, pi, pacc, cnt, trans, Sd, Qd,
-        events, cshift, xi, xi_user, chain_id, out, yfut_w, yfut, win_slot0, win_pib_off, totS, totQ;
+        events, cshift, xi, xi_user, chain_id, out, yfut_w, yfut, win_slot0, win_pib_off, totS, totQ, slot_pi_off;
+    bool wide = false;
     int n_groups = 1, n_bufs = 1;
     std::vector<cudaStream_t> gstreams;
     std::vector<cudaEvent_t> pool_events;
@@ -756,7 +927,9 @@ static int validate_problem(hmcgpu_ctx* ctx, const hmcgpu_problem* p) {
     if (!p) return fail(ctx, HMCGPU_ERR_ARG, "problem is NULL");
     if (!p->y || p->y_len < 2 || p->n_series < 1) return fail(ctx, HMCGPU_ERR_ARG, "empty series");
     if (p->n_windows < 1 || !p->win_start || !p->win_end) return fail(ctx, HMCGPU_ERR_ARG, "no windows");
-    if (!k_supported(p->K)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "K=%d not supported (2..4)", p->K);
+    if (!k_supported(p->K)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "K=%d not supported (2..32)", p->K);
+    if (!k_thread(p->K) && (p->flags & HMCGPU_FLAG_SMOOTHED_MEAN))
+        return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "smoothed means are only implemented for K <= 4");
     if (p->n_chains < 1) return fail(ctx, HMCGPU_ERR_ARG, "n_chains < 1");
     if (p->burnin < 0 || p->nrun < 1) return fail(ctx, HMCGPU_ERR_ARG, "burnin < 0 or nrun < 1");
     if (p->burnin + p->nrun > 0xffffffffLL) return fail(ctx, HMCGPU_ERR_ARG, "more than 2^32 sweeps");
@@ -793,7 +966,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         pl->max_T = std::max(pl->max_T, pl->wT[w]);
     }
     pl->pib_total = pib_total;
-    if ((long long)pl->max_T - 1 > ((1ll << (64 / K)) - 1)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "window too long for K=%d", K);
+    if (k_thread(K) && (long long)pl->max_T - 1 > ((1ll << (64 / K)) - 1)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "window too long for K=%d", K);
     pl->state_steps = sumT * nc * (p->burnin + p->nrun);
     std::iota(pl->order.begin(), pl->order.end(), 0);
     std::stable_sort(pl->order.begin(), pl->order.end(), [&](int a, int b) { return pl->wT[a] > pl->wT[b]; });
@@ -821,12 +994,15 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         }
     }
     long long pi_elems = 0;
+    pl->wide = !k_thread(K);
+    std::vector<long long> slot_off(n_slots, 0);
     for (int wp = 0; wp < n_warps; ++wp) {
         int m = 0;
         for (int l = 0; l < 32; ++l) m = std::max(m, Ts[wp * 32 + l]);
         warp_T[wp] = m;
         warp_off[wp] = pi_elems;
-        pi_elems += (long long)m * K * 32;
+        if (!pl->wide) pi_elems += (long long)m * K * 32;
+        else for (int l = 0; l < 32; ++l) { slot_off[wp * 32 + l] = pi_elems; pi_elems += (long long)Ts[wp * 32 + l] * K; }
     }
     // forecasts: realised y at end+h per window (NaN outside the series), horizons sorted ascending
     std::vector<double> yfut_w((size_t)nw * std::max(1, p->n_h), NAN);
@@ -841,7 +1017,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         }
 
     // task groups: interleaved subsets of the (longest-first) warp tasks, each driven through its own stream
-    pl->n_groups = n_warps >= 1024 ? 4 : (n_warps >= 256 ? 2 : 1);
+    pl->n_groups = pl->wide ? 1 : (n_warps >= 1024 ? 4 : (n_warps >= 256 ? 2 : 1));
     if (const char* e = getenv("HMCGPU_GROUPS")) pl->n_groups = std::max(1, std::min(8, atoi(e)));
     pl->n_groups = std::min(pl->n_groups, n_warps);
     // double-buffered draw chunks let the groups drift apart (not with the smoothing accumulators, which are shared)
@@ -874,6 +1050,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     CU(ctx, up(pl->ybase, ybase.data(), n_slots * sizeof(long long)));
     CU(ctx, up(pl->warp_T, warp_T.data(), n_warps * sizeof(int)));
     CU(ctx, up(pl->warp_pi_off, warp_off.data(), n_warps * sizeof(long long)));
+    if (pl->wide) CU(ctx, up(pl->slot_pi_off, slot_off.data(), n_slots * sizeof(long long)));
     CU(ctx, up(pl->chain_id, chain_id.data(), n_slots * sizeof(unsigned)));
     CU(ctx, up(pl->win_slot0, win_slot0.data(), nw * sizeof(int)));
     CU(ctx, up(pl->win_pib_off, pl->pib_off.data(), nw * sizeof(long long)));
@@ -923,7 +1100,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     a.warp_T = pl->warp_T.as<int>(); a.warp_pi_off = pl->warp_pi_off.as<long long>(); a.pi = pl->pi.p; a.pib_acc = pl->pacc.p;
     a.cnt = pl->cnt.as<int>(); a.trans = pl->trans.as<int>(); a.Sd = pl->Sd.p; a.Qd = pl->Qd.p; a.events = pl->events.as<int>();
     a.cshift = pl->cshift.p; a.xi = pl->xi.p; a.totS = pl->totS.p; a.totQ = pl->totQ.p; a.n_warps = n_warps;
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 32; ++i) {
         a.alpha[i] = (p->alpha && i < K) ? p->alpha[i] : 1.0;      // :137
         a.nu[i] = (p->nu && i < K) ? p->nu[i] : 1.0;               // :140
         a.beta0[i] = (p->beta0 && i < K) ? p->beta0[i] : 1.0;      // :179
@@ -956,6 +1133,7 @@ static int plan_run_t(hmcgpu_plan* pl) {
     hmcgpu_ctx* ctx = pl->ctx;
     cudaStream_t st = ctx->stream;
     const int ns = pl->n_slots, G = pl->n_groups, L = sweeps_per_launch();
+    const int Kr = pl->K;                                    // runtime K (the template K is 0 for the lane-per-state kernel)
     pl->n_launches = 0; pl->n_sweep_launches = 0; pl->sweep_ms = 0.0;
     size_t ev_used = 0;
     auto new_event = [&](cudaEvent_t* e) -> cudaError_t {
@@ -969,7 +1147,7 @@ static int plan_run_t(hmcgpu_plan* pl) {
         return cudaSuccess;
     };
     CU(ctx, cudaEventRecord(pl->ev0, st));
-    chain_init_kernel<R><<<grid_for(ns, 128), 128, 0, st>>>(K, ns, pl->slot_win.as<int>(), pl->wi.as<WinInit>(),
+    chain_init_kernel<R><<<grid_for(ns, 128), 128, 0, st>>>(Kr, ns, pl->slot_win.as<int>(), pl->wi.as<WinInit>(),
                                                             pl->xi_user.as<double>(), pl->cnt.as<int>(), pl->trans.as<int>(),
                                                             pl->Sd.as<R>(), pl->Qd.as<R>(), pl->cshift.as<R>(), pl->xi.as<R>(),
                                                             pl->totS.as<R>(), pl->totQ.as<R>(), pl->events.as<int>());
@@ -997,7 +1175,7 @@ static int plan_run_t(hmcgpu_plan* pl) {
         const R* buf = pl->out.as<R>() + (size_t)(k % pl->n_bufs) * buf_elems;
         if (pl->flags & HMCGPU_FLAG_DRAWS) {
             dim3 blk(32, 8), grd(grid_for(ns, 32), grid_for(n, 8));
-            gather_draws_kernel<R><<<grd, blk, 0, st>>>(K, pl->n_h, ns, pl->chunk, n, d0, pl->nrun, pl->n_chains, pl->slot_win.as<int>(),
+            gather_draws_kernel<R><<<grd, blk, 0, st>>>(Kr, pl->n_h, ns, pl->chunk, n, d0, pl->nrun, pl->n_chains, pl->slot_win.as<int>(),
                                                          pl->slot_chain.as<int>(), buf, pl->d_mu.as<double>(), pl->d_sig2.as<double>(),
                                                          pl->d_A.as<double>(), pl->d_pie.as<double>(), pl->d_fc.as<double>(), pl->d_ll.as<double>());
             CU(ctx, cudaGetLastError());
@@ -1011,7 +1189,7 @@ static int plan_run_t(hmcgpu_plan* pl) {
             ++pl->n_launches;
         }
         if (pl->flags & HMCGPU_FLAG_SMOOTHED_MEAN) {
-            pib_reduce_kernel<R><<<pl->n_windows, 256, 0, st>>>(K, pl->n_chains, pl->win_slot0.as<int>(), pl->wTd.as<int>(),
+            pib_reduce_kernel<R><<<pl->n_windows, 256, 0, st>>>(Kr, pl->n_chains, pl->win_slot0.as<int>(), pl->wTd.as<int>(),
                                                                 pl->warp_pi_off.as<long long>(), pl->win_pib_off.as<long long>(),
                                                                 pl->pacc.as<R>(), pl->d_pibsum.as<double>());
             CU(ctx, cudaGetLastError());
@@ -1057,7 +1235,8 @@ static int plan_run_t(hmcgpu_plan* pl) {
             }
             a.sweep0 = s0; a.n_sweeps = (int)n;
             a.task0 = g; a.task_stride = G; a.n_tasks = (pl->n_warps - g + G - 1) / G;
-            CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
+            if constexpr (K == 0) CU(ctx, (launch_gibbs_wide<R>(cfg, a, pl->K, pl->slot_pi_off.as<long long>(), gs)));
+            else CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
             ++pl->n_launches; ++pl->n_sweep_launches;
             next[g] = s0 + n;
             if (k >= 0 && next[g] == pl->burnin + std::min<long long>(pl->nrun, (k + 1) * pl->chunk)) {

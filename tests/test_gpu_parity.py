@@ -37,7 +37,7 @@ def test_philox_known_answers_on_device(ctx, oracle):
         assert out[i].tolist() == oracle.philox(ctr[i], key[i])
 
 
-@pytest.mark.parametrize("K", [2, 3, 4])
+@pytest.mark.parametrize("K", [2, 3, 4, 5, 8, 32])
 @pytest.mark.parametrize("precision,rtol", [(64, RTOL64), (32, RTOL32)])
 def test_filter_matches_oracle(ctx, oracle, K, precision, rtol):
     rng = np.random.default_rng(100 + K)
@@ -86,7 +86,7 @@ def test_smoother_matches_oracle(ctx, oracle, precision, rtol):
         np.testing.assert_allclose(g[b], pib, rtol=rtol, atol=rtol * 1e-3)
 
 
-@pytest.mark.parametrize("K", [2, 3, 4])
+@pytest.mark.parametrize("K", [2, 3, 4, 8, 32])
 def test_state_paths_bit_exact_under_injected_uniforms(ctx, oracle, K):
     rng = np.random.default_rng(31 + K)
     B, T = 64, 600
@@ -323,9 +323,96 @@ def test_error_paths(H, ctx):
         _run(H, ctx, y, [1], [60], K=3)
     assert e.value.code == -1
     with pytest.raises(H.HmcGpuError) as e:
-        _run(H, ctx, y, [1], [40], K=7)
+        _run(H, ctx, y, [1], [40], K=40)
+    assert e.value.code == -4
+    with pytest.raises(H.HmcGpuError) as e:          # smoothing accumulators exist for the thread-per-chain kernels only
+        _run(H, ctx, y, [1], [40], K=8, flags=H.FLAG_SMOOTHED_MEAN)
     assert e.value.code == -4
     with pytest.raises(H.HmcGpuError):
         _run(H, ctx, y, [10], [10], K=3)
     with pytest.raises(H.HmcGpuError):
         H.Context(99)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K = 5..32: the lane-per-state kernel (gibbs_wide_kernel) and the runtime-K deterministic entry points
+
+def _truth(K):
+    A = np.full((K, K), 0.1 / (K - 1)) + np.eye(K) * (0.9 - 0.1 / (K - 1))
+    return dict(A=A, mu=2.0 * np.arange(K), sigma2=np.full(K, 0.5))           # K=8/32 truth
+
+
+@pytest.mark.parametrize("K", [5, 8, 32])
+def test_wide_smoother_forecast_draws_match_oracle(ctx, oracle, K):
+    rng = np.random.default_rng(200 + K)
+    B, T = 6, 120
+    A, mu, s2, rho = random_params(rng, B, K)
+    y = rng.normal(0, 3, size=(B, T))
+    pif = np.stack([oracle.forward(y[b], A[b], mu[b], s2[b], rho[b]).pif for b in range(B)])
+    g = ctx.smooth(A, pif, precision=64)
+    fc = ctx.forecast(mu, A, rho, [1, 12], [0.5, -0.25])
+    for b in range(B):
+        f = oracle.forward(y[b], A[b], mu[b], s2[b], rho[b])
+        _, pib = oracle.backward(f.Pf, f.pif)
+        np.testing.assert_allclose(g[b], pib, rtol=RTOL64, atol=1e-9)
+        for j, h in enumerate((1, 12)):
+            fo, eo = oracle.forecast(mu[b], A[b], rho[b], h, (0.5, -0.25)[j])
+            assert abs(fc[b, j, 0] - fo) < 1e-11 * max(1, abs(fo)) and abs(fc[b, j, 1] - eo) < 1e-10 * max(1, abs(eo))
+    Ni = rng.integers(0, 50, size=(B, K)); S = Ni * rng.normal(3, 2, size=(B, K)); S2 = Ni * rng.uniform(0.3, 2, size=(B, K))
+    trans = rng.integers(0, 30, size=(B, K, K)) + 1
+    xi, one = np.full(K, 3.0), np.ones(K)
+    s2d, mud, rhod, Ad = ctx.draw_params(Ni, S, S2, trans, xi, one, one, 2 * one, seed=99, chain0=7, sweep=3, precision=64)
+    for b in range(B):
+        o = oracle.draw_params(Ni[b], S[b], S2[b], trans[b], xi, one, one, 2 * one, 99, 7 + b, 3)
+        np.testing.assert_allclose(s2d[b], o[0], rtol=1e-9)
+        np.testing.assert_allclose(mud[b], o[1], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(rhod[b], o[2], rtol=1e-9)
+        np.testing.assert_allclose(Ad[b], o[3], rtol=1e-9)
+
+
+@pytest.mark.parametrize("K,T", [(5, 150), (8, 200), (16, 160), (32, 260)])
+def test_wide_gibbs_first_sweeps_follow_the_oracle_chain(H, ctx, oracle, K, T):
+    """fp64 lane-per-state chain vs the oracle chain on the same Philox streams (several chains: sub-warp groups)."""
+    y, _ = synth_hmm(T + 12, seed=5 + K, **_truth(K))
+    hs = (1, 12)
+    nch = 5
+    o = _run(H, ctx, y, [1, 3], [T, T - 17], K=K, n_chains=nch, burnin=1, nrun=4, seed=31, horizons=hs, precision=64,
+             flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_LOGLIK)
+    assert o.events == 0
+    for w, (s, e) in enumerate(((1, T), (3, T - 17))):
+        for c in range(nch):
+            r = oracle.gibbs(y[s - 1:e], K, 1, 4, seed=31, chain=w * nch + c, horizons=hs, y_future=[y[e - 1 + h] for h in hs],
+                             flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM)
+            sl = slice(c * 4, (c + 1) * 4)
+            np.testing.assert_allclose(o.mu[w][:, sl].T, r.mu, rtol=1e-7, atol=1e-9)
+            np.testing.assert_allclose(o.sigma2[w][:, sl].T, r.sigma2, rtol=1e-7)
+            np.testing.assert_allclose(np.transpose(o.A[w][:, :, sl], (2, 1, 0)), r.A, rtol=1e-7, atol=1e-12)
+            np.testing.assert_allclose(o.pi_end[w][:, sl].T, r.pi_end, rtol=1e-6, atol=1e-12)
+            np.testing.assert_allclose(o.forecasts[w][:, sl].T, r.forecasts, rtol=1e-7, atol=1e-8)
+            np.testing.assert_allclose(o.loglik[w][sl], r.loglik, rtol=1e-8)
+
+
+def test_wide_gibbs_fp32_posterior_matches_oracle(H, ctx, oracle):
+    """fp32 lane-per-state kernel: pooled posterior means vs the oracle's under identical settings (K=8 mixes slowly from
+    the makeParams start, so both are compared to each other, not to the generating truth)."""
+    K = 8
+    tr = _truth(K)
+    y, _ = synth_hmm(612, seed=3, **tr)
+    burn, nrun = 300, 200
+    o = _run(H, ctx, y, [1], [600], K=K, n_chains=96, burnin=burn, nrun=nrun, seed=4, horizons=(1, 12), precision=32,
+             flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY)
+    m = o.summary_mean[0]
+    assert o.events == 0 and np.isfinite(m).all()
+    outs, _ = oracle.gibbs_batch([dict(y=y[:600], K=K, burnin=burn, nrun=nrun, seed=8, chain=c, horizons=(1, 12),
+                                       y_future=[y[600], y[611]]) for c in range(48)])
+    om = np.concatenate([r.mu for r in outs]).mean(0)
+    os2 = np.concatenate([r.sigma2 for r in outs]).mean(0)
+    oA = np.concatenate([r.A for r in outs]).mean(0)
+    ofc = np.concatenate([r.forecasts for r in outs]).mean(0)
+    assert np.all(np.diff(m[0:K]) > 0)
+    np.testing.assert_allclose(m[0:K], om, atol=0.35)
+    np.testing.assert_allclose(m[K:2 * K], os2, rtol=0.35, atol=0.15)
+    A = m[2 * K:2 * K + K * K].reshape(K, K).T                 # summary index s*K+r -> A[r, s]
+    np.testing.assert_allclose(A, oA, atol=0.06)
+    np.testing.assert_allclose(A.sum(1), 1.0, atol=1e-4)
+    np.testing.assert_allclose(m[3 * K + K * K:3 * K + K * K + 4], ofc, atol=0.3)
