@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-HEADERS = [os.path.join(CSRC, f) for f in ("gibbs_kernel.cuh", "gibbs_wide_kernel.cuh", "hmm_device.cuh", "rng.cuh")] + [
+HEADERS = [os.path.join(CSRC, f) for f in ("gibbs_kernel.cuh", "gibbs_pair_kernel.cuh", "gibbs_wide_kernel.cuh", "hmm_device.cuh", "rng.cuh")] + [
     os.path.join(HERE, "..", "include", "hmcgpu.h")]
 LIB = os.path.join(HERE, "lib", "libhmcgpu.so")
 TAG = os.environ.get("HMC_TAG")             # experiment knob: build/load a side library lib/libhmcgpu_<tag>.so ...
@@ -21,7 +21,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O2",
          "-Xptxas", "-v", "--fmad=true"]
 UNITS = [("hmcgpu", "hmcgpu.cu", [])] + [
-    (f"gibbs_{r}_{k}", "gibbs_inst.cu", [f"-DHMC_R={r}", f"-DHMC_K={k}"]) for r in ("float", "double") for k in (2, 3, 4)] + [
+    (f"gibbs_{r}_{k}", "gibbs_inst.cu", [f"-DHMC_R={r}", f"-DHMC_K={k}"] + (["-DHMC_WITH_PAIR"] if r == "float" else []))
+    for r in ("float", "double") for k in (2, 3, 4)] + [
     (f"gibbs_wide_{r}", "gibbs_wide_inst.cu", [f"-DHMC_R={r}"]) for r in ("float", "double")]
 
 

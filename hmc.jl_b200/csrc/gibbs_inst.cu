@@ -2,6 +2,9 @@
 // compiled with -DHMC_R=<float|double> -DHMC_K=<2|3|4> (hmc.jl_b200/build.py builds the six units in parallel).
 #include <algorithm>
 #include "gibbs_kernel.cuh"
+#ifdef HMC_WITH_PAIR
+#include "gibbs_pair_kernel.cuh"
+#endif
 
 namespace hmc {
 
@@ -41,6 +44,25 @@ template <typename R, int K> int gibbs_capacity_warps(const GibbsLaunch& cfg) {
 }
 
 template cudaError_t launch_gibbs<HMC_R, HMC_K>(const GibbsLaunch&, const GibbsArgs&, cudaStream_t);
+
+#ifdef HMC_WITH_PAIR
+// fp32 only: two chains per thread, packed FP32x2 arithmetic (gibbs_pair_kernel.cuh); a task is 64 chains
+template <int K> cudaError_t launch_gibbs_pair(const GibbsLaunch& cfg, const GibbsArgs& a, cudaStream_t st) {
+    const unsigned grid = (unsigned)((a.n_tasks + kGibbsThreads / 32 - 1) / (kGibbsThreads / 32));
+    const bool ll = cfg.flags & 16u;
+    auto go = [&](auto kern, size_t smem) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, kGibbsThreads, smem, st>>>(a);
+        return cudaGetLastError();
+    };
+    if (wide_rows<K>(cfg)) return ll ? go(gibbs_pair_kernel<K, true, true>, kPairSmemBytes<K, true>()) : go(gibbs_pair_kernel<K, false, true>, kPairSmemBytes<K, true>());
+    return ll ? go(gibbs_pair_kernel<K, true, false>, kPairSmemBytes<K, false>()) : go(gibbs_pair_kernel<K, false, false>, kPairSmemBytes<K, false>());
+}
+template cudaError_t launch_gibbs_pair<HMC_K>(const GibbsLaunch&, const GibbsArgs&, cudaStream_t);
+#endif
 template int gibbs_capacity_warps<HMC_R, HMC_K>(const GibbsLaunch&);
 
 }  // namespace hmc

@@ -251,21 +251,84 @@ struct GibbsWarp {
         ll = R(0);
         const R* yp = ch.y0;
         R* pip = ch.pi0;
+        // fp32: the K states are processed as K/2 packed pairs (+ one scalar state when K is odd) with FFMA2/FMUL2/FADD2:
+        // the kernel is bound by instruction issue, and the packed forms halve the slots of the emission quadratic, the
+        // K x K prediction and the normalisation.  Same operations and roundings as the scalar form (Emission/forward_step).
+        constexpr int KP = K / 2;
+        constexpr bool kOdd = (K & 1) != 0;
+        f2 negmu2[KP > 0 ? KP : 1], q2[KP > 0 ? KP : 1], c2[KP > 0 ? KP : 1], A2[K][KP > 0 ? KP : 1];
+        float negmu_l = 0.f, q_l = 0.f, c_l = 0.f, A_l[K];
+        if constexpr (sizeof(R) == 4) {
+#pragma unroll
+            for (int p = 0; p < KP; ++p) {
+                negmu2[p] = mk2(-(float)em.mu[2 * p], -(float)em.mu[2 * p + 1]);
+                q2[p] = mk2((float)em.q[2 * p], (float)em.q[2 * p + 1]);
+                c2[p] = mk2((float)em.c[2 * p], (float)em.c[2 * p + 1]);
+#pragma unroll
+                for (int r = 0; r < K; ++r) A2[r][p] = mk2((float)ch.A[r][2 * p], (float)ch.A[r][2 * p + 1]);
+            }
+            if (kOdd) {
+                negmu_l = -(float)em.mu[K - 1]; q_l = (float)em.q[K - 1]; c_l = (float)em.c[K - 1];
+#pragma unroll
+                for (int r = 0; r < K; ++r) A_l[r] = (float)ch.A[r][K - 1];
+            }
+        }
         auto step = [&](int j, int u) {
             if (!ragged || j >= ch.off) {
                 const R yt = ld_ro(yp + u * yld);
-                R e[K];
-                const R m2 = em.eval(yt, e);
-                bool ok;
-                const R tot = forward_step<R, K>(ch.A, e, pf, ok);
-                if (CHECKED && !ok) {
-                    ++events;
+                if constexpr (sizeof(R) == 4) {
+                    const f2 y2 = splat2((float)yt);
+                    f2 l2[KP > 0 ? KP : 1];
+                    float l_l = -3.0e38f;
 #pragma unroll
-                    for (int s = 0; s < K; ++s) pf[s] = R(1) / R(K);
-                }
-                if (LOGLIK) {
-                    if (sizeof(R) == 4) ll += (Real<float>::lg2((float)tot) + (float)m2) * 0.6931471805599453f;
-                    else ll += (R)log((double)tot);
+                    for (int p = 0; p < KP; ++p) { const f2 d = y2 + negmu2[p]; l2[p] = fma2(d * d, q2[p], c2[p]); }
+                    if (kOdd) { const float d = (float)yt + negmu_l; l_l = fmaf(d * d, q_l, c_l); }
+                    float m2 = l_l;
+#pragma unroll
+                    for (int p = 0; p < KP; ++p) m2 = fmaxf(m2, fmaxf(l2[p].v.x, l2[p].v.y));
+                    const f2 nm = splat2(-m2);
+                    f2 qq2[KP > 0 ? KP : 1];
+                    float qq_l = 0.f;
+#pragma unroll
+                    for (int p = 0; p < KP; ++p) {
+                        const f2 a = l2[p] + nm;
+                        const f2 e = mk2(Real<float>::ex2(a.v.x), Real<float>::ex2(a.v.y));
+                        f2 pred = splat2((float)pf[0]) * A2[0][p];
+#pragma unroll
+                        for (int r = 1; r < K; ++r) pred = fma2(splat2((float)pf[r]), A2[r][p], pred);
+                        qq2[p] = pred * e;
+                    }
+                    if (kOdd) {
+                        const float e = Real<float>::ex2(l_l - m2);
+                        float pred = (float)pf[0] * A_l[0];
+#pragma unroll
+                        for (int r = 1; r < K; ++r) pred = fmaf((float)pf[r], A_l[r], pred);
+                        qq_l = pred * e;
+                    }
+                    float tot = kOdd ? qq_l : 0.f;
+#pragma unroll
+                    for (int p = 0; p < KP; ++p) tot += qq2[p].v.x + qq2[p].v.y;
+                    const f2 inv = splat2(Real<float>::rcp(tot));
+#pragma unroll
+                    for (int p = 0; p < KP; ++p) { const f2 r2 = qq2[p] * inv; pf[2 * p] = (R)r2.v.x; pf[2 * p + 1] = (R)r2.v.y; }
+                    if (kOdd) pf[K - 1] = (R)(qq_l * inv.v.x);
+                    if (CHECKED && !((tot > 0.f) && (tot < 3.0e38f))) {
+                        ++events;
+#pragma unroll
+                        for (int s = 0; s < K; ++s) pf[s] = R(1) / R(K);
+                    }
+                    if (LOGLIK) ll += (R)((Real<float>::lg2(tot) + m2) * 0.6931471805599453f);
+                } else {
+                    R e[K];
+                    em.eval(yt, e);
+                    bool ok;
+                    const R tot = forward_step<R, K>(ch.A, e, pf, ok);
+                    if (CHECKED && !ok) {
+                        ++events;
+#pragma unroll
+                        for (int s = 0; s < K; ++s) pf[s] = R(1) / R(K);
+                    }
+                    if (LOGLIK) ll += (R)log((double)tot);
                 }
 #pragma unroll
                 for (int s = 0; s < K; ++s) st_stream(pip + (u * K + s) * 32, pf[s]);

@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --shared (see hmc.jl_b200/build.py).
 #include "../../include/hmcgpu.h"
 #include "gibbs_wide_kernel.cuh"
+#include "gibbs_pair_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -904,6 +905,7 @@ struct hmcgpu_plan {
     DevBuf y64, yr, wbase, wTd, wi, slot_win, slot_chain, T, ybase, warp_T, warp_pi_off, pi, pacc, cnt, trans, Sd, Qd,
         events, cshift, xi, xi_user, chain_id, out, yfut_w, yfut, win_slot0, win_pib_off, totS, totQ, slot_pi_off;
     bool wide = false;
+    bool pair = false;   // fp32 paired kernel: a task is 64 chain slots (two chains per thread)
     int n_groups = 1, n_bufs = 1;
     std::vector<cudaStream_t> gstreams;
     std::vector<cudaEvent_t> pool_events;
@@ -971,10 +973,20 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     std::iota(pl->order.begin(), pl->order.end(), 0);
     std::stable_sort(pl->order.begin(), pl->order.end(), [&](int a, int b) { return pl->wT[a] > pl->wT[b]; });
 
-    // slots: windows by decreasing T, chains consecutive; padded to a multiple of 32
+    // slots: windows by decreasing T, chains consecutive; padded to a multiple of the task size (32 chains per warp task,
+    // 64 for the fp32 paired kernel, which needs an even number of chains per window so that a pair shares its window)
+    pl->wide = !k_thread(K);
+    pl->pair = !pl->wide && p->precision == 32 && nc % 2 == 0 && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN);
+    // Two chains per thread cut the instruction count by 30 % but need 168 registers (12 warps per SM): measured slower
+    // than the scalar kernel unless the batch is far wider than the machine, so it is opt-in.
+    {
+        const char* e = getenv("HMCGPU_PAIR");
+        pl->pair = pl->pair && e && atoi(e) != 0;
+    }
+    const int ts = pl->pair ? 64 : 32;
     const long long n_real = (long long)nw * nc;
-    const int n_slots = (int)((n_real + 31) / 32 * 32);
-    const int n_warps = n_slots / 32;
+    const int n_slots = (int)((n_real + ts - 1) / ts * ts);
+    const int n_warps = n_slots / ts;                       // number of warp tasks
     pl->n_slots = n_slots; pl->n_warps = n_warps;
     std::vector<int> slot_win(n_slots, -1), slot_chain(n_slots, 0), Ts(n_slots, 0), win_slot0(nw), warp_T(n_warps, 0);
     std::vector<long long> ybase(n_slots, 0), warp_off(n_warps, 0), wbase(nw);
@@ -994,15 +1006,14 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         }
     }
     long long pi_elems = 0;
-    pl->wide = !k_thread(K);
     std::vector<long long> slot_off(n_slots, 0);
     for (int wp = 0; wp < n_warps; ++wp) {
         int m = 0;
-        for (int l = 0; l < 32; ++l) m = std::max(m, Ts[wp * 32 + l]);
+        for (int l = 0; l < ts; ++l) m = std::max(m, Ts[wp * ts + l]);
         warp_T[wp] = m;
         warp_off[wp] = pi_elems;
-        if (!pl->wide) pi_elems += (long long)m * K * 32;
-        else for (int l = 0; l < 32; ++l) { slot_off[wp * 32 + l] = pi_elems; pi_elems += (long long)Ts[wp * 32 + l] * K; }
+        if (!pl->wide) pi_elems += (long long)m * K * ts;
+        else for (int l = 0; l < ts; ++l) { slot_off[wp * ts + l] = pi_elems; pi_elems += (long long)Ts[wp * ts + l] * K; }
     }
     // forecasts: realised y at end+h per window (NaN outside the series), horizons sorted ascending
     std::vector<double> yfut_w((size_t)nw * std::max(1, p->n_h), NAN);
@@ -1235,8 +1246,14 @@ static int plan_run_t(hmcgpu_plan* pl) {
             }
             a.sweep0 = s0; a.n_sweeps = (int)n;
             a.task0 = g; a.task_stride = G; a.n_tasks = (pl->n_warps - g + G - 1) / G;
-            if constexpr (K == 0) CU(ctx, (launch_gibbs_wide<R>(cfg, a, pl->K, pl->slot_pi_off.as<long long>(), gs)));
-            else CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
+            if constexpr (K == 0) {
+                CU(ctx, (launch_gibbs_wide<R>(cfg, a, pl->K, pl->slot_pi_off.as<long long>(), gs)));
+            } else if constexpr (std::is_same<R, float>::value) {
+                if (pl->pair) CU(ctx, (launch_gibbs_pair<K>(cfg, a, gs)));
+                else CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
+            } else {
+                CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
+            }
             ++pl->n_launches; ++pl->n_sweep_launches;
             next[g] = s0 + n;
             if (k >= 0 && next[g] == pl->burnin + std::min<long long>(pl->nrun, (k + 1) * pl->chunk)) {

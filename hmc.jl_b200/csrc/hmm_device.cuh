@@ -6,6 +6,14 @@
 
 namespace hmc {
 
+// Blackwell packed two-wide fp32 arithmetic (FFMA2 / FMUL2 / FADD2: one issue slot, two results)
+struct f2 { float2 v; };
+__device__ __forceinline__ f2 mk2(float a, float b) { f2 r; r.v = make_float2(a, b); return r; }
+__device__ __forceinline__ f2 splat2(float a) { return mk2(a, a); }
+__device__ __forceinline__ f2 operator+(f2 a, f2 b) { f2 r; r.v = __fadd2_rn(a.v, b.v); return r; }
+__device__ __forceinline__ f2 operator*(f2 a, f2 b) { f2 r; r.v = __fmul2_rn(a.v, b.v); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r; }
+
 template <typename R> struct Real;
 template <> struct Real<float> {
     static __device__ __forceinline__ float ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
