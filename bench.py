@@ -224,7 +224,7 @@ def main():
     ap.add_argument("--nrun", type=int, default=1000)
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--traffic", type=float, default=2.53e9,
+    ap.add_argument("--traffic", type=float, default=2.52e9,
                     help="dram__bytes_read+write per sweep-kernel launch from the ncu --set full capture "
                          "(profiles/r1_gibbs_sweeps_ncu_full.txt: one task group of 1000 warp tasks x 16 sweeps = 1.79e8 state-steps)")
     args = ap.parse_args()
