@@ -6,6 +6,6 @@ api.py (mirror of Hmc.estopt / Hmc.estimatemodel), julia/HmcGPU.jl (the ccall bi
 """
 from . import build  # noqa: F401
 from .api import (EstOpt, estimatemodel, estimate_windows, shard_windows, expanding_windows,  # noqa: F401
-                  gather_window_summaries, saveresults, write_summaries)
+                  gather_window_summaries, saveresults, write_summaries, forecastinsample)
 from .binding import (Context, HmcGpuError, Plan, ProblemSpec, estimate, estimate_multi, load, lib_path,  # noqa: F401
                       FLAG_REF_Q1, FLAG_DRAWS, FLAG_SUMMARY, FLAG_SMOOTHED_MEAN, FLAG_LOGLIK, SYMBOLS)

@@ -218,3 +218,31 @@ def write_summaries(out, K: int, horizons: Sequence[int], dates: Sequence, direc
                 f.write(",".join([str(d)] + [repr(float(v)) for v in row]) + "\n")
         paths[name] = path
     return paths
+
+
+def forecastinsample(opt: EstOpt, horizon_index: int = -1, ctx: Optional[B.Context] = None):
+    """GPU version of the reference's in-sample table (forecastinsample + saveinsampleforecasts, src/Hmc.jl:683-705;
+    the reference's own function is stale/un-callable): one full-sample estimation, then per date t of the sample the
+    posterior means of the h-step forecast pib[j,t,:]' A_j^h mu_j, its error vs y[t+h], y[t], y[t+h] and the smoothed state
+    probabilities.  Returns a dict of columns: date, forecast, forecasterror, current, future, s1..sD."""
+    own = ctx is None
+    ctx = ctx or B.Context(opt.device)
+    try:
+        sr = opt.sampleRange
+        y = np.asarray(opt.rawdata, dtype=np.float64)
+        spec = B.ProblemSpec(y, [sr[0]], [sr[-1]], K=opt.D, n_chains=opt.n_chains, burnin=opt.burnin, nrun=opt.Nrun,
+                             seed=opt.seed, horizons=list(opt.horizons), precision=opt.precision,
+                             flags=B.FLAG_REF_Q1 | B.FLAG_SMOOTHED_MEAN)
+        o = B.estimate(ctx, spec)
+    finally:
+        if own:
+            ctx.close()
+    h = list(opt.horizons)[horizon_index]
+    fc = o.insample_forecast_mean[0][:, horizon_index]
+    idx = np.arange(sr[0], sr[-1] + 1)                       # 1-based dates of the sample
+    fut = np.array([y[i - 1 + h] if i - 1 + h < len(y) else np.nan for i in idx])
+    table = {"date": [opt.dates[i - 1] for i in idx] if opt.dates is not None else idx.tolist(),
+             "forecast": fc, "forecasterror": fc - fut, "current": y[idx - 1], "future": fut}
+    for k in range(opt.D):
+        table[f"s{k + 1}"] = o.pib_mean[0][:, k]
+    return table

@@ -46,7 +46,7 @@ class Problem(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [("mu", _dp), ("sigma2", _dp), ("A", _dp), ("pi_end", _dp), ("forecasts", _dp), ("loglik", _dp),
-                ("summary_mean", _dp), ("summary_var", _dp), ("pib_mean", _dp), ("status", _i32p),
+                ("summary_mean", _dp), ("summary_var", _dp), ("pib_mean", _dp), ("insample_forecast_mean", _dp), ("status", _i32p),
                 ("gpu_ms", C.c_double), ("sweep_kernel_ms", C.c_double), ("n_launches", C.c_int64),
                 ("n_sweep_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("state_steps", C.c_int64)]
@@ -226,7 +226,7 @@ class ProblemSpec:
         R = self.n_chains * self.nrun
         F = 3 * K + K * K + 2 * nh + 1
         o = SimpleNamespace(mu=None, sigma2=None, A=None, pi_end=None, forecasts=None, loglik=None, summary_mean=None,
-                            summary_var=None, pib_mean=None, status=np.zeros((nw, self.n_chains), dtype=np.int32))
+                            summary_var=None, pib_mean=None, insample_forecast_mean=None, status=np.zeros((nw, self.n_chains), dtype=np.int32))
         if self.flags & FLAG_DRAWS:
             # Julia column-major (R x K) per window == C arrays [window][k][draw]
             o.mu = np.empty((nw, K, R)); o.sigma2 = np.empty((nw, K, R)); o.A = np.empty((nw, K, K, R))
@@ -237,8 +237,9 @@ class ProblemSpec:
             o.summary_mean = np.empty((nw, F)); o.summary_var = np.empty((nw, F))
         if self.flags & FLAG_SMOOTHED_MEAN:
             o.pib_mean = np.empty(int(self.T.sum()) * K)
+            o.insample_forecast_mean = np.empty(int(self.T.sum()) * nh) if nh else None
         res = Result(_p(o.mu), _p(o.sigma2), _p(o.A), _p(o.pi_end), _p(o.forecasts), _p(o.loglik), _p(o.summary_mean),
-                     _p(o.summary_var), _p(o.pib_mean), _p(o.status, _i32p), 0, 0, 0, 0, 0, 0, 0)
+                     _p(o.summary_var), _p(o.pib_mean), _p(o.insample_forecast_mean), _p(o.status, _i32p), 0, 0, 0, 0, 0, 0, 0)
         return o, res
 
     def finish(self, o, res, rc):
@@ -252,6 +253,12 @@ class ProblemSpec:
                 parts.append(o.pib_mean[off:off + n * K].reshape(K, n).T)
                 off += n * K
             o.pib_mean = parts
+        if o.insample_forecast_mean is not None:   # per-window [N_w, n_h]
+            nh, off, parts = self.n_h, 0, []
+            for n in self.T:
+                parts.append(o.insample_forecast_mean[off:off + n * nh].reshape(nh, n).T)
+                off += n * nh
+            o.insample_forecast_mean = parts
         return o
 
 

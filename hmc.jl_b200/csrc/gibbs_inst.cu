@@ -29,8 +29,9 @@ template <typename R, int K> cudaError_t launch_gibbs(const GibbsLaunch& cfg, co
         kern<<<grid, kGibbsThreads, smem, st>>>(a);
         return cudaGetLastError();
     };
-    if (wide_rows<K>(cfg)) return with_variant<R, K, true>(cfg, [&](auto kern) { return go(kern, kGibbsSmemBytes<R, K, true>()); });
-    return with_variant<R, K, false>(cfg, [&](auto kern) { return go(kern, kGibbsSmemBytes<R, K, false>()); });
+    const bool smooth = cfg.flags & 8u;
+    if (wide_rows<K>(cfg)) return with_variant<R, K, true>(cfg, [&](auto kern) { return go(kern, gibbs_smem_bytes<R, K, true>(smooth, cfg.n_h)); });
+    return with_variant<R, K, false>(cfg, [&](auto kern) { return go(kern, gibbs_smem_bytes<R, K, false>(smooth, cfg.n_h)); });
 }
 
 template <typename R, int K> int gibbs_capacity_warps(const GibbsLaunch& cfg) {
@@ -39,8 +40,8 @@ template <typename R, int K> int gibbs_capacity_warps(const GibbsLaunch& cfg) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGibbsThreads, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
         return per_sm * cfg.sm_count * (kGibbsThreads / 32);
     };
-    if (wide_rows<K>(cfg)) return with_variant<R, K, true>(cfg, [&](auto kern) { return q(kern, kGibbsSmemBytes<R, K, true>()); });
-    return with_variant<R, K, false>(cfg, [&](auto kern) { return q(kern, kGibbsSmemBytes<R, K, false>()); });
+    if (wide_rows<K>(cfg)) return with_variant<R, K, true>(cfg, [&](auto kern) { return q(kern, gibbs_smem_bytes<R, K, true>(cfg.flags & 8u, cfg.n_h)); });
+    return with_variant<R, K, false>(cfg, [&](auto kern) { return q(kern, gibbs_smem_bytes<R, K, false>(cfg.flags & 8u, cfg.n_h)); });
 }
 
 template cudaError_t launch_gibbs<HMC_R, HMC_K>(const GibbsLaunch&, const GibbsArgs&, cudaStream_t);

@@ -66,6 +66,7 @@ struct GibbsArgs {
     const long long* warp_pi_off;// [n_warps] element offset of the warp's pif tile
     void* pi;                    // R*  pif spill: tile[(row*K + k)*32 + lane]
     void* pib_acc;               // R*  same layout, smoothed-probability sums of this chunk (SMOOTH only)
+    void* fc_acc;                // R*  in-sample forecast sums of this chunk: tile[(row*n_h + j)*32 + lane] at offset warp_pi_off/K*n_h
     // chain state between launches
     int* cnt;                    // [K][n_slots]
     int* trans;                  // [K*K][n_slots]
@@ -111,17 +112,20 @@ template <int K, bool WIDE> struct TransPack {
     __device__ __forceinline__ int get(int i, int j) const { return (int)((row[i] >> (kBits * j)) & (Row)kMaxT); }
 };
 
+// What the backward step needs once X_{t+1} = x is known, fetched with one (fp32, K<=3) vector load from shared memory
+// instead of K+1 register selects: column x of A and the packed-counter increment of destination x.
+template <typename R, int K, bool WIDE> struct alignas(16) GibbsEntry {
+    R a[K];
+    typename TransPack<K, WIDE>::Row inc;
+};
+template <typename R, int K, bool WIDE> __host__ __device__ constexpr size_t gibbs_smem_bytes(bool smooth, int n_h);
+
 template <typename R, int K, bool SMOOTH, bool LOGLIK, bool WIDE>
 struct GibbsWarp {
     using Pack = TransPack<K, WIDE>;
     using Row = typename Pack::Row;
 
-    // What the backward step needs once X_{t+1} = x is known, fetched with one (fp32, K<=3) vector load from shared
-    // memory instead of K+1 register selects: column x of A and the packed-counter increment of destination x.
-    struct alignas(16) Entry {
-        R a[K];
-        Row inc;
-    };
+    using Entry = GibbsEntry<R, K, WIDE>;
 
     // per-sweep constants of one chain
     struct Chain {
@@ -134,6 +138,9 @@ struct GibbsWarp {
         const R* y0;              // row j -> y0[j*yld]
         R* pi0;                   // row j, state k -> pi0[(j*K + k)*32]
         R* pacc0;
+        R* facc0;                 // in-sample forecast sums (SMOOTH): row j, horizon h -> facc0[(j*n_hi + h)*32]
+        unsigned mh_off;          // shared memory (bytes): this thread's A^h mu vectors, mh[(h*K + s)*kGibbsThreads]
+        int n_hi;                 // horizons with in-sample forecasts (0 = none)
         unsigned tab_off;         // shared memory (bytes): tab[x*kGibbsThreads] = {A[:,x], 1 << (kBits*x)} of this thread's chain
         unsigned ring_off;        // shared memory (bytes): this warp's ring of kRing groups x 4 rows x K x 32 lanes (HMC_ASYNC)
     };
@@ -204,8 +211,19 @@ struct GibbsWarp {
     // one backward step at loop row j: draw X_t | X_{t+1} (src/Hmc.jl:466-481 in the pif form), update the statistics.
     // Quirk Q5 (:472-480: p = 1/D when total = pif[t+1, x_{t+1}] <= eps()) practically never fires.  GATED = handle it
     // in place; otherwise only record it in `bad` and let the caller redo the pass gated (counter-based RNG: same draws).
+    // in-sample forecast of the row whose smoothed marginal is pb: sum_s pb[s] (A^h mu)[s] for every horizon (:683-699)
+    static __device__ __forceinline__ void insample_accumulate(const Chain& ch, const R (&pb)[K], R* __restrict__ fap) {
+        const R* mh = reinterpret_cast<const R*>(smem_base() + ch.mh_off);
+        for (int j = 0; j < ch.n_hi; ++j) {
+            R f = R(0);
+#pragma unroll
+            for (int s = 0; s < K; ++s) f = fma(pb[s], mh[(j * K + s) * kGibbsThreads], f);
+            st_stream(fap + j * 32, ld_stream(fap + j * 32) + f);
+        }
+    }
+
     template <bool GATED>
-    static __device__ __forceinline__ void back_step(Back& b, const Chain& ch, const R (&pt)[K], R* __restrict__ pap,
+    static __device__ __forceinline__ void back_step(Back& b, const Chain& ch, const R (&pt)[K], R* __restrict__ pap, R* __restrict__ fap,
                                                       R yt, uint32_t word, bool save, bool& bad) {
         R p[K];
 #pragma unroll
@@ -225,6 +243,7 @@ struct GibbsWarp {
             if (save) {
 #pragma unroll
                 for (int s = 0; s < K; ++s) st_stream(pap + ch.rank[s] * 32, ld_stream(pap + ch.rank[s] * 32) + b.pb[s]);
+                insample_accumulate(ch, b.pb, fap);
             }
         }
         commit(b, ch, lt, pt, yt, false);
@@ -390,6 +409,7 @@ struct GibbsWarp {
                 if (save) {
 #pragma unroll
                     for (int s = 0; s < K; ++s) st_stream(pap + ch.rank[s] * 32, ld_stream(pap + ch.rank[s] * 32) + pf[s]);
+                    insample_accumulate(ch, b.pb, ch.facc0 + (size_t)(Tw - 1) * ch.n_hi * 32);
                 }
             }
             commit(b, ch, lt, pf, ld_ro(yp), true);
@@ -404,7 +424,9 @@ struct GibbsWarp {
             yt = (!ragged || i + u < T) ? ld_ro(yp - (u + 1) * ys) : R(0);
         };
 #define HMC_BACK(u, word, PT, YT)                                                                                      \
-    if (!ragged || i + (u) < T) back_step<GATED>(b, ch, PT, SMOOTH ? pap - ((u) + 1) * K * 32 : nullptr, YT, (word), save, bad);
+    if (!ragged || i + (u) < T)                                                                                          \
+        back_step<GATED>(b, ch, PT, SMOOTH ? pap - ((u) + 1) * K * 32 : nullptr,                                         \
+                         SMOOTH ? ch.facc0 + (size_t)(Tw - 1 - (i + (u))) * ch.n_hi * 32 : nullptr, YT, (word), save, bad);
         {
             R p0[K], p1[K], p2[K], y0, y1, y2;
             if (Tw > 1) load_row(0, p0, y0);
@@ -492,6 +514,9 @@ struct GibbsWarp {
         ch.yld = a.yld;
         ch.pi0 = reinterpret_cast<R*>(a.pi) + a.warp_pi_off[warp] + lane;
         ch.pacc0 = SMOOTH ? reinterpret_cast<R*>(a.pib_acc) + a.warp_pi_off[warp] + lane : nullptr;
+        ch.n_hi = (SMOOTH && a.fc_acc) ? a.n_h : 0;
+        ch.facc0 = ch.n_hi ? reinterpret_cast<R*>(a.fc_acc) + a.warp_pi_off[warp] / K * ch.n_hi + lane : nullptr;
+        ch.mh_off = (unsigned)(gibbs_smem_bytes<R, K, WIDE>(false, 0) + threadIdx.x * sizeof(R));
         ch.y0 = reinterpret_cast<const R*>(a.y) + a.ybase[slot] - (long long)ch.off * ch.yld;
         ch.c = reinterpret_cast<const R*>(a.cshift)[slot];
         ch.tab_off = (unsigned)(threadIdx.x * sizeof(Entry));
@@ -594,6 +619,31 @@ struct GibbsWarp {
                 if (LOGLIK) o[(size_t)(f0 + 2 * a.n_h) * cs] = ll;
             }
 
+            if (SMOOTH && save && ch.n_hi > 0) {
+                // A^h mu for every requested horizon (chain labels), read back by the in-sample forecasts of the backward pass
+                R* mh = reinterpret_cast<R*>(smem_base() + ch.mh_off);
+                R v[K];
+#pragma unroll
+                for (int s = 0; s < K; ++s) v[s] = mu[s];
+                int h = 0;
+                for (int j = 0; j < a.n_h; ++j) {
+                    for (; h < a.h_sorted[j]; ++h) {
+                        R nv[K];
+#pragma unroll
+                        for (int r = 0; r < K; ++r) {
+                            R acc = ch.A[r][0] * v[0];
+#pragma unroll
+                            for (int s = 1; s < K; ++s) acc = fma(ch.A[r][s], v[s], acc);
+                            nv[r] = acc;
+                        }
+#pragma unroll
+                        for (int s = 0; s < K; ++s) v[s] = nv[s];
+                    }
+#pragma unroll
+                    for (int s = 0; s < K; ++s) mh[(a.h_slot[j] * K + s) * kGibbsThreads] = v[s];
+                }
+            }
+
             // ---- 4. backward pass
             Back b;
 #pragma unroll
@@ -657,9 +707,10 @@ struct GibbsWarp {
     }
 };
 
-template <typename R, int K, bool WIDE> constexpr size_t kGibbsSmemBytes() {
-    return sizeof(typename GibbsWarp<R, K, false, false, WIDE>::Entry) * K * kGibbsThreads      // selection tables
-           + (HMC_ASYNC ? sizeof(R) * (size_t)(kGibbsThreads / 32) * kRing * 4 * K * 32 : 0);    // cp.async rings
+template <typename R, int K, bool WIDE> __host__ __device__ constexpr size_t gibbs_smem_bytes(bool smooth, int n_h) {
+    return sizeof(GibbsEntry<R, K, WIDE>) * K * kGibbsThreads                                    // selection tables
+           + (HMC_ASYNC ? sizeof(R) * (size_t)(kGibbsThreads / 32) * kRing * 4 * K * 32 : 0)      // cp.async rings
+           + (smooth ? sizeof(R) * (size_t)n_h * K * kGibbsThreads : 0);                          // A^h mu (in-sample forecasts)
 }
 
 template <typename R, int K, bool SMOOTH, bool LOGLIK, bool WIDE>
@@ -674,7 +725,7 @@ __global__ void __launch_bounds__(kGibbsThreads, kGibbsMinBlocks) gibbs_sweeps_k
 }
 
 // host-side launcher, instantiated once per (R, K) in gibbs_inst.cu (one translation unit each, built in parallel)
-struct GibbsLaunch { unsigned flags; int max_T; int sm_count; };
+struct GibbsLaunch { unsigned flags; int max_T; int sm_count; int n_h; };
 template <typename R, int K> cudaError_t launch_gibbs(const GibbsLaunch& cfg, const GibbsArgs& a, cudaStream_t st);
 // how many persistent warps of this kernel variant fit on the device at once
 template <typename R, int K> int gibbs_capacity_warps(const GibbsLaunch& cfg);

@@ -865,24 +865,27 @@ __global__ void __launch_bounds__(128) summary_accum_kernel(int F, int n_slots, 
 }
 
 // smoothed-probability sums of this chunk, pooled over the window's chains, added to the fp64 per-window accumulator
+// Tile of per-(row, column) sums: tile[(row*ncols + col)*32 + lane] per warp task at offset warp_pi_off/K*ncols (ncols = K for the
+// smoothed probabilities, n_h for the in-sample forecasts).  Pools the window's chains and adds to the fp64 per-window sums.
 template <typename R>
-__global__ void pib_reduce_kernel(int K, int n_chains, const int* __restrict__ win_slot0, const int* __restrict__ wT,
-                                  const long long* __restrict__ warp_pi_off, const long long* __restrict__ win_pib_off,
-                                  R* __restrict__ pacc, double* __restrict__ pib_sum) {
+__global__ void tile_reduce_kernel(int K, int ncols, int n_chains, const int* __restrict__ win_slot0, const int* __restrict__ wT,
+                                   const long long* __restrict__ warp_pi_off, const int* __restrict__ warp_T,
+                                   const long long* __restrict__ win_off, R* __restrict__ acc_tile, double* __restrict__ win_sum) {
     const int w = blockIdx.x;
     const int N = wT[w];
     const int s0 = win_slot0[w];
-    double* dst = pib_sum + win_pib_off[w];
-    for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
-        const int t = e / K, k = e % K;
+    double* dst = win_sum + win_off[w] / K * ncols;
+    for (int e = threadIdx.x; e < N * ncols; e += blockDim.x) {
+        const int t = e / ncols, k = e % ncols;
         double acc = 0.0;
         for (int cidx = 0; cidx < n_chains; ++cidx) {
             const int slot = s0 + cidx;
-            R* p = pacc + warp_pi_off[slot >> 5] + (size_t)(t * K + k) * 32 + (slot & 31);
+            const int row = t + (warp_T[slot >> 5] - N);     // windows are right-aligned inside their warp task
+            R* p = acc_tile + warp_pi_off[slot >> 5] / K * ncols + (size_t)(row * ncols + k) * 32 + (slot & 31);
             acc += (double)*p;
             *p = R(0);
         }
-        dst[(size_t)k * N + t] += acc;                       // column-major N_w x K
+        dst[(size_t)k * N + t] += acc;                       // column-major N_w x ncols
     }
 }
 
@@ -902,14 +905,14 @@ struct hmcgpu_plan {
     int n_slots = 0, n_warps = 0, chunk = 0, max_T = 0;
     GibbsArgs args{};
     // device buffers
-    DevBuf y64, yr, wbase, wTd, wi, slot_win, slot_chain, T, ybase, warp_T, warp_pi_off, pi, pacc, cnt, trans, Sd, Qd,
+    DevBuf y64, yr, wbase, wTd, wi, slot_win, slot_chain, T, ybase, warp_T, warp_pi_off, pi, pacc, facc, cnt, trans, Sd, Qd,
         events, cshift, xi, xi_user, chain_id, out, yfut_w, yfut, win_slot0, win_pib_off, totS, totQ, slot_pi_off;
     bool wide = false;
     bool pair = false;   // fp32 paired kernel: a task is 64 chain slots (two chains per thread)
     int n_groups = 1, n_bufs = 1;
     std::vector<cudaStream_t> gstreams;
     std::vector<cudaEvent_t> pool_events;
-    DevBuf d_mu, d_sig2, d_A, d_pie, d_fc, d_ll, d_sum, d_sumsq, d_pibsum;
+    DevBuf d_mu, d_sig2, d_A, d_pie, d_fc, d_ll, d_sum, d_sumsq, d_pibsum, d_fcsum;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     double gpu_ms = 0.0, sweep_ms = 0.0;
     long long n_launches = 0, n_sweep_launches = 0, h2d = 0, d2h = 0;
@@ -1095,6 +1098,10 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     }
     if (p->flags & HMCGPU_FLAG_SMOOTHED_MEAN) {
         CU(ctx, pl->pacc.alloc((size_t)pi_elems * sizeof(R)));
+        if (p->n_h > 0) {
+            CU(ctx, pl->facc.alloc((size_t)pi_elems / K * p->n_h * sizeof(R)));
+            CU(ctx, pl->d_fcsum.alloc((size_t)pib_total / K * p->n_h * sizeof(double)));
+        }
         CU(ctx, pl->d_pibsum.alloc((size_t)pib_total * sizeof(double)));
     }
     // window statistics (once per plan)
@@ -1108,7 +1115,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
 
     GibbsArgs& a = pl->args;
     a.n_slots = n_slots; a.T = pl->T.as<int>(); a.ybase = pl->ybase.as<long long>(); a.yld = nser; a.y = pl->yr.p;
-    a.warp_T = pl->warp_T.as<int>(); a.warp_pi_off = pl->warp_pi_off.as<long long>(); a.pi = pl->pi.p; a.pib_acc = pl->pacc.p;
+    a.warp_T = pl->warp_T.as<int>(); a.warp_pi_off = pl->warp_pi_off.as<long long>(); a.pi = pl->pi.p; a.pib_acc = pl->pacc.p; a.fc_acc = pl->facc.p;
     a.cnt = pl->cnt.as<int>(); a.trans = pl->trans.as<int>(); a.Sd = pl->Sd.p; a.Qd = pl->Qd.p; a.events = pl->events.as<int>();
     a.cshift = pl->cshift.p; a.xi = pl->xi.p; a.totS = pl->totS.p; a.totQ = pl->totQ.p; a.n_warps = n_warps;
     for (int i = 0; i < 32; ++i) {
@@ -1166,12 +1173,13 @@ static int plan_run_t(hmcgpu_plan* pl) {
     ++pl->n_launches;
     if (pl->d_sum.p) { CU(ctx, cudaMemsetAsync(pl->d_sum.p, 0, pl->d_sum.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_sumsq.p, 0, pl->d_sumsq.bytes, st)); }
     if (pl->pacc.p) { CU(ctx, cudaMemsetAsync(pl->pacc.p, 0, pl->pacc.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_pibsum.p, 0, pl->d_pibsum.bytes, st)); }
+    if (pl->facc.p) { CU(ctx, cudaMemsetAsync(pl->facc.p, 0, pl->facc.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_fcsum.p, 0, pl->d_fcsum.bytes, st)); }
     cudaEvent_t ev_init;
     CU(ctx, new_event(&ev_init));
     CU(ctx, cudaEventRecord(ev_init, st));
     for (int g = 0; g < G; ++g) CU(ctx, cudaStreamWaitEvent(pl->gstreams[g], ev_init, 0));
 
-    const GibbsLaunch cfg{pl->flags, pl->max_T, ctx->sm_count};
+    const GibbsLaunch cfg{pl->flags, pl->max_T, ctx->sm_count, pl->n_h};
     const long long S = pl->burnin + pl->nrun;
     const long long n_chunks = (pl->nrun + pl->chunk - 1) / pl->chunk;
     const size_t buf_elems = (size_t)pl->F * pl->chunk * ns;
@@ -1200,9 +1208,18 @@ static int plan_run_t(hmcgpu_plan* pl) {
             ++pl->n_launches;
         }
         if (pl->flags & HMCGPU_FLAG_SMOOTHED_MEAN) {
-            pib_reduce_kernel<R><<<pl->n_windows, 256, 0, st>>>(Kr, pl->n_chains, pl->win_slot0.as<int>(), pl->wTd.as<int>(),
-                                                                pl->warp_pi_off.as<long long>(), pl->win_pib_off.as<long long>(),
-                                                                pl->pacc.as<R>(), pl->d_pibsum.as<double>());
+            tile_reduce_kernel<R><<<pl->n_windows, 256, 0, st>>>(Kr, Kr, pl->n_chains, pl->win_slot0.as<int>(), pl->wTd.as<int>(),
+                                                                 pl->warp_pi_off.as<long long>(), pl->warp_T.as<int>(), pl->win_pib_off.as<long long>(),
+                                                                 pl->pacc.as<R>(), pl->d_pibsum.as<double>());
+            CU(ctx, cudaGetLastError());
+            ++pl->n_launches;
+            if (pl->facc.p) {
+                tile_reduce_kernel<R><<<pl->n_windows, 256, 0, st>>>(Kr, pl->n_h, pl->n_chains, pl->win_slot0.as<int>(), pl->wTd.as<int>(),
+                                                                     pl->warp_pi_off.as<long long>(), pl->warp_T.as<int>(), pl->win_pib_off.as<long long>(),
+                                                                     pl->facc.as<R>(), pl->d_fcsum.as<double>());
+                CU(ctx, cudaGetLastError());
+                ++pl->n_launches;
+            }
             CU(ctx, cudaGetLastError());
             ++pl->n_launches;
         }
@@ -1322,8 +1339,8 @@ extern "C" int hmcgpu_plan_fetch(hmcgpu_plan* pl, hmcgpu_result* r) {
         return fail(ctx, HMCGPU_ERR_ARG, "per-draw outputs requested without HMCGPU_FLAG_DRAWS");
     if ((r->summary_mean || r->summary_var) && !(pl->flags & HMCGPU_FLAG_SUMMARY))
         return fail(ctx, HMCGPU_ERR_ARG, "summary requested without HMCGPU_FLAG_SUMMARY");
-    if (r->pib_mean && !(pl->flags & HMCGPU_FLAG_SMOOTHED_MEAN))
-        return fail(ctx, HMCGPU_ERR_ARG, "pib_mean requested without HMCGPU_FLAG_SMOOTHED_MEAN");
+    if ((r->pib_mean || r->insample_forecast_mean) && !(pl->flags & HMCGPU_FLAG_SMOOTHED_MEAN))
+        return fail(ctx, HMCGPU_ERR_ARG, "pib_mean / insample_forecast_mean requested without HMCGPU_FLAG_SMOOTHED_MEAN");
     if (r->loglik && !(pl->flags & HMCGPU_FLAG_LOGLIK)) return fail(ctx, HMCGPU_ERR_ARG, "loglik requested without HMCGPU_FLAG_LOGLIK");
     CU(ctx, down(r->mu, pl->d_mu, nw * Rr * K * sizeof(double)));
     CU(ctx, down(r->sigma2, pl->d_sig2, nw * Rr * K * sizeof(double)));
@@ -1331,7 +1348,7 @@ extern "C" int hmcgpu_plan_fetch(hmcgpu_plan* pl, hmcgpu_result* r) {
     CU(ctx, down(r->pi_end, pl->d_pie, nw * Rr * K * sizeof(double)));
     CU(ctx, down(r->forecasts, pl->d_fc, nw * Rr * 2 * pl->n_h * sizeof(double)));
     CU(ctx, down(r->loglik, pl->d_ll, nw * Rr * sizeof(double)));
-    std::vector<double> sum, sumsq, pibsum;
+    std::vector<double> sum, sumsq, pibsum, fcsum;
     std::vector<int> ev(pl->n_slots);
     if (r->summary_mean || r->summary_var) {
         sum.resize((size_t)nw * pl->F); sumsq.resize((size_t)nw * pl->F);
@@ -1339,6 +1356,10 @@ extern "C" int hmcgpu_plan_fetch(hmcgpu_plan* pl, hmcgpu_result* r) {
         CU(ctx, down(sumsq.data(), pl->d_sumsq, sumsq.size() * sizeof(double)));
     }
     if (r->pib_mean) { pibsum.resize((size_t)pl->pib_total); CU(ctx, down(pibsum.data(), pl->d_pibsum, pibsum.size() * sizeof(double))); }
+    if (r->insample_forecast_mean && pl->d_fcsum.p) {
+        fcsum.resize((size_t)pl->pib_total / K * pl->n_h);
+        CU(ctx, down(fcsum.data(), pl->d_fcsum, fcsum.size() * sizeof(double)));
+    }
     CU(ctx, down(ev.data(), pl->events, ev.size() * sizeof(int)));
     CU(ctx, cudaStreamSynchronize(st));
     const double n = (double)Rr;
@@ -1348,6 +1369,7 @@ extern "C" int hmcgpu_plan_fetch(hmcgpu_plan* pl, hmcgpu_result* r) {
         if (r->summary_var) r->summary_var[i] = std::max(0.0, sumsq[i] / n - m * m);
     }
     for (size_t i = 0; i < pibsum.size(); ++i) r->pib_mean[i] = pibsum[i] / n;
+    for (size_t i = 0; i < fcsum.size(); ++i) r->insample_forecast_mean[i] = fcsum[i] / n;
     // slot order -> caller order
     std::vector<int> slot_win(pl->n_slots), slot_chain(pl->n_slots);
     int bad = 0;
@@ -1427,7 +1449,7 @@ extern "C" int hmcgpu_estimate_multi(const int* devices, int n_dev, const hmcgpu
             }
             hmcgpu_problem q = *p;
             q.n_windows = n; q.win_series = ser.data(); q.win_start = st.data(); q.win_end = en.data(); q.win_id = id.data();
-            std::vector<double> mu, s2, A, pe, fc, ll, sm, sv, pb;
+            std::vector<double> mu, s2, A, pe, fc, ll, sm, sv, pb, ifc;
             std::vector<int32_t> status;
             hmcgpu_result& o = parts[d];
             if (r->mu) { mu.resize(n * Rr * K); o.mu = mu.data(); }
@@ -1439,6 +1461,7 @@ extern "C" int hmcgpu_estimate_multi(const int* devices, int n_dev, const hmcgpu
             if (r->summary_mean) { sm.resize((size_t)n * F); o.summary_mean = sm.data(); }
             if (r->summary_var) { sv.resize((size_t)n * F); o.summary_var = sv.data(); }
             if (r->pib_mean) { pb.resize(pibn); o.pib_mean = pb.data(); }
+            if (r->insample_forecast_mean) { ifc.resize(pibn / K * std::max(1, nh)); o.insample_forecast_mean = ifc.data(); }
             if (r->status) { status.resize((size_t)n * p->n_chains); o.status = status.data(); }
             rc = hmcgpu_estimate(ctx, &q, &o);
             rcs[d] = rc;
@@ -1455,7 +1478,9 @@ extern "C" int hmcgpu_estimate_multi(const int* devices, int n_dev, const hmcgpu
                     if (r->loglik) memcpy(r->loglik + w * Rr, ll.data() + j * Rr, Rr * sizeof(double));
                     if (r->summary_mean) memcpy(r->summary_mean + w * F, sm.data() + (size_t)j * F, F * sizeof(double));
                     if (r->summary_var) memcpy(r->summary_var + w * F, sv.data() + (size_t)j * F, F * sizeof(double));
-                    if (r->pib_mean) { memcpy(r->pib_mean + pib_off[w], pb.data() + po, (size_t)Tw((int)w) * K * sizeof(double)); po += (size_t)Tw((int)w) * K; }
+                    if (r->insample_forecast_mean) memcpy(r->insample_forecast_mean + pib_off[w] / K * nh, ifc.data() + po / K * nh, (size_t)Tw((int)w) * nh * sizeof(double));
+                    if (r->pib_mean) memcpy(r->pib_mean + pib_off[w], pb.data() + po, (size_t)Tw((int)w) * K * sizeof(double));
+                    po += (size_t)Tw((int)w) * K;
                     if (r->status) memcpy(r->status + w * p->n_chains, status.data() + (size_t)j * p->n_chains, p->n_chains * sizeof(int32_t));
                 }
             }

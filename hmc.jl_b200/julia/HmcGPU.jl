@@ -34,7 +34,7 @@ end
 # struct hmcgpu_result
 mutable struct Result
     mu::Ptr{Float64}; sigma2::Ptr{Float64}; A::Ptr{Float64}; pi_end::Ptr{Float64}; forecasts::Ptr{Float64}; loglik::Ptr{Float64}
-    summary_mean::Ptr{Float64}; summary_var::Ptr{Float64}; pib_mean::Ptr{Float64}; status::Ptr{Int32}
+    summary_mean::Ptr{Float64}; summary_var::Ptr{Float64}; pib_mean::Ptr{Float64}; insample_forecast_mean::Ptr{Float64}; status::Ptr{Int32}
     gpu_ms::Float64; sweep_kernel_ms::Float64; n_launches::Int64; n_sweep_launches::Int64
     h2d_bytes::Int64; d2h_bytes::Int64; state_steps::Int64
 end
@@ -75,7 +75,7 @@ function estimate(ctx::Context, rawdata::Vector{Float64}, win_start::Vector{Int3
     fc = Array{Float64}(undef, R, 2nh, nw)
     status = zeros(Int32, n_chains, nw)
     res = Result(pointer(mu), pointer(sig), pointer(A), pointer(pie), nh > 0 ? pointer(fc) : C_NULL, C_NULL,
-                 C_NULL, C_NULL, C_NULL, pointer(status), 0.0, 0.0, 0, 0, 0, 0, 0)
+                 C_NULL, C_NULL, C_NULL, C_NULL, pointer(status), 0.0, 0.0, 0, 0, 0, 0, 0)
     rc = GC.@preserve rawdata win_start win_end horizons mu sig A pie fc status begin
         prob = Problem(pointer(rawdata), length(rawdata), 1, nw, C_NULL, pointer(win_start), pointer(win_end), C_NULL,
                        D, n_chains, burnin, Nrun, UInt64(seed), C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, 1.0, C_NULL,

@@ -96,6 +96,9 @@ typedef struct hmcgpu_problem {
  *   mu[K], sigma2[K], A[K*K] (index s*K+r), pi_end[K], forecasts[2*n_h], loglik:
  *   summary_mean[w*F + f], summary_var[w*F + f]  (population variance over the R pooled draws)
  * pib_mean: per window N_w x K column-major, concatenated: offset_w = K * sum_{v<w} N_v.
+ * insample_forecast_mean: per window N_w x n_h column-major, concatenated (offset_w = n_h * sum_{v<w} N_v): the posterior
+ *   mean of pib[t,:]' A^h mu for every date t of the window and every horizon (forecastinsample, src/Hmc.jl:683-699);
+ *   the forecast error of date t is this minus y[t+h].  Needs HMCGPU_FLAG_SMOOTHED_MEAN (K <= 4).
  * status[w*n_chains + c]: event count of that chain. */
 typedef struct hmcgpu_result {
     double* mu;
@@ -107,6 +110,7 @@ typedef struct hmcgpu_result {
     double* summary_mean;
     double* summary_var;
     double* pib_mean;
+    double* insample_forecast_mean;
     int32_t* status;
     /* filled by the library */
     double gpu_ms;        /* device time of the sweeps (CUDA events on the library's stream) */

@@ -416,3 +416,35 @@ def test_wide_gibbs_fp32_posterior_matches_oracle(H, ctx, oracle):
     np.testing.assert_allclose(A, oA, atol=0.06)
     np.testing.assert_allclose(A.sum(1), 1.0, atol=1e-4)
     np.testing.assert_allclose(m[3 * K + K * K:3 * K + K * K + 4], ofc, atol=0.3)
+
+
+def test_insample_forecast_means(H, ctx, oracle):
+    """forecastinsample (src/Hmc.jl:683-699): per-date posterior mean of pib[j,t,:]' A_j^h mu_j.  fp64 device chain vs the
+    oracle chain on the same Philox streams (pib_full + per-draw mu, A from the oracle), plus an fp32 Monte-Carlo check."""
+    y, _ = synth_hmm(172, **K3_TRUTH)
+    hs = (1, 12)
+    wins = ((1, 160), (5, 140))
+    o = _run(H, ctx, y, [w[0] for w in wins], [w[1] for w in wins], K=3, n_chains=2, burnin=2, nrun=5, seed=11, horizons=hs,
+             precision=64, flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_SMOOTHED_MEAN)
+    for w, (s, e) in enumerate(wins):
+        n = e - s + 1
+        ref_fc, ref_pib = np.zeros((n, len(hs))), np.zeros((n, 3))
+        for c in range(2):
+            r = oracle.gibbs(y[s - 1:e], 3, 2, 5, seed=11, chain=w * 2 + c, horizons=hs, y_future=[y[e - 1 + h] for h in hs],
+                             flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM, want_pib_full=True)
+            for j in range(5):
+                for k, h in enumerate(hs):
+                    ref_fc[:, k] += r.pib_full[j] @ np.linalg.matrix_power(r.A[j], h) @ r.mu[j]
+                ref_pib += r.pib_full[j]
+        assert o.insample_forecast_mean[w].shape == (n, len(hs))
+        np.testing.assert_allclose(o.insample_forecast_mean[w], ref_fc / 10, rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(o.pib_mean[w], ref_pib / 10, rtol=1e-6, atol=1e-10)
+        # the last date's in-sample forecast is the end-of-window forecast
+        np.testing.assert_allclose(o.insample_forecast_mean[w][-1], o.forecasts[w][0::2].mean(1), rtol=1e-9)
+    # fp32, pooled chains: same quantity within Monte-Carlo error of the fp64 run
+    a = _run(H, ctx, y, [1], [160], K=3, n_chains=64, burnin=300, nrun=200, seed=12, horizons=hs, precision=32,
+             flags=H.FLAG_REF_Q1 | H.FLAG_SMOOTHED_MEAN | H.FLAG_SUMMARY)
+    b = _run(H, ctx, y, [1], [160], K=3, n_chains=64, burnin=300, nrun=200, seed=13, horizons=hs, precision=64,
+             flags=H.FLAG_REF_Q1 | H.FLAG_SMOOTHED_MEAN | H.FLAG_SUMMARY)
+    assert np.abs(a.insample_forecast_mean[0] - b.insample_forecast_mean[0]).max() < 0.15
+    np.testing.assert_allclose(a.insample_forecast_mean[0][-1], a.summary_mean[0][18:22:2], rtol=1e-4)

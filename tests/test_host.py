@@ -23,7 +23,7 @@ def test_struct_layout_matches_header(H):
     # field order/size of the ctypes mirrors = the C structs (8-byte pointers, natural alignment)
     from hmc_jl_b200 import binding as B
     assert ctypes.sizeof(B.Problem) == 176
-    assert ctypes.sizeof(B.Result) == 10 * 8 + 2 * 8 + 5 * 8
+    assert ctypes.sizeof(B.Result) == 11 * 8 + 2 * 8 + 5 * 8
     assert B.Problem.flags.offset == 172 and B.Problem.K.offset == 56
 
 
