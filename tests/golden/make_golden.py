@@ -2,8 +2,8 @@
 
 Inputs  (read-only, /root/reference): data/processed/inflation.csv (the monthly series run_hmm.jl estimates on) and
 data/output/official/*_summary.csv (the reference's own posterior means over 250 000 draws per end date, produced by
-code/run_hmm.jl official <idx> + code/aggregate.jl).  Outputs: inflation_offic_inf.csv and official_summary_subset.json
-(every 27th end date, 18 windows) — small enough to commit; nothing at test time reads /root/reference.
+code/run_hmm.jl official <idx> + code/aggregate.jl).  Outputs: inflation_offic_inf.csv, official_summary_subset.json
+(every 27th end date, 19 windows) and official_summary_all.json (all 460 end dates, values rounded to 6 digits) — small enough to commit; nothing at test time reads /root/reference.
 Header caveat: in the summary files column trans_a_b holds A[b,a].
 """
 import csv
@@ -36,3 +36,16 @@ for idx in list(range(120, 580, 27)) + [579]:
 subset["columns"] = {n: tabs[n][0] for n in names}
 json.dump(subset, open(f"{HERE}/official_summary_subset.json", "w"), indent=1)
 print(len(subset["windows"]), "windows")
+
+# the complete official run (all 460 end dates, idx 120..579), compact: one row per end date
+full = {"source": subset["source"], "note": subset["note"], "columns": subset["columns"], "end_index": [], "date": []}
+for n in names:
+    full[n] = []
+for idx in range(120, 580):
+    d = dates[idx - 1]
+    if all(d in tabs[n][1] for n in names):
+        full["end_index"].append(idx); full["date"].append(d)
+        for n in names:
+            full[n].append([round(v, 6) for v in tabs[n][1][d]])
+json.dump(full, open(f"{HERE}/official_summary_all.json", "w"), separators=(",", ":"))
+print(len(full["end_index"]), "end dates in the full table")
