@@ -199,7 +199,9 @@ def workload_config(args, world):
     if getattr(args, "workload", "c2") != "c2":
         return {"workload": {"c1": "C1: one window T=600, K=3, one chain (latency-bound by construction)",
                              "c4": "C4: independent series of T=2000, K=3, one chain each (wide batch)",
-                             "c5": f"C5: independent series of T={args.length}, K={args.states}, one chain each"}[args.workload],
+                             "c5": f"C5: independent series of T={args.length}, K={args.states}, one chain each",
+                             "sig": "S1 noisy-signal Monte Carlo (estimatesignals!, src/Hmc.jl:868-914): 64 end dates x 100 perturbed "
+                                    "copies, 12 signals after each end date (kappa = 1), smoothed state probabilities at the end date"}[args.workload],
                 "K": getattr(args, "K_run", K), "chains": args.chains, "burnin": args.burnin, "nrun": args.nrun, "precision": f"fp{args.precision}"}
     return {"workload": "C2 rolling estimation: 500 expanding windows T=101..600 of one synthetic K=3 series (len 612, "
                         "default_rng(1234)), burnin+nrun Gibbs sweeps, forecasts h=1..12, per-window posterior summaries",
@@ -217,7 +219,7 @@ def main():
     ap.add_argument("--chains", type=int, default=256, help="chains per window per GPU")
     ap.add_argument("--states", type=int, default=3, help="K for --workload c5 (K=3: SURVEY truth; otherwise mu_k=2k, sigma2=0.5)")
     ap.add_argument("--length", type=int, default=2000, help="T for --workload c4/c5")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c1", "c4", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c1", "c4", "c5", "sig"],
                     help="c2 (default, BASELINE configs[1]): 500 expanding windows; c1: one window T=600, one chain; "
                          "c4: --chains independent series (default 65536) of T=2000, K=3")
     ap.add_argument("--burnin", type=int, default=1000)
@@ -238,6 +240,7 @@ def main():
     torch.zeros(1, device=f"cuda:{local}")          # create the primary context torch.cuda.synchronize() needs
 
     win_series = None
+    sig_kw = {}
     if args.workload == "c2":
         y = synth_series()
         ws_all, we_all = H.expanding_windows(101, 600)
@@ -246,6 +249,23 @@ def main():
         y = synth_series()
         ws_all, we_all = np.array([1], dtype=np.int32), np.array([600], dtype=np.int32)
         n_chains = 1
+    elif args.workload == "sig":                    # signals_official_noise_* runs, many end dates per call
+        y0 = synth_series()
+        n_dates, n_copies, sig_len = 64, 100, 12
+        ends = np.arange(600 - n_dates + 1 - sig_len, 600 - sig_len + 1)           # end dates; the window runs to end + 12
+        rng = np.random.default_rng(1234)
+        n_ser = n_dates * n_copies * world
+        y = np.tile(y0, (n_ser + 1, 1))                                             # series 0 = the real data
+        mask = np.zeros((n_ser + 1, len(y0)), dtype=np.uint8)
+        we_all = np.tile(np.repeat(ends + sig_len, n_copies), world).astype(np.int32)
+        for i in range(n_ser):
+            e = we_all[i] - sig_len
+            y[i + 1, e:e + sig_len] += rng.standard_normal(sig_len) * 0.8
+            mask[i + 1, e:e + sig_len] = 1
+        ws_all = np.ones(n_ser, dtype=np.int32)
+        win_series = np.arange(1, n_ser + 1, dtype=np.int32)
+        n_chains = args.chains if args.chains != 256 else 4
+        sig_kw = dict(is_signal=mask, kappa=1.0, alpha=np.full(K, 2.0), nu=np.full(K, 2.0), pi_row_back=sig_len)
     else:                                           # c4 / c5: wide batch of independent series
         Kw = args.states if args.workload == "c5" else 3
         truth = TRUTH if Kw == 3 else dict(A=np.full((Kw, Kw), 0.1 / (Kw - 1)) + np.eye(Kw) * (0.9 - 0.1 / (Kw - 1)),
@@ -269,7 +289,8 @@ def main():
     ws, we = ws_all[shard], we_all[shard]
     spec = H.ProblemSpec(y, ws, we, K=getattr(args, "K_run", K), n_chains=n_chains, burnin=args.burnin, nrun=args.nrun, seed=1234, horizons=HORIZONS,
                          precision=args.precision, flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY, win_id=shard,
-                         win_series=None if win_series is None else win_series[shard])
+                         win_series=None if win_series is None else win_series[shard],
+                         win_init_series=np.zeros(len(shard), dtype=np.int32) if sig_kw else None, **sig_kw)
     ctx = H.Context(local)
     plan = H.Plan(ctx, spec)
     for _ in range(args.warmup):

@@ -2,10 +2,10 @@
 
 The directory name contains a dot, so import it through the root shim:  `import hmc_jl_b200`.
 Layout: csrc/ (CUDA kernels + C ABI), lib/ (built libhmcgpu.so), binding.py (ctypes over include/hmcgpu.h),
-api.py (mirror of Hmc.estopt / Hmc.estimatemodel), julia/HmcGPU.jl (the ccall binding a Julia user loads).
+api.py (mirror of Hmc.estopt / Hmc.estimatemodel / Hmc.estimatesignals!), julia/HmcGPU.jl (the ccall binding a Julia user loads).
 """
 from . import build  # noqa: F401
-from .api import (EstOpt, estimatemodel, estimate_windows, shard_windows, expanding_windows,  # noqa: F401
+from .api import (EstOpt, estimatemodel, estimatesignals, estimate_windows, shard_windows, expanding_windows,  # noqa: F401
                   gather_window_summaries, saveresults, write_summaries, forecastinsample)
 from .binding import (Context, HmcGpuError, Plan, ProblemSpec, estimate, estimate_multi, load, lib_path,  # noqa: F401
                       FLAG_REF_Q1, FLAG_DRAWS, FLAG_SUMMARY, FLAG_SMOOTHED_MEAN, FLAG_LOGLIK, SYMBOLS)

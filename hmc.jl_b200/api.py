@@ -3,6 +3,7 @@ parity tests drive is Python; hmc.jl_b200/julia/HmcGPU.jl is the same thing for 
 
   EstOpt           <- Hmc.estopt           (src/Hmc.jl:17-73)   same field names and defaults
   estimatemodel    <- Hmc.estimatemodel    (src/Hmc.jl:850-865) returns (μ, σ, πb, A, forecasts, obsdates)
+  estimatesignals  <- Hmc.estimatesignals! (src/Hmc.jl:868-914) noisy-signal Monte Carlo, one chain per perturbed copy
   estimate_windows <- the SLURM array of run_hmm.jl jobs (slurmscripts/base_estimation.sh:5,17): many end dates at once
 """
 from __future__ import annotations
@@ -47,10 +48,20 @@ class EstOpt:
         sr = self.sampleRange
         if len(sr) < 2 or sr.step != 1:
             raise ValueError("sampleRange must be a contiguous range of at least 2 observations")
-        if len(self.signalRange) != 0:
-            raise NotImplementedError("signalRange: the noisy-signal tier (estimatesignals!) is not implemented on the GPU path")
         if sr[0] < 1 or sr[-1] > len(self.rawdata):
             raise ValueError("sampleRange outside rawdata")
+        # the reference only logs these two (@error, src/Hmc.jl:61-62) and carries on; here they are hard errors
+        if not set(self.signalRange) <= set(sr):
+            raise ValueError("signalRange is not a subset of sampleRange")
+        if not set(self.signalSave) <= set(self.signalRange):
+            raise ValueError("signalSave is not a subset of signalRange")
+
+    def signal_mask(self):
+        """uint8 flag per index of rawdata: 1 on opt.signalRange (obsRange = setdiff(sampleRange, signalRange), :63)."""
+        m = np.zeros(len(self.rawdata), dtype=np.uint8)
+        for i in self.signalRange:
+            m[i - 1] = 1
+        return m
 
 
 def estimatemodel(opt: EstOpt, ctx: Optional[B.Context] = None):
@@ -66,21 +77,96 @@ def estimatemodel(opt: EstOpt, ctx: Optional[B.Context] = None):
     ctx = ctx or B.Context(opt.device)
     try:
         sr = opt.sampleRange
+        # With a non-empty signalRange the reference's estimatemodel still routes through the signal branches of
+        # update_μσ! / forwardupdate_P! with hp = HyperParams(Y, D), i.e. κ = 1.0 (:132, :853) — mirrored here.
+        sig = opt.signal_mask() if len(opt.signalRange) else None
         spec = B.ProblemSpec(np.asarray(opt.rawdata, dtype=np.float64), [sr[0]], [sr[-1]], K=opt.D, n_chains=opt.n_chains,
                              burnin=opt.burnin, nrun=opt.Nrun, seed=opt.seed, horizons=list(opt.horizons),
-                             precision=opt.precision, flags=B.FLAG_REF_Q1 | B.FLAG_DRAWS)
+                             precision=opt.precision, flags=B.FLAG_REF_Q1 | B.FLAG_DRAWS, is_signal=sig, kappa=1.0)
         o = B.estimate(ctx, spec)
     finally:
         if own:
             ctx.close()
     R = opt.n_chains * opt.Nrun
     date = opt.dates[opt.endIndex - 1] if opt.dates is not None else None
+    fc = o.forecasts[0].T.copy() if o.forecasts is not None else np.empty((R, 0))
+    if sr[-1] != opt.endIndex:
+        # :861 propagates πb[end] h steps from the END of the window but scores against yobs(endIndex + h)
+        y = np.asarray(opt.rawdata, dtype=np.float64)
+        for k, h in enumerate(opt.horizons):
+            fc[:, 2 * k + 1] = fc[:, 2 * k] - (y[opt.endIndex + h - 1] if opt.endIndex + h <= len(y) else np.nan)
     return SimpleNamespace(
         μ=o.mu[0].T.copy(), σ=o.sigma2[0].T.copy(),
         A=np.transpose(o.A[0], (2, 1, 0)).copy(),            # stored [s][r][draw] -> (draw, r, s)
         πb=o.pi_end[0].T.copy()[:, None, :],
-        forecasts=o.forecasts[0].T.copy() if o.forecasts is not None else np.empty((R, 0)),
+        forecasts=fc,
         obsdates=np.array([date] * R, dtype=object), events=o.events, gpu_ms=o.gpu_ms)
+
+
+def estimatesignals(opt: EstOpt, ctx: Optional[B.Context] = None, rng: Optional[np.random.Generator] = None):
+    """GPU drop-in for Hmc.estimatesignals!(opt) (src/Hmc.jl:868-914): the noisy-signal Monte Carlo.
+
+    opt.noiseSamples perturbed copies of the sample (real data + N(0, σsignal²) noise on opt.signalRange, :890) are
+    estimated with the signal-aware sampler: signals are emitted with sd·(1+κ) (:382) and enter the conjugate draws with
+    weight 1/(1+κ) (:302-314), κ = opt.noise, priors HyperParams(opt) (α = ν = 2, ξ = mean of the real sample,
+    :148-159); X0 comes from makeParams on the real data (:888).  As in the reference, a zero opt.σsignal is first set to
+    mean(σ²-draws)·noise from a plain estimatemodel run (:869-872) — opt is updated in place like the `!` says.
+
+    One difference, stated: the reference runs the copies one after the other on ONE chain (copy s starts from the final
+    state of copy s−1, each with its own signalburnin); here every copy is an independent chain started from X0, all
+    copies side by side on the GPU (× opt.n_chains chains per copy).  After burn-in the draws have the same distribution.
+    The perturbations use numpy's Generator(seed) — Julia's MersenneTwister stream cannot be reproduced.
+
+    Returns the reference's NamedTuple fields: μ, σ (Ndraws, D), πb (Ndraws, D) = smoothed probabilities at row
+    opt.endIndex (:893), A (Ndraws, D, D), forecasts (Ndraws, 2|H|), obsdates, signalvals (Ndraws, |signalSave|),
+    signalids; Ndraws = noiseSamples·n_chains·signalNrun, copy-major."""
+    own = ctx is None
+    ctx = ctx or B.Context(opt.device)
+    try:
+        if np.isclose(opt.σsignal, 0.0):                                      # :869-872
+            base = estimatemodel(opt, ctx)
+            opt.σsignal = float(base.σ.mean() * opt.noise)
+        sr, D, S = opt.sampleRange, opt.D, opt.noiseSamples
+        y = np.asarray(opt.rawdata, dtype=np.float64)
+        rng = rng or np.random.default_rng(opt.seed)
+        sig_idx = np.array(list(opt.signalRange), dtype=np.int64) - 1
+        series = np.tile(y, (S + 1, 1))                                        # series 0 = real data, s = 1..S perturbed
+        series[1:, sig_idx] += rng.standard_normal((S, len(sig_idx))) * opt.σsignal   # :890
+        sigLen = (opt.signalRange[-1] if len(opt.signalRange) else opt.endIndex) - opt.endIndex     # :886
+        hs = [max(h - sigLen, 0) for h in opt.horizons]                        # :901-905: horizon counted from the window end
+        two = np.full(D, 2.0)
+        xi = np.full(D, y[sr[0] - 1:sr[-1]].mean())                           # HyperParams(opt) :148-159
+        spec = B.ProblemSpec(series, [sr[0]] * S, [sr[-1]] * S, K=D, n_chains=opt.n_chains, burnin=opt.signalburnin,
+                             nrun=opt.signalNrun, seed=opt.seed, horizons=hs, precision=opt.precision,
+                             flags=B.FLAG_REF_Q1 | B.FLAG_DRAWS, win_series=np.arange(1, S + 1), win_init_series=np.zeros(S),
+                             xi=xi, alpha=two, nu=two, kappa=opt.noise, is_signal=opt.signal_mask(),
+                             pi_row_back=sr[-1] - opt.endIndex)
+        o = B.estimate(ctx, spec)
+    finally:
+        if own:
+            ctx.close()
+    R = opt.n_chains * opt.signalNrun
+    cat = lambda a: np.concatenate([a[w].T for w in range(S)])                  # (S*R, ...) copy-major
+    fc = cat(o.forecasts) if o.forecasts is not None else np.empty((S * R, 0))
+    for k, h in enumerate(opt.horizons):
+        yreal = y[opt.endIndex + h - 1] if opt.endIndex + h <= len(y) else np.nan
+        if sigLen == h:                                                        # forecastsignal (:670-681), `noise` = σsignal (:904)
+            a = (1.0 / opt.σsignal) / (1.0 + 1.0 / opt.σsignal)
+            signal = np.repeat(series[1:, opt.endIndex + h - 1], R)
+            fc[:, 2 * k] = a * signal + (1.0 - a) * fc[:, 2 * k]             # horizon 0 from the window end = πb_end'μ
+            fc[:, 2 * k + 1] = fc[:, 2 * k] - yreal
+        elif sigLen > h:                                                       # left unassigned by the reference (:900-906)
+            fc[:, 2 * k:2 * k + 2] = np.nan
+        else:
+            fc[:, 2 * k + 1] = fc[:, 2 * k] - yreal                           # error against the REAL series (:902)
+    date = opt.dates[opt.endIndex - 1] if opt.dates is not None else None
+    save_idx = np.array(list(opt.signalSave), dtype=np.int64) - 1
+    return SimpleNamespace(
+        μ=cat(o.mu), σ=cat(o.sigma2), πb=cat(o.pi_end),
+        A=np.concatenate([np.transpose(o.A[w], (2, 1, 0)) for w in range(S)]),
+        forecasts=fc, obsdates=np.array([date] * (S * R), dtype=object),
+        signalvals=np.repeat(series[1:, save_idx], R, axis=0), signalids=np.repeat(np.arange(1, S + 1), R),
+        events=o.events, gpu_ms=o.gpu_ms, σsignal=opt.σsignal)
 
 
 def expanding_windows(first_end: int, last_end: int, start: int = 1):
@@ -159,7 +245,7 @@ def _fmt(v, digits=5):
     return repr(round(float(v), digits))
 
 
-def saveresults(samples, opt: EstOpt, directory: str, precision: int = 5):
+def saveresults(samples, opt: EstOpt, directory: str, precision: int = 5, hassignals: bool = False):
     """Mirror of Hmc.saveresults(samples, opt, dir; hassignals=false) (src/Hmc.jl:724-748 -> basicsave :707-722):
     five CSVs per end date, one row per draw, values rounded to `precision` digits (:719).  Headers as the current
     reference code builds them: state_i; trans_i_j in column-major order of (i, j) with column trans_i_j = A[i, j]
@@ -177,7 +263,7 @@ def saveresults(samples, opt: EstOpt, directory: str, precision: int = 5):
     tables = {
         "filtered_means": (h1, samples.μ),
         "filtered_variances": (h1, samples.σ),
-        "filtered_state_probs": (h1, samples.πb[:, -1, :]),                                  # :744
+        "filtered_state_probs": (h1, samples.πb if hassignals else samples.πb[:, -1, :]),    # :738 / :744
         "filtered_trans_probs": (h2, np.transpose(samples.A, (0, 2, 1)).reshape(R, D * D)),  # reshape(A, Nrun, :) column-major
         "forecasts": (h3, samples.forecasts),
     }
@@ -185,9 +271,15 @@ def saveresults(samples, opt: EstOpt, directory: str, precision: int = 5):
     for name, (hdr, data) in tables.items():
         path = os.path.join(directory, f"{name}_{date}.csv")
         with open(path, "w") as f:
-            f.write(",".join(["date"] + hdr) + "\n")
-            for row in np.asarray(data):
-                f.write(",".join([date] + [_fmt(v, precision) for v in row]) + "\n")
+            if hassignals:   # basicsave with signal / signalids (:707-721): date, signalid, data..., signal_1..n
+                nsig = samples.signalvals.shape[1]
+                f.write(",".join(["date", "signalid"] + hdr + [f"signal_{i}" for i in range(1, nsig + 1)]) + "\n")
+                for sid, row, sv in zip(samples.signalids, np.asarray(data), samples.signalvals):
+                    f.write(",".join([date, str(int(sid))] + [_fmt(v, precision) for v in row] + [_fmt(v, 5) for v in sv]) + "\n")
+            else:
+                f.write(",".join(["date"] + hdr) + "\n")
+                for row in np.asarray(data):
+                    f.write(",".join([date] + [_fmt(v, precision) for v in row]) + "\n")
         paths[name] = path
     return paths
 

@@ -41,7 +41,8 @@ class Problem(C.Structure):
                 ("K", C.c_int32), ("n_chains", C.c_int32), ("burnin", C.c_int64), ("nrun", C.c_int64),
                 ("seed", C.c_uint64), ("xi", _dp), ("alpha", _dp), ("nu", _dp), ("beta0", _dp), ("beta", _dp),
                 ("kappa", C.c_double), ("is_signal", _u8p), ("horizons", _i32p), ("n_h", C.c_int32),
-                ("X0", _i64p), ("precision", C.c_int32), ("flags", C.c_uint32)]
+                ("X0", _i64p), ("precision", C.c_int32), ("flags", C.c_uint32),
+                ("win_init_series", _i32p), ("pi_row_back", C.c_int32), ("is_signal_per_series", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -197,7 +198,8 @@ class ProblemSpec:
 
     def __init__(self, y, win_start, win_end, K=3, n_chains=1, burnin=1000, nrun=1000, seed=1234, horizons=(12,),
                  precision=32, flags=FLAG_REF_Q1 | FLAG_DRAWS, win_series=None, win_id=None,
-                 xi=None, alpha=None, nu=None, beta0=None, beta=None, kappa=1.0):
+                 xi=None, alpha=None, nu=None, beta0=None, beta=None, kappa=1.0, is_signal=None, X0=None,
+                 win_init_series=None, pi_row_back=0):
         y = np.asarray(y, dtype=np.float64)
         if y.ndim == 1:
             y = y[None, :]
@@ -214,12 +216,24 @@ class ProblemSpec:
         self.precision, self.flags, self.kappa = precision, flags, kappa
         self.hp = [_f64(v) for v in (xi, alpha, nu, beta0, beta)]
         self.T = (self.win_end - self.win_start + 1).astype(np.int64)
+        self.is_signal = None if is_signal is None else np.ascontiguousarray(is_signal, dtype=np.uint8)
+        if self.is_signal is not None and self.is_signal.shape not in ((self.y_len,), (self.n_series, self.y_len)):
+            raise ValueError("is_signal must have one flag per time index of the series ([y_len] or [n_series, y_len])")
+        self.sig_per_series = int(self.is_signal is not None and self.is_signal.ndim == 2)
+        if X0 is not None and not isinstance(X0, np.ndarray):
+            X0 = np.concatenate([np.asarray(x, dtype=np.int64) for x in X0])     # list of per-window paths
+        self.X0 = None if X0 is None else np.ascontiguousarray(X0, dtype=np.int64)
+        if self.X0 is not None and self.X0.shape != (int(self.T.sum()),):
+            raise ValueError("X0 must hold sum_w T_w states")
+        self.win_init_series = None if win_init_series is None else np.ascontiguousarray(win_init_series, dtype=np.int32)
+        self.pi_row_back = int(pi_row_back)
 
     def struct(self) -> Problem:
         return Problem(_p(self.y), self.y_len, self.n_series, self.n_windows, _p(self.win_series, _i32p),
                        _p(self.win_start, _i32p), _p(self.win_end, _i32p), _p(self.win_id, _i64p), self.K, self.n_chains,
-                       self.burnin, self.nrun, self.seed, *[_p(v) for v in self.hp], self.kappa, None,
-                       _p(self.horizons, _i32p), self.n_h, None, self.precision, self.flags)
+                       self.burnin, self.nrun, self.seed, *[_p(v) for v in self.hp], self.kappa, _p(self.is_signal, _u8p),
+                       _p(self.horizons, _i32p), self.n_h, _p(self.X0, _i64p), self.precision, self.flags,
+                       _p(self.win_init_series, _i32p), self.pi_row_back, self.sig_per_series)
 
     def alloc_result(self):
         K, nw, nh = self.K, self.n_windows, self.n_h

@@ -11,6 +11,10 @@ namespace hmc {
 // calls f(kernel) with the variant the flags / window length select
 template <typename R, int K, bool WIDE, typename F> static auto with_variant(const GibbsLaunch& cfg, F f) {
     const bool smooth = cfg.flags & 8u /*HMCGPU_FLAG_SMOOTHED_MEAN*/, ll = cfg.flags & 16u /*HMCGPU_FLAG_LOGLIK*/;
+    if (cfg.sig) {   // signals tier (mask, kappa-weighted statistics, pi_row_back); never combined with the smoothed means
+        if (ll) return f(gibbs_sweeps_kernel<R, K, false, true, WIDE, true>);
+        return f(gibbs_sweeps_kernel<R, K, false, false, WIDE, true>);
+    }
     if (smooth && ll) return f(gibbs_sweeps_kernel<R, K, true, true, WIDE>);
     if (smooth) return f(gibbs_sweeps_kernel<R, K, true, false, WIDE>);
     if (ll) return f(gibbs_sweeps_kernel<R, K, false, true, WIDE>);

@@ -92,6 +92,18 @@ struct GibbsArgs {
     int h_slot[kMaxH];           // original position of each sorted horizon
     const void* yfut;            // R* [n_h][n_slots] realised y at end+h (NaN when outside the series)
     unsigned flags;
+    // ---- signals tier (SIG kernels only; estimatesignals! src/Hmc.jl:868-914, mask rules :267-300 and :380-383)
+    const void* sigw;            // R* emission z-scale, time-major [y_len][sld]: +1 = observation, -1/(1+kappa) = signal
+    const long long* sbase;      // [n_slots] element offset of the window's first time step in sigw
+    int sld;                     // stride between consecutive time steps in sigw (1 = one mask for every series, else n_series)
+    int* cntM;                   // [K][n_slots] signals per state (cnt holds the observations only)
+    void* Sm;                    // R* [K][n_slots]  sum (y-c) over the signals of each state (Sd/Qd: observations only)
+    void* Qm;                    // R* [K][n_slots]  sum (y-c)^2 over the signals
+    const void* totSm;           // R* [n_slots]  window totals over the signals (totS/totQ: over the observations)
+    const void* totQm;
+    const int* totM;             // [n_slots] number of signals in the window
+    double kappa;
+    int pi_back;                 // the pi_end field of a draw is the smoothed marginal pib[N - pi_back, :] (:893); 0 = last row
 };
 
 // Transition counts n_ij of the sampled path, packed: one word per origin state, one bit-field per destination.
@@ -120,15 +132,30 @@ template <typename R, int K, bool WIDE> struct alignas(16) GibbsEntry {
 };
 template <typename R, int K, bool WIDE> __host__ __device__ constexpr size_t gibbs_smem_bytes(bool smooth, int n_h);
 
-template <typename R, int K, bool SMOOTH, bool LOGLIK, bool WIDE>
+struct NoSig {};
+template <typename R> struct SigChain {
+    const R* s0;                  // row j -> s0[j*sld] (z-scale, sign = signal flag)
+    long long sld;
+    R* opi;                       // pi_end field of the draw being saved (stride ocs between states)
+    size_t ocs;
+    int pi_back;
+};
+template <typename R, int K> struct SigBack {
+    R Sm[K - 1], Qm[K - 1];       // statistics of the signals of states 0..K-2
+    int Mi[K - 1];
+    int nback;                    // smoothing steps left before pib[N - pi_back, :] is emitted
+};
+
+template <typename R, int K, bool SMOOTH, bool LOGLIK, bool WIDE, bool SIG = false>
 struct GibbsWarp {
+    static_assert(!(SIG && SMOOTH), "the signals tier has no smoothed-mean variant");
     using Pack = TransPack<K, WIDE>;
     using Row = typename Pack::Row;
 
     using Entry = GibbsEntry<R, K, WIDE>;
 
     // per-sweep constants of one chain
-    struct Chain {
+    struct Chain : std::conditional<SIG, SigChain<R>, NoSig>::type {
         R A[K][K];
         R c;                      // shift of the sufficient statistics
         int rank[K];              // position of each chain label in increasing-mu order
@@ -146,7 +173,7 @@ struct GibbsWarp {
     };
 
     // state carried by the backward pass; the sampled state of the later time step is kept one-hot in (lt[])
-    struct Back {
+    struct Back : std::conditional<SIG, SigBack<R, K>, NoSig>::type {
         R Sd[K - 1], Qd[K - 1];   // statistics of states 0..K-2 (the last one follows from the window totals)
         Pack tr;
         Row inc;                  // Row(1) << (kBits * x_{t+1})
@@ -180,15 +207,22 @@ struct GibbsWarp {
 
     // book-keeping after X_t was drawn (one-hot in lt): transition x_t -> x_{t+1}, statistics, and the selections
     // the next (earlier) step needs
-    static __device__ __forceinline__ void commit(Back& b, const Chain& ch, const bool (&lt)[K - 1], const R (&pt)[K], R yt, bool first) {
+    static __device__ __forceinline__ void commit(Back& b, const Chain& ch, const bool (&lt)[K - 1], const R (&pt)[K], R yt, R sw, bool first) {
         if (!first) {
 #pragma unroll
             for (int i = 0; i < K; ++i) if (is_state(lt, i)) b.tr.row[i] += b.inc;
         }
         const R d = yt - ch.c, dd = d * d;
+        bool obs = true;
+        if constexpr (SIG) {                                       // signals keep their own statistics (:267-300)
+            obs = !(sw < R(0));
+#pragma unroll
+            for (int i = 0; i < K - 1; ++i)
+                if (!obs && is_state(lt, i)) { b.Sm[i] += d; b.Qm[i] += dd; b.Mi[i] += 1; }
+        }
 #pragma unroll
         for (int i = 0; i < K - 1; ++i)
-            if (is_state(lt, i)) { b.Sd[i] += d; b.Qd[i] += dd; }
+            if (obs && is_state(lt, i)) { b.Sd[i] += d; b.Qd[i] += dd; }
 #if HMC_SEL_LDS
         const Entry* e = reinterpret_cast<const Entry*>(smem_base() + ch.tab_off);
 #pragma unroll
@@ -224,7 +258,7 @@ struct GibbsWarp {
 
     template <bool GATED>
     static __device__ __forceinline__ void back_step(Back& b, const Chain& ch, const R (&pt)[K], R* __restrict__ pap, R* __restrict__ fap,
-                                                      R yt, uint32_t word, bool save, bool& bad) {
+                                                      R yt, R sw, uint32_t word, bool save, bool& bad) {
         R p[K];
 #pragma unroll
         for (int r = 0; r < K; ++r) p[r] = pt[r] * b.Acol[r];
@@ -246,7 +280,17 @@ struct GibbsWarp {
                 insample_accumulate(ch, b.pb, fap);
             }
         }
-        commit(b, ch, lt, pt, yt, false);
+        if constexpr (SIG) {
+            // samples.πb[:, endIndex, :] (:893): the smoothed marginal pi_back rows before the end of the window
+            if (b.nback > 0) {
+                smooth_step<R, K>(ch.A, pt, b.pb);
+                if (--b.nback == 0 && save) {
+#pragma unroll
+                    for (int s = 0; s < K; ++s) ch.opi[(size_t)ch.rank[s] * ch.ocs] = b.pb[s];
+                }
+            }
+        }
+        commit(b, ch, lt, pt, yt, sw, false);
     }
 
     // forward filter (forwardupdate_P! :371-440); pif rows stored for the backward pass.  CHECKED = per-step handling
@@ -269,6 +313,8 @@ struct GibbsWarp {
         for (int s = 0; s < K; ++s) pf[s] = rho[s];                  // t = 1 uses ρ (:390)
         ll = R(0);
         const R* yp = ch.y0;
+        const R* sp = nullptr;                                       // z-scale of the emission per row (SIG)
+        if constexpr (SIG) sp = ch.s0;
         R* pip = ch.pi0;
         // fp32: the K states are processed as K/2 packed pairs (+ one scalar state when K is odd) with FFMA2/FMUL2/FADD2:
         // the kernel is bound by instruction issue, and the packed forms halve the slots of the emission quadratic, the
@@ -295,13 +341,24 @@ struct GibbsWarp {
         auto step = [&](int j, int u) {
             if (!ragged || j >= ch.off) {
                 const R yt = ld_ro(yp + u * yld);
+                R sw = R(1);                                         // signals: sd x (1+kappa) (:382) <=> z scaled by 1/(1+kappa)
+                if constexpr (SIG) sw = ld_ro(sp + u * ch.sld);
                 if constexpr (sizeof(R) == 4) {
                     const f2 y2 = splat2((float)yt);
+                    const f2 sw2 = splat2((float)sw);
                     f2 l2[KP > 0 ? KP : 1];
                     float l_l = -3.0e38f;
 #pragma unroll
-                    for (int p = 0; p < KP; ++p) { const f2 d = y2 + negmu2[p]; l2[p] = fma2(d * d, q2[p], c2[p]); }
-                    if (kOdd) { const float d = (float)yt + negmu_l; l_l = fmaf(d * d, q_l, c_l); }
+                    for (int p = 0; p < KP; ++p) {
+                        f2 d = y2 + negmu2[p];
+                        if constexpr (SIG) d = d * sw2;
+                        l2[p] = fma2(d * d, q2[p], c2[p]);
+                    }
+                    if (kOdd) {
+                        float d = (float)yt + negmu_l;
+                        if constexpr (SIG) d *= (float)sw;
+                        l_l = fmaf(d * d, q_l, c_l);
+                    }
                     float m2 = l_l;
 #pragma unroll
                     for (int p = 0; p < KP; ++p) m2 = fmaxf(m2, fmaxf(l2[p].v.x, l2[p].v.y));
@@ -336,10 +393,14 @@ struct GibbsWarp {
 #pragma unroll
                         for (int s = 0; s < K; ++s) pf[s] = R(1) / R(K);
                     }
-                    if (LOGLIK) ll += (R)((Real<float>::lg2(tot) + m2) * 0.6931471805599453f);
+                    if (LOGLIK) {
+                        float l2t = Real<float>::lg2(tot) + m2;
+                        if constexpr (SIG) l2t += Real<float>::lg2(fabsf((float)sw));   // the 1/(1+kappa) of the signal pdf
+                        ll += (R)(l2t * 0.6931471805599453f);
+                    }
                 } else {
                     R e[K];
-                    em.eval(yt, e);
+                    if constexpr (SIG) em.eval_scaled(yt, sw, e); else em.eval(yt, e);
                     bool ok;
                     const R tot = forward_step<R, K>(ch.A, e, pf, ok);
                     if (CHECKED && !ok) {
@@ -354,8 +415,14 @@ struct GibbsWarp {
             }
         };
         int j = 0;
-        for (; j + 3 < ch.Tw; j += 4, yp += 4 * yld, pip += 4 * K * 32) { step(j, 0); step(j + 1, 1); step(j + 2, 2); step(j + 3, 3); }
-        for (; j < ch.Tw; ++j, yp += yld, pip += K * 32) step(j, 0);
+        for (; j + 3 < ch.Tw; j += 4, yp += 4 * yld, pip += 4 * K * 32) {
+            step(j, 0); step(j + 1, 1); step(j + 2, 2); step(j + 3, 3);
+            if constexpr (SIG) sp += 4 * ch.sld;
+        }
+        for (; j < ch.Tw; ++j, yp += yld, pip += K * 32) {
+            step(j, 0);
+            if constexpr (SIG) sp += ch.sld;
+        }
         o.events = events;
         return o;
     }
@@ -381,6 +448,15 @@ struct GibbsWarp {
 #pragma unroll
         for (int s = 0; s < K; ++s) { b.Acol[s] = R(0); b.pb[s] = R(0); }
         const R* yp = ch.y0 + (long long)(Tw - 1) * ys;
+        const R* sp = nullptr;
+        long long ss = 0;                                             // stride of the z-scale rows (SIG)
+        if constexpr (SIG) {
+            ss = ch.sld;
+            sp = ch.s0 + (long long)(Tw - 1) * ss;
+#pragma unroll
+            for (int i = 0; i < K - 1; ++i) { b.Sm[i] = R(0); b.Qm[i] = R(0); b.Mi[i] = 0; }
+            b.nback = ch.pi_back < T - 1 ? ch.pi_back : (T > 0 ? T - 1 : 0);
+        }
         const R* pip = ch.pi0 + (size_t)(Tw - 1) * K * 32;
         R* pap = SMOOTH ? ch.pacc0 + (size_t)(Tw - 1) * K * 32 : nullptr;
         uint4 w = rng_block(key, sweep, (KIND_STATES << 16), 0u);
@@ -403,40 +479,50 @@ struct GibbsWarp {
             draw(pN, u01<R>(w.x), lt);
 #pragma unroll
             for (int i = 0; i < K - 1; ++i) xN += lt[i] ? 1 : 0;
-            if (SMOOTH) {
+            if (SMOOTH || SIG) {
 #pragma unroll
                 for (int s = 0; s < K; ++s) b.pb[s] = pf[s];           // pib[N,:] = pif[N,:]
+            }
+            if (SMOOTH) {
                 if (save) {
 #pragma unroll
                     for (int s = 0; s < K; ++s) st_stream(pap + ch.rank[s] * 32, ld_stream(pap + ch.rank[s] * 32) + pf[s]);
                     insample_accumulate(ch, b.pb, ch.facc0 + (size_t)(Tw - 1) * ch.n_hi * 32);
                 }
             }
-            commit(b, ch, lt, pf, ld_ro(yp), true);
+            R swN = R(1);
+            if constexpr (SIG) swN = ld_ro(sp);
+            commit(b, ch, lt, pf, ld_ro(yp), swN, true);
         }
         int i = 1;
         // one step; u = position inside the current group of 4 (pointers move once per group).  The filtered rows and
         // observations of a group are loaded into registers one whole group ahead (they do not depend on the sampled
         // states), so the HBM/L2 latency of group g+1 hides behind the dependent chain of group g.
-        auto load_row = [&](int u, R (&pt)[K], R& yt) {
+        auto load_sw = [&](int u) -> R {
+            if constexpr (SIG) return (!ragged || i + u < T) ? ld_ro(sp - (u + 1) * ss) : R(1);
+            else return R(1);
+        };
+        auto load_row = [&](int u, R (&pt)[K], R& yt, R& st) {
 #pragma unroll
             for (int s = 0; s < K; ++s) pt[s] = ld_stream(pip + (s - (u + 1) * K) * 32);
             yt = (!ragged || i + u < T) ? ld_ro(yp - (u + 1) * ys) : R(0);
+            st = load_sw(u);
         };
-#define HMC_BACK(u, word, PT, YT)                                                                                      \
+#define HMC_BACK(u, word, PT, YT, ST)                                                                                  \
     if (!ragged || i + (u) < T)                                                                                          \
         back_step<GATED>(b, ch, PT, SMOOTH ? pap - ((u) + 1) * K * 32 : nullptr,                                         \
-                         SMOOTH ? ch.facc0 + (size_t)(Tw - 1 - (i + (u))) * ch.n_hi * 32 : nullptr, YT, (word), save, bad);
+                         SMOOTH ? ch.facc0 + (size_t)(Tw - 1 - (i + (u))) * ch.n_hi * 32 : nullptr, YT, ST, (word), save, bad);
         {
-            R p0[K], p1[K], p2[K], y0, y1, y2;
-            if (Tw > 1) load_row(0, p0, y0);
-            if (Tw > 2) load_row(1, p1, y1);
-            if (Tw > 3) load_row(2, p2, y2);
-            if (Tw > 1) { HMC_BACK(0, w.y, p0, y0) }
-            if (Tw > 2) { HMC_BACK(1, w.z, p1, y1) }
-            if (Tw > 3) { HMC_BACK(2, w.w, p2, y2) }
+            R p0[K], p1[K], p2[K], y0, y1, y2, s0 = R(1), s1 = R(1), s2 = R(1);
+            if (Tw > 1) load_row(0, p0, y0, s0);
+            if (Tw > 2) load_row(1, p1, y1, s1);
+            if (Tw > 3) load_row(2, p2, y2, s2);
+            if (Tw > 1) { HMC_BACK(0, w.y, p0, y0, s0) }
+            if (Tw > 2) { HMC_BACK(1, w.z, p1, y1, s1) }
+            if (Tw > 3) { HMC_BACK(2, w.w, p2, y2, s2) }
             const int done = Tw > 3 ? 3 : Tw - 1;
             i += done; yp -= done * ys; pip -= (size_t)done * K * 32; if (SMOOTH) pap -= (size_t)done * K * 32;
+            if constexpr (SIG) sp -= done * ss;
         }
 #if HMC_ASYNC
         {
@@ -461,7 +547,7 @@ struct GibbsWarp {
             };
 #pragma unroll
             for (int g = 0; g < kRing - 1; ++g) issue(g);
-            for (int g = 0; g < n_groups; ++g, i += 4, yp -= 4 * ys, pip -= 4 * K * 32, pap -= SMOOTH ? 4 * K * 32 : 0) {
+            for (int g = 0; g < n_groups; ++g, i += 4, yp -= 4 * ys, pip -= 4 * K * 32, pap -= SMOOTH ? 4 * K * 32 : 0, sp -= 4 * ss) {
                 issue(g + kRing - 1);                                    // overwrites the stage consumed in iteration g-1
                 cp_async_wait<kRing - 1>();                              // group g has landed (for this lane's chunks)
                 __syncwarp();                                            // ... and for every other lane's
@@ -475,36 +561,37 @@ struct GibbsWarp {
                 y1 = (!ragged || i + 1 < T) ? ld_ro(yp - 2 * ys) : R(0);
                 y2 = (!ragged || i + 2 < T) ? ld_ro(yp - 3 * ys) : R(0);
                 y3 = (!ragged || i + 3 < T) ? ld_ro(yp - 4 * ys) : R(0);
+                const R s0 = load_sw(0), s1 = load_sw(1), s2 = load_sw(2), s3 = load_sw(3);
                 w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
-                HMC_BACK(0, w.x, c0, y0) HMC_BACK(1, w.y, c1, y1) HMC_BACK(2, w.z, c2, y2) HMC_BACK(3, w.w, c3, y3)
+                HMC_BACK(0, w.x, c0, y0, s0) HMC_BACK(1, w.y, c1, y1, s1) HMC_BACK(2, w.z, c2, y2, s2) HMC_BACK(3, w.w, c3, y3, s3)
                 __syncwarp();                                            // all lanes are done with this stage
             }
             cp_async_wait<0>();
         }
 #else
-        for (; i + 3 < Tw; i += 4, yp -= 4 * ys, pip -= 4 * K * 32, pap -= SMOOTH ? 4 * K * 32 : 0) {
-            R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3;
-            load_row(0, c0, y0); load_row(1, c1, y1); load_row(2, c2, y2); load_row(3, c3, y3);
+        for (; i + 3 < Tw; i += 4, yp -= 4 * ys, pip -= 4 * K * 32, pap -= SMOOTH ? 4 * K * 32 : 0, sp -= 4 * ss) {
+            R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3, s0, s1, s2, s3;
+            load_row(0, c0, y0, s0); load_row(1, c1, y1, s1); load_row(2, c2, y2, s2); load_row(3, c3, y3, s3);
             w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
-            HMC_BACK(0, w.x, c0, y0) HMC_BACK(1, w.y, c1, y1) HMC_BACK(2, w.z, c2, y2) HMC_BACK(3, w.w, c3, y3)
+            HMC_BACK(0, w.x, c0, y0, s0) HMC_BACK(1, w.y, c1, y1, s1) HMC_BACK(2, w.z, c2, y2, s2) HMC_BACK(3, w.w, c3, y3, s3)
         }
 #endif
         if (i < Tw) {
             w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
-            R p0[K], p1[K], p2[K], y0 = R(0), y1 = R(0), y2 = R(0);
-            load_row(0, p0, y0);
-            if (i + 1 < Tw) load_row(1, p1, y1);
-            if (i + 2 < Tw) load_row(2, p2, y2);
-            HMC_BACK(0, w.x, p0, y0)
-            if (i + 1 < Tw) { HMC_BACK(1, w.y, p1, y1) }
-            if (i + 2 < Tw) { HMC_BACK(2, w.z, p2, y2) }
+            R p0[K], p1[K], p2[K], y0 = R(0), y1 = R(0), y2 = R(0), s0 = R(1), s1 = R(1), s2 = R(1);
+            load_row(0, p0, y0, s0);
+            if (i + 1 < Tw) load_row(1, p1, y1, s1);
+            if (i + 2 < Tw) load_row(2, p2, y2, s2);
+            HMC_BACK(0, w.x, p0, y0, s0)
+            if (i + 1 < Tw) { HMC_BACK(1, w.y, p1, y1, s1) }
+            if (i + 2 < Tw) { HMC_BACK(2, w.z, p2, y2, s2) }
         }
 #undef HMC_BACK
         o.xN = xN;
         o.bad = bad;
         return o;
     }
-    static __device__ void run(const GibbsArgs& a, const int warp, const int lane, Entry* smem_tab) {
+    static __device__ __forceinline__ void run(const GibbsArgs& a, const int warp, const int lane, Entry* smem_tab) {
         const int slot = warp * 32 + lane;
         const int ns = a.n_slots;
         Chain ch;
@@ -521,6 +608,12 @@ struct GibbsWarp {
         ch.c = reinterpret_cast<const R*>(a.cshift)[slot];
         ch.tab_off = (unsigned)(threadIdx.x * sizeof(Entry));
         ch.ring_off = (unsigned)(sizeof(Entry) * K * kGibbsThreads + sizeof(R) * (threadIdx.x >> 5) * (kRing * 4 * K * 32));
+        if constexpr (SIG) {
+            ch.sld = a.sld;
+            ch.s0 = reinterpret_cast<const R*>(a.sigw) + a.sbase[slot] - (long long)ch.off * ch.sld;
+            ch.pi_back = a.pi_back;
+            ch.opi = nullptr; ch.ocs = 0;
+        }
         const int T = ch.T;
         // padding lanes (T = 0) only exist in the last warp, which therefore counts as ragged
         ch.ragged = __any_sync(0xffffffffu, ch.off != 0);
@@ -544,6 +637,20 @@ struct GibbsWarp {
             for (int j = 0; j < K; ++j) trans[i][j] = a.trans[(i * K + j) * ns + slot];
         }
         int events = 0;
+        SigStats<R, K> sg;                                            // statistics of the signals (SIG)
+        R totSm = R(0), totQm = R(0);
+        int totM = 0;
+        if constexpr (SIG) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                sg.m[i] = a.cntM[i * ns + slot];
+                sg.Sm[i] = reinterpret_cast<const R*>(a.Sm)[i * ns + slot];
+                sg.Qm[i] = reinterpret_cast<const R*>(a.Qm)[i * ns + slot];
+            }
+            sg.k1 = (R)(1.0 / (1.0 + a.kappa));
+            totSm = reinterpret_cast<const R*>(a.totSm)[slot]; totQm = reinterpret_cast<const R*>(a.totQm)[slot];
+            totM = a.totM[slot];
+        }
 
         for (int sw = 0; sw < a.n_sweeps; ++sw) {
             const long long gs = a.sweep0 + sw;
@@ -551,7 +658,7 @@ struct GibbsWarp {
             // ---- 1. conjugate draws (update_μσ! :231-336 with β of this sweep — quirk Q2 —, update_ρ!, update_A!)
 #pragma unroll
             for (int i = 0; i < K; ++i) hp.beta[i] = (R)(gs == 0 ? a.beta0[i] : a.beta[i]);
-            events += draw_params<R, K>(cnt, Sd, Qd, trans, ch.c, hp, key, sweep, sig2, mu, rho, ch.A);
+            events += draw_params<R, K, SIG>(cnt, Sd, Qd, trans, ch.c, hp, key, sweep, sig2, mu, rho, ch.A, &sg);
 
             // ---- 2. forward filter
             Emission<R, K> em;
@@ -582,6 +689,7 @@ struct GibbsWarp {
                 const size_t i = (size_t)(draw_idx - a.draw0);
                 const size_t cs = (size_t)a.chunk * ns;             // stride between fields
                 R* o = out + i * ns + slot;
+                if constexpr (SIG) { ch.opi = o + (size_t)(2 * K + K * K) * cs; ch.ocs = cs; }
 #pragma unroll
                 for (int s = 0; s < K; ++s) {
                     o[(size_t)(ch.rank[s]) * cs] = mu[s];
@@ -690,6 +798,20 @@ struct GibbsWarp {
 #pragma unroll
                 for (int i = 0; i < K - 1; ++i) { Sd[i] = b.Sd[i]; Qd[i] = b.Qd[i]; sS += b.Sd[i]; sQ += b.Qd[i]; }
                 Sd[K - 1] = totS - sS; Qd[K - 1] = totQ - sQ;
+                if constexpr (SIG) {
+                    // cnt so far counts every time step of a state: split into observations and signals
+                    R mS = R(0), mQ = R(0);
+                    int mM = 0;
+#pragma unroll
+                    for (int i = 0; i < K - 1; ++i) {
+                        sg.m[i] = b.Mi[i]; sg.Sm[i] = b.Sm[i]; sg.Qm[i] = b.Qm[i];
+                        mM += b.Mi[i]; mS += b.Sm[i]; mQ += b.Qm[i];
+                    }
+                    sg.m[K - 1] = totM - mM; sg.Sm[K - 1] = totSm - mS; sg.Qm[K - 1] = totQm - mQ;
+                    if (sg.m[K - 1] == 0) { sg.Sm[K - 1] = R(0); sg.Qm[K - 1] = R(0); }
+#pragma unroll
+                    for (int i = 0; i < K; ++i) cnt[i] -= sg.m[i];
+                }
                 if (cnt[K - 1] == 0) { Sd[K - 1] = R(0); Qd[K - 1] = R(0); }
             }
         }
@@ -702,6 +824,11 @@ struct GibbsWarp {
             reinterpret_cast<R*>(a.Qd)[i * ns + slot] = Qd[i];
 #pragma unroll
             for (int j = 0; j < K; ++j) a.trans[(i * K + j) * ns + slot] = trans[i][j];
+            if constexpr (SIG) {
+                a.cntM[i * ns + slot] = sg.m[i];
+                reinterpret_cast<R*>(a.Sm)[i * ns + slot] = sg.Sm[i];
+                reinterpret_cast<R*>(a.Qm)[i * ns + slot] = sg.Qm[i];
+            }
         }
         a.events[slot] += events;
     }
@@ -713,9 +840,9 @@ template <typename R, int K, bool WIDE> __host__ __device__ constexpr size_t gib
            + (smooth ? sizeof(R) * (size_t)n_h * K * kGibbsThreads : 0);                          // A^h mu (in-sample forecasts)
 }
 
-template <typename R, int K, bool SMOOTH, bool LOGLIK, bool WIDE>
+template <typename R, int K, bool SMOOTH, bool LOGLIK, bool WIDE, bool SIG = false>
 __global__ void __launch_bounds__(kGibbsThreads, kGibbsMinBlocks) gibbs_sweeps_kernel(const GibbsArgs a) {
-    using W = GibbsWarp<R, K, SMOOTH, LOGLIK, WIDE>;
+    using W = GibbsWarp<R, K, SMOOTH, LOGLIK, WIDE, SIG>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename W::Entry* tab = reinterpret_cast<typename W::Entry*>(smem_raw);
     const int lane = threadIdx.x & 31;
@@ -725,7 +852,7 @@ __global__ void __launch_bounds__(kGibbsThreads, kGibbsMinBlocks) gibbs_sweeps_k
 }
 
 // host-side launcher, instantiated once per (R, K) in gibbs_inst.cu (one translation unit each, built in parallel)
-struct GibbsLaunch { unsigned flags; int max_T; int sm_count; int n_h; };
+struct GibbsLaunch { unsigned flags; int max_T; int sm_count; int n_h; bool sig; };
 template <typename R, int K> cudaError_t launch_gibbs(const GibbsLaunch& cfg, const GibbsArgs& a, cudaStream_t st);
 // how many persistent warps of this kernel variant fit on the device at once
 template <typename R, int K> int gibbs_capacity_warps(const GibbsLaunch& cfg);

@@ -676,7 +676,9 @@ extern "C" int hmcgpu_philox(hmcgpu_ctx* ctx, int64_t n, const uint32_t* ctr, co
 struct WinInit {          // per window, fp64
     double mean;          // ξ default and the shift c
     double cnt[32], Sd[32], Qd[32], trans[1024];
-    double totS, totQ;    // sum over the window of (y-mean), (y-mean)^2
+    double totS, totQ;    // sum over the window's observations of (y-mean), (y-mean)^2
+    // noisy signals (src/Hmc.jl:267-300): cnt/Sd/Qd/totS/totQ above then cover the plain observations only
+    double cntM[32], Sm[32], Qm[32], totSm, totQm, totM;
 };
 
 __device__ __forceinline__ unsigned long long orderable(double v) {
@@ -719,8 +721,14 @@ __device__ double block_select(const double* y, size_t yld, int N, int k, unsign
     return from_orderable(prefix);
 }
 
+// y: the series the chain runs on; yi: the series the makeParams / HyperParams rules read (estimatesignals! initialises
+// from the real data and estimates on a perturbed copy, :888-892); sig: signal flag per absolute time index (or NULL);
+// X0u: user-supplied initial paths (1-based states) at offset x0_off[w] (or NULL = makeParams rule).
 __global__ void __launch_bounds__(256) window_init_kernel(int K, const double* __restrict__ y64, int yld,
-                                                          const long long* __restrict__ wbase, const int* __restrict__ wT,
+                                                          const long long* __restrict__ wbase, const long long* __restrict__ wbase_init,
+                                                          const int* __restrict__ wT, const unsigned char* __restrict__ sig,
+                                                          const long long* __restrict__ wsbase, int sld,
+                                                          const long long* __restrict__ X0u, const long long* __restrict__ x0_off,
                                                           WinInit* __restrict__ out) {
     extern __shared__ unsigned char x0[];                 // X0, one byte per time step
     __shared__ double shd[256];
@@ -729,23 +737,26 @@ __global__ void __launch_bounds__(256) window_init_kernel(int K, const double* _
     const int w = blockIdx.x;
     const int N = wT[w];
     const double* y = y64 + wbase[w];
+    const double* yi = wbase_init ? y64 + wbase_init[w] : y;
+    const unsigned char* sg = sig ? sig + wsbase[w] : nullptr;          // time-major mask, stride sld between time steps
     const size_t ld = (size_t)yld;
     auto add = [](double a, double b) { return a + b; };
     double s = 0.0, mn = 1e300, mx = -1e300;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) { const double v = y[i * ld]; s += v; mn = fmin(mn, v); mx = fmax(mx, v); }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { const double v = yi[i * ld]; s += v; mn = fmin(mn, v); mx = fmax(mx, v); }
     const double mean = block_reduce<double>(s, shd, add) / N;
     mn = block_reduce<double>(mn, shd, [](double a, double b) { return fmin(a, b); });
     mx = block_reduce<double>(mx, shd, [](double a, double b) { return fmax(a, b); });
     double ss = 0.0;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) { const double d = y[i * ld] - mean; ss += d * d; }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { const double d = yi[i * ld] - mean; ss += d * d; }
     const double sd = sqrt(block_reduce<double>(ss, shd, add) / (N - 1));             // Statistics.std (:177)
-    double med = block_select(y, ld, N, N / 2, shu);
-    if (!(N & 1)) med = 0.5 * (block_select(y, ld, N, N / 2 - 1, shu) + med);
+    double med = block_select(yi, ld, N, N / 2, shu);
+    if (!(N & 1)) med = 0.5 * (block_select(yi, ld, N, N / 2 - 1, shu) + med);
     const double R = mx - mn, lo = med - 0.25 * R, hi = med + 0.25 * R;               // :175-176
     if ((int)threadIdx.x < K) mu0[threadIdx.x] = (K > 1) ? lo + (hi - lo) * ((double)threadIdx.x / (double)(K - 1)) : med;
     __syncthreads();
     for (int i = threadIdx.x; i < N; i += blockDim.x) {                               // :185-187 findmax of the pdfs
-        const double v = y[i * ld];
+        if (X0u) { x0[i] = (unsigned char)(X0u[x0_off[w] + i] - 1); continue; }
+        const double v = yi[i * ld];
         int best = 0;
         double z = (v - mu0[0]) / sd, bv = exp(-(z * z) / 2.0) * 0.3989422804014327 / sd;
         for (int k = 1; k < K; ++k) {
@@ -760,10 +771,15 @@ __global__ void __launch_bounds__(256) window_init_kernel(int K, const double* _
     const int tid = threadIdx.x;
     for (int q = tid; q < K + K * K; q += blockDim.x) {
         if (q < K) {
-            double c = 0.0, sdv = 0.0, qd = 0.0;
+            double c = 0.0, sdv = 0.0, qd = 0.0, cm = 0.0, sm = 0.0, qm = 0.0;
             for (int i = 0; i < N; ++i)
-                if (x0[i] == q) { const double d = y[i * ld] - mean; c += 1.0; sdv += d; qd += d * d; }
+                if (x0[i] == q) {
+                    const double d = y[i * ld] - mean;
+                    if (sg && sg[(size_t)i * sld]) { cm += 1.0; sm += d; qm += d * d; }
+                    else { c += 1.0; sdv += d; qd += d * d; }
+                }
             out[w].cnt[q] = c; out[w].Sd[q] = sdv; out[w].Qd[q] = qd;
+            out[w].cntM[q] = cm; out[w].Sm[q] = sm; out[w].Qm[q] = qm;
         } else {
             const int j = q - K, r = j / K, s2 = j % K;
             double c = 0.0;
@@ -773,16 +789,20 @@ __global__ void __launch_bounds__(256) window_init_kernel(int K, const double* _
     }
     if (tid == 0) {
         out[w].mean = mean;
-        double a = 0.0, b = 0.0;
-        for (int i = 0; i < N; ++i) { const double d = y[i * ld] - mean; a += d; b += d * d; }
-        out[w].totS = a; out[w].totQ = b;
+        double a = 0.0, b = 0.0, am = 0.0, bm = 0.0, m = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const double d = y[i * ld] - mean;
+            if (sg && sg[(size_t)i * sld]) { am += d; bm += d * d; m += 1.0; }
+            else { a += d; b += d * d; }
+        }
+        out[w].totS = a; out[w].totQ = b; out[w].totSm = am; out[w].totQm = bm; out[w].totM = m;
     }
 }
 
 template <typename R>
 __global__ void chain_init_kernel(int K, int n_slots, const int* __restrict__ slot_win, const WinInit* __restrict__ wi,
                                   const double* __restrict__ xi_user, int* cnt, int* trans, R* Sd, R* Qd, R* cshift, R* xi,
-                                  R* totS, R* totQ, int* events) {
+                                  R* totS, R* totQ, int* events, int* cntM, R* Sm, R* Qm, R* totSm, R* totQm, int* totM) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
     const int w = slot_win[slot];
@@ -792,11 +812,35 @@ __global__ void chain_init_kernel(int K, int n_slots, const int* __restrict__ sl
         Sd[i * n_slots + slot] = w < 0 ? R(0) : (R)wi[w].Sd[i];
         Qd[i * n_slots + slot] = w < 0 ? R(0) : (R)wi[w].Qd[i];
         xi[i * n_slots + slot] = w < 0 ? R(0) : (R)(xi_user ? xi_user[i] : wi[w].mean);
+        if (cntM) {
+            cntM[i * n_slots + slot] = w < 0 ? 0 : (int)wi[w].cntM[i];
+            Sm[i * n_slots + slot] = w < 0 ? R(0) : (R)wi[w].Sm[i];
+            Qm[i * n_slots + slot] = w < 0 ? R(0) : (R)wi[w].Qm[i];
+        }
         for (int j = 0; j < K; ++j) trans[(i * K + j) * n_slots + slot] = w < 0 ? 0 : (int)wi[w].trans[i * K + j];
     }
     cshift[slot] = w < 0 ? R(0) : (R)wi[w].mean;
     totS[slot] = w < 0 ? R(0) : (R)wi[w].totS;
     totQ[slot] = w < 0 ? R(0) : (R)wi[w].totQ;
+    if (cntM) {
+        totSm[slot] = w < 0 ? R(0) : (R)wi[w].totSm;
+        totQm[slot] = w < 0 ? R(0) : (R)wi[w].totQm;
+        totM[slot] = w < 0 ? 0 : (int)wi[w].totM;
+    }
+}
+
+// signal mask (series-major [S][y_len] as the host gives it, S = 1 or n_series) -> time-major [y_len][S] flags and the
+// emission z-scale: +1 = observation, -1/(1+kappa) = signal (the sign is the signal flag)
+template <typename R>
+__global__ void sigw_kernel(long long y_len, int S, const unsigned char* __restrict__ sig, double kappa,
+                            unsigned char* __restrict__ mask_tm, R* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= y_len * S) return;
+    const long long t = i / S;
+    const int s = (int)(i % S);
+    const bool f = sig && sig[(long long)s * y_len + t];
+    if (mask_tm) mask_tm[i] = f ? 1 : 0;
+    out[i] = f ? (R)(-1.0 / (1.0 + kappa)) : R(1);
 }
 
 // y (fp64, series-major as the host gives it) -> time-major fp64 and R copies
@@ -907,6 +951,8 @@ struct hmcgpu_plan {
     // device buffers
     DevBuf y64, yr, wbase, wTd, wi, slot_win, slot_chain, T, ybase, warp_T, warp_pi_off, pi, pacc, facc, cnt, trans, Sd, Qd,
         events, cshift, xi, xi_user, chain_id, out, yfut_w, yfut, win_slot0, win_pib_off, totS, totQ, slot_pi_off;
+    DevBuf sigmask, sigmask_tm, sigw, sbase, wsbase, wbase_init, X0, x0_off, cntM, Sm, Qm, totSm, totQm, totM;    // signals tier / user initial states
+    bool sig = false;    // SIG kernels: signal mask and / or pi_row_back
     bool wide = false;
     bool pair = false;   // fp32 paired kernel: a task is 64 chain slots (two chains per thread)
     int n_groups = 1, n_bufs = 1;
@@ -940,13 +986,28 @@ static int validate_problem(hmcgpu_ctx* ctx, const hmcgpu_problem* p) {
     if (p->burnin + p->nrun > 0xffffffffLL) return fail(ctx, HMCGPU_ERR_ARG, "more than 2^32 sweeps");
     if (p->precision != 32 && p->precision != 64) return fail(ctx, HMCGPU_ERR_ARG, "precision must be 32 or 64");
     if (p->n_h < 0 || p->n_h > kMaxH || (p->n_h > 0 && !p->horizons)) return fail(ctx, HMCGPU_ERR_ARG, "0 <= n_h <= %d", kMaxH);
-    if (p->is_signal) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "is_signal: the signals tier is not implemented");
-    if (p->X0) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "X0: user initial states are not implemented");
-    for (int j = 0; j < p->n_h; ++j) if (p->horizons[j] < 1) return fail(ctx, HMCGPU_ERR_ARG, "horizons must be >= 1");
+    if (p->is_signal || p->pi_row_back != 0) {
+        if (!k_thread(p->K)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "is_signal / pi_row_back are only implemented for K <= 4");
+        if (p->flags & HMCGPU_FLAG_SMOOTHED_MEAN) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "is_signal / pi_row_back cannot be combined with HMCGPU_FLAG_SMOOTHED_MEAN");
+        if (p->is_signal && !(p->kappa >= 0.0)) return fail(ctx, HMCGPU_ERR_ARG, "kappa must be >= 0 with is_signal");
+        if (p->pi_row_back < 0) return fail(ctx, HMCGPU_ERR_ARG, "pi_row_back < 0");
+    }
+    for (int j = 0; j < p->n_h; ++j) if (p->horizons[j] < 0) return fail(ctx, HMCGPU_ERR_ARG, "horizons must be >= 0");
     for (int w = 0; w < p->n_windows; ++w) {
         const long long s = p->win_start[w], e = p->win_end[w];
         if (s < 1 || e > p->y_len || e - s + 1 < 2) return fail(ctx, HMCGPU_ERR_ARG, "window %d: [%lld,%lld] outside 1..%lld or shorter than 2", w, s, e, (long long)p->y_len);
         if (p->win_series && (p->win_series[w] < 0 || p->win_series[w] >= p->n_series)) return fail(ctx, HMCGPU_ERR_ARG, "window %d: bad series index", w);
+        if (p->win_init_series && (p->win_init_series[w] < 0 || p->win_init_series[w] >= p->n_series)) return fail(ctx, HMCGPU_ERR_ARG, "window %d: bad init series index", w);
+        if (p->pi_row_back >= e - s + 1) return fail(ctx, HMCGPU_ERR_ARG, "window %d: pi_row_back %d >= window length", w, p->pi_row_back);
+    }
+    if (p->X0) {
+        size_t off = 0;
+        for (int w = 0; w < p->n_windows; ++w) {
+            const long long n = (long long)p->win_end[w] - p->win_start[w] + 1;
+            for (long long i = 0; i < n; ++i)
+                if (p->X0[off + i] < 1 || p->X0[off + i] > p->K) return fail(ctx, HMCGPU_ERR_ARG, "X0: state %lld of window %d is outside 1..%d", (long long)p->X0[off + i], w, p->K);
+            off += (size_t)n;
+        }
     }
     return 0;
 }
@@ -979,7 +1040,8 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     // slots: windows by decreasing T, chains consecutive; padded to a multiple of the task size (32 chains per warp task,
     // 64 for the fp32 paired kernel, which needs an even number of chains per window so that a pair shares its window)
     pl->wide = !k_thread(K);
-    pl->pair = !pl->wide && p->precision == 32 && nc % 2 == 0 && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN);
+    pl->sig = p->is_signal != nullptr || p->pi_row_back != 0;
+    pl->pair = !pl->wide && !pl->sig && p->precision == 32 && nc % 2 == 0 && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN);
     // Two chains per thread cut the instruction count by 30 % but need 168 registers (12 warps per SM): measured slower
     // than the scalar kernel unless the batch is far wider than the machine, so it is opt-in.
     {
@@ -992,11 +1054,15 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     const int n_warps = n_slots / ts;                       // number of warp tasks
     pl->n_slots = n_slots; pl->n_warps = n_warps;
     std::vector<int> slot_win(n_slots, -1), slot_chain(n_slots, 0), Ts(n_slots, 0), win_slot0(nw), warp_T(n_warps, 0);
-    std::vector<long long> ybase(n_slots, 0), warp_off(n_warps, 0), wbase(nw);
+    std::vector<long long> ybase(n_slots, 0), warp_off(n_warps, 0), wbase(nw), wbase_init(nw), x0_off(nw);
     std::vector<unsigned> chain_id(n_slots, 0);
+    long long x0_total = 0;
     for (int w = 0; w < nw; ++w) {
         const int ser = p->win_series ? p->win_series[w] : 0;
         wbase[w] = (long long)(p->win_start[w] - 1) * nser + ser;       // time-major [y_len][n_series]
+        wbase_init[w] = (long long)(p->win_start[w] - 1) * nser + (p->win_init_series ? p->win_init_series[w] : ser);
+        x0_off[w] = x0_total;
+        x0_total += pl->wT[w];
     }
     for (int j = 0; j < nw; ++j) {
         const int w = pl->order[j];
@@ -1070,6 +1136,31 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     CU(ctx, up(pl->win_pib_off, pl->pib_off.data(), nw * sizeof(long long)));
     CU(ctx, up(pl->yfut_w, yfut_w.data(), yfut_w.size() * sizeof(double)));
     if (p->xi) CU(ctx, up(pl->xi_user, p->xi, K * sizeof(double)));
+    if (p->win_init_series) CU(ctx, up(pl->wbase_init, wbase_init.data(), nw * sizeof(long long)));
+    if (p->X0) {
+        CU(ctx, up(pl->X0, p->X0, (size_t)x0_total * sizeof(long long)));
+        CU(ctx, up(pl->x0_off, x0_off.data(), nw * sizeof(long long)));
+    }
+    const int sld = (p->is_signal && p->is_signal_per_series) ? nser : 1;
+    if (p->is_signal) CU(ctx, up(pl->sigmask, p->is_signal, (size_t)p->y_len * sld));
+    if (pl->sig) {
+        std::vector<long long> sbase(n_slots, 0), wsbase(nw, 0);
+        for (int w = 0; w < nw; ++w) wsbase[w] = (long long)(p->win_start[w] - 1) * sld + (sld > 1 ? (p->win_series ? p->win_series[w] : 0) : 0);
+        for (int slot = 0; slot < n_slots; ++slot) if (slot_win[slot] >= 0) sbase[slot] = wsbase[slot_win[slot]];
+        CU(ctx, up(pl->sbase, sbase.data(), n_slots * sizeof(long long)));
+        CU(ctx, up(pl->wsbase, wsbase.data(), nw * sizeof(long long)));
+        CU(ctx, pl->sigw.alloc((size_t)p->y_len * sld * sizeof(R)));
+        CU(ctx, pl->sigmask_tm.alloc((size_t)p->y_len * sld));
+        sigw_kernel<R><<<grid_for(p->y_len * sld, 256), 256, 0, st>>>(p->y_len, sld, pl->sigmask.as<unsigned char>(), p->kappa,
+                                                                       pl->sigmask_tm.as<unsigned char>(), pl->sigw.as<R>());
+        CU(ctx, cudaGetLastError());
+        CU(ctx, pl->cntM.alloc((size_t)K * n_slots * sizeof(int)));
+        CU(ctx, pl->Sm.alloc((size_t)K * n_slots * sizeof(R)));
+        CU(ctx, pl->Qm.alloc((size_t)K * n_slots * sizeof(R)));
+        CU(ctx, pl->totSm.alloc((size_t)n_slots * sizeof(R)));
+        CU(ctx, pl->totQm.alloc((size_t)n_slots * sizeof(R)));
+        CU(ctx, pl->totM.alloc((size_t)n_slots * sizeof(int)));
+    }
     CU(ctx, pl->wi.alloc(nw * sizeof(WinInit)));
     CU(ctx, pl->pi.alloc((size_t)pi_elems * sizeof(R)));
     CU(ctx, pl->cnt.alloc((size_t)K * n_slots * sizeof(int)));
@@ -1108,7 +1199,10 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     const size_t smem = (size_t)pl->max_T;
     if (smem > 200 * 1024) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "window longer than %d observations", 200 * 1024);
     if (smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute(window_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    window_init_kernel<<<nw, 256, smem, st>>>(K, pl->y64.as<double>(), nser, pl->wbase.as<long long>(), pl->wTd.as<int>(), pl->wi.as<WinInit>());
+    window_init_kernel<<<nw, 256, smem, st>>>(K, pl->y64.as<double>(), nser, pl->wbase.as<long long>(), pl->wbase_init.as<long long>(),
+                                              pl->wTd.as<int>(), p->is_signal ? pl->sigmask_tm.as<unsigned char>() : nullptr,
+                                              pl->wsbase.as<long long>(), sld, pl->X0.as<long long>(),
+                                              pl->x0_off.as<long long>(), pl->wi.as<WinInit>());
     CU(ctx, cudaGetLastError());
     yfut_kernel<R><<<grid_for(n_slots, 128), 128, 0, st>>>(n_slots, p->n_h, pl->slot_win.as<int>(), pl->yfut_w.as<double>(), pl->yfut.as<R>());
     CU(ctx, cudaGetLastError());
@@ -1128,6 +1222,8 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     a.burnin = p->burnin; a.out = pl->out.p; a.chunk = pl->chunk; a.n_h = p->n_h;
     for (int j = 0; j < p->n_h; ++j) { a.h_sorted[j] = p->horizons[hs[j]]; a.h_slot[j] = hs[j]; }
     a.yfut = pl->yfut.p; a.flags = p->flags;
+    a.sigw = pl->sigw.p; a.sbase = pl->sbase.as<long long>(); a.sld = sld; a.cntM = pl->cntM.as<int>(); a.Sm = pl->Sm.p; a.Qm = pl->Qm.p; a.totSm = pl->totSm.p; a.totQm = pl->totQm.p;
+    a.totM = pl->totM.as<int>(); a.kappa = p->kappa; a.pi_back = p->pi_row_back;
     for (int g = 0; g < pl->n_groups; ++g) {
         cudaStream_t s2;
         CU(ctx, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
@@ -1168,7 +1264,9 @@ static int plan_run_t(hmcgpu_plan* pl) {
     chain_init_kernel<R><<<grid_for(ns, 128), 128, 0, st>>>(Kr, ns, pl->slot_win.as<int>(), pl->wi.as<WinInit>(),
                                                             pl->xi_user.as<double>(), pl->cnt.as<int>(), pl->trans.as<int>(),
                                                             pl->Sd.as<R>(), pl->Qd.as<R>(), pl->cshift.as<R>(), pl->xi.as<R>(),
-                                                            pl->totS.as<R>(), pl->totQ.as<R>(), pl->events.as<int>());
+                                                            pl->totS.as<R>(), pl->totQ.as<R>(), pl->events.as<int>(),
+                                                            pl->cntM.as<int>(), pl->Sm.as<R>(), pl->Qm.as<R>(), pl->totSm.as<R>(),
+                                                            pl->totQm.as<R>(), pl->totM.as<int>());
     CU(ctx, cudaGetLastError());
     ++pl->n_launches;
     if (pl->d_sum.p) { CU(ctx, cudaMemsetAsync(pl->d_sum.p, 0, pl->d_sum.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_sumsq.p, 0, pl->d_sumsq.bytes, st)); }
@@ -1179,7 +1277,7 @@ static int plan_run_t(hmcgpu_plan* pl) {
     CU(ctx, cudaEventRecord(ev_init, st));
     for (int g = 0; g < G; ++g) CU(ctx, cudaStreamWaitEvent(pl->gstreams[g], ev_init, 0));
 
-    const GibbsLaunch cfg{pl->flags, pl->max_T, ctx->sm_count, pl->n_h};
+    const GibbsLaunch cfg{pl->flags, pl->max_T, ctx->sm_count, pl->n_h, pl->sig};
     const long long S = pl->burnin + pl->nrun;
     const long long n_chunks = (pl->nrun + pl->chunk - 1) / pl->chunk;
     const size_t buf_elems = (size_t)pl->F * pl->chunk * ns;
@@ -1438,17 +1536,21 @@ extern "C" int hmcgpu_estimate_multi(const int* devices, int n_dev, const hmcgpu
             hmcgpu_ctx* ctx = nullptr;
             int rc = hmcgpu_ctx_create(devices[d], &ctx);
             if (rc != 0) { rcs[d] = rc; errs[d] = hmcgpu_last_error(nullptr); return; }
-            std::vector<int32_t> ser(n), st(n), en(n);
-            std::vector<int64_t> id(n);
+            std::vector<int32_t> ser(n), iser(n), st(n), en(n);
+            std::vector<int64_t> id(n), x0;
             size_t pibn = 0;
             for (int j = 0; j < n; ++j) {
                 const int w = ws[j];
                 ser[j] = p->win_series ? p->win_series[w] : 0; st[j] = p->win_start[w]; en[j] = p->win_end[w];
+                iser[j] = p->win_init_series ? p->win_init_series[w] : ser[j];
                 id[j] = p->win_id ? p->win_id[w] : w;
                 pibn += (size_t)Tw(w) * K;
+                if (p->X0) x0.insert(x0.end(), p->X0 + pib_off[w] / K, p->X0 + pib_off[w] / K + Tw(w));
             }
             hmcgpu_problem q = *p;
             q.n_windows = n; q.win_series = ser.data(); q.win_start = st.data(); q.win_end = en.data(); q.win_id = id.data();
+            if (p->win_init_series) q.win_init_series = iser.data();
+            if (p->X0) q.X0 = x0.data();
             std::vector<double> mu, s2, A, pe, fc, ll, sm, sv, pb, ifc;
             std::vector<int32_t> status;
             hmcgpu_result& o = parts[d];

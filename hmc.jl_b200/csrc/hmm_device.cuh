@@ -71,6 +71,12 @@ template <int K> struct Emission<double, K> {
         for (int s = 0; s < K; ++s) { const double z = (y - mu[s]) * isd[s]; e[s] = exp(-0.5 * (z * z)) * nrm[s]; }
         return 0.0;
     }
+    // signal rows: Normal(mu, (1+kappa) sd) (src/Hmc.jl:382); sw = +-1/(1+kappa) or 1 (the sign only flags a signal)
+    __device__ __forceinline__ void eval_scaled(double y, double sw, double (&e)[K]) const {
+        const double a = fabs(sw);
+#pragma unroll
+        for (int s = 0; s < K; ++s) { const double z = (y - mu[s]) * isd[s] * a; e[s] = exp(-0.5 * (z * z)) * (nrm[s] * a); }
+    }
 };
 
 // ---------------------------------------------------------------- forward step (src/Hmc.jl:386-432)
@@ -173,24 +179,44 @@ __device__ __forceinline__ int backward_sample_step(const R (&Acol)[K], const R 
 // ---------------------------------------------------------------- conjugate draws (src/Hmc.jl:302-335, :350-369)
 // Sufficient statistics are kept about a shift c:  Sd = sum(y-c), Qd = sum((y-c)^2) over t with X_t = i.
 template <typename R, int K> struct Hyper { R xi[K], alpha[K], nu[K], beta[K]; };
+// statistics of the noisy signals of a window (src/Hmc.jl:267-300): counts Mi, shifted sums over the signal time steps;
+// k1 = 1/(1+kappa) is their relative precision weight (:302, :314)
+template <typename R, int K> struct SigStats { int m[K]; R Sm[K], Qm[K]; R k1; };
 
-template <typename R, int K>
+// cnt / Sd / Qd describe the plain observations; with SIG the signals enter through sg (cnt then excludes them)
+template <typename R, int K, bool SIG = false>
 __device__ __forceinline__ int draw_params(const int (&cnt)[K], const R (&Sd)[K], const R (&Qd)[K], const int (&trans)[K][K],
                                            R c, const Hyper<R, K>& hp, const RngKey& key, uint32_t sweep,
-                                           R (&sig2)[K], R (&mu)[K], R (&rho)[K], R (&A)[K][K]) {
+                                           R (&sig2)[K], R (&mu)[K], R (&rho)[K], R (&A)[K][K],
+                                           const SigStats<R, K>* sg = nullptr) {
     int events = 0;
-    R neff[K];
+    R neff[K], sumd[K], ntot[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         const R n = (R)cnt[i];
         const R dbar = cnt[i] > 0 ? Sd[i] / n : R(0);               // ybar - c
         R s2 = Qd[i] - n * dbar * dbar;                              // sum (y - ybar)^2   (:291-294)
         s2 = s2 > R(0) ? s2 : R(0);
-        const R totalbar = cnt[i] > 0 ? dbar + c : R(0);             // :282-288
+        R totalbar = cnt[i] > 0 ? dbar + c : R(0);                   // :282-288
+        R a = hp.alpha[i] + R(0.5) * n;                              // :313
+        R ne = n, extra = R(0);
+        sumd[i] = Sd[i]; ntot[i] = n;
+        if constexpr (SIG) {
+            const R m = (R)sg->m[i];
+            const R sbar = sg->m[i] > 0 ? sg->Sm[i] / m : R(0);      // sbar - c   (:272-278)
+            R sm2 = sg->Qm[i] - m * sbar * sbar;                     // sum (signal - sbar)^2   (:297-300)
+            sm2 = sm2 > R(0) ? sm2 : R(0);
+            sumd[i] = Sd[i] + sg->Sm[i]; ntot[i] = n + m;
+            totalbar = (cnt[i] + sg->m[i]) > 0 ? sumd[i] / ntot[i] + c : R(0);
+            ne = n + m * sg->k1;                                     // Neff = Ni + Mi/(1+kappa)  (:302-303)
+            a += R(0.5) * m;
+            extra = R(0.5) * sg->k1 * sm2;                           // (0.5/(1+kappa)) Sm2  (:314)
+        }
         const R dev = totalbar - hp.xi[i];
-        const R a = hp.alpha[i] + R(0.5) * n;                        // :313
-        const R b = hp.beta[i] + R(0.5) * s2 + R(0.5) * n * hp.nu[i] / (n + hp.nu[i]) * (dev * dev);   // :314
-        neff[i] = n;
+        R b = hp.beta[i] + R(0.5) * s2;                              // :314
+        if constexpr (SIG) b += extra;
+        b += R(0.5) * ne * hp.nu[i] / (ne + hp.nu[i]) * (dev * dev);
+        neff[i] = ne;
         if (a > R(0) && b > R(0)) {
             const R g = gamma_mt<R>(a, key, sweep, (KIND_SIGMA << 16) | (uint32_t)i);
             sig2[i] = b / g;                                         // :320 InverseGamma(a,b)
@@ -201,7 +227,7 @@ __device__ __forceinline__ int draw_params(const int (&cnt)[K], const R (&Sd)[K]
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         const R n = neff[i];
-        const R sum_y = Sd[i] + n * c;
+        const R sum_y = sumd[i] + ntot[i] * c;                       // S + Sm: the plain sum over observations and signals (:331)
         const R m = (sum_y + hp.nu[i] * hp.xi[i]) / (n + hp.nu[i]);  // :331
         const R s = M<R>::sqrt(sig2[i] / (n + hp.nu[i]));            // :332
         const uint4 w = rng_block(key, sweep, (KIND_MU << 16), (uint32_t)(i >> 1));

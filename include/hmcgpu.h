@@ -76,13 +76,25 @@ typedef struct hmcgpu_problem {
     const double* nu;         /* [K] NULL = 1 (:140) */
     const double* beta0;      /* [K] β used by the first sweep; NULL = 1 (:179) */
     const double* beta;       /* [K] β afterwards; NULL = 2 (:347) */
-    double kappa;             /* relative signal precision (:116); only used with is_signal */
-    const uint8_t* is_signal; /* reserved for the signals tier; must be NULL */
-    const int32_t* horizons;  /* [n_h] forecast horizons (reference scripts: {12}) */
+    double kappa;             /* hp.κ = opt.noise (:116, :158): signals are emitted with sd*(1+κ) (:382) and weigh 1/(1+κ) in
+                                 the statistics (:302, :314); only used with is_signal */
+    const uint8_t* is_signal; /* [y_len] 1 = time index belongs to opt.signalRange (noisy signal), 0 = observation: one mask for
+                                 every series, or [y_len x n_series] column-major like y when is_signal_per_series != 0.
+                                 NULL = no signals (estimatemodel).  K <= 4, not with SMOOTHED_MEAN. */
+    const int32_t* horizons;  /* [n_h] forecast horizons >= 0 from the window end (reference scripts: {12}); 0 = pi_end'mu */
     int32_t n_h;
-    const int64_t* X0;        /* reserved: initial states; must be NULL (makeParams rule :185-187 is applied) */
+    const int64_t* X0;        /* [sum_w T_w] initial state paths (1-based states), windows concatenated in caller order and
+                                 shared by the window's chains; NULL = makeParams rule (:185-187) */
     int32_t precision;        /* 32 or 64: device arithmetic */
     uint32_t flags;
+    /* ---- signals tier (estimatesignals!, :868-914); zero / NULL = estimatemodel behaviour */
+    const int32_t* win_init_series; /* [n_windows] series the makeParams / HyperParams rules read (X0, default xi), while the
+                                 chain itself runs on win_series: estimatesignals! initialises from the real data and
+                                 estimates on the perturbed copy (:888-892).  NULL = win_series */
+    int32_t pi_row_back;      /* pi_end (and its summary) = smoothed marginal pib[N - pi_row_back, :] instead of the last row:
+                                 samples.πb[:, opt.endIndex, :] with signalLen rows after endIndex (:893).  K <= 4. */
+    int32_t is_signal_per_series; /* 0: is_signal holds y_len flags; 1: y_len flags per series (many end dates, each with its
+                                 own signalRange, in one call) */
 } hmcgpu_problem;
 
 /* Caller-allocated outputs; any pointer may be NULL.  R = n_chains*nrun draws per window, draw index

@@ -470,3 +470,152 @@ def test_complete_official_run_against_reference_summaries(H, ctx):
     assert np.median(d_mu) < 0.01 and np.median(d_s2) < 0.01 and np.median(d_A) < 1e-3 and np.median(d_pi) < 1e-3
     assert np.median(d_fc) < 0.01
     assert (d_mu < 0.1).mean() > 0.85 and (d_A < 0.01).mean() > 0.9 and (d_fc < 0.1).mean() > 0.85
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# signals tier: signal mask, kappa-weighted statistics, user X0, init series, pi_row_back
+
+def _signal_case(T=180, extra=12):
+    y, _ = synth_hmm(T + extra, **K3_TRUTH)
+    mask = np.zeros(len(y), dtype=np.uint8)
+    mask[T - 6:T] = 1            # a block of signals at the end of the window (run_hmm.jl:146-148) ...
+    mask[[20, 21, 77]] = 1       # ... and a few inside it
+    return y, mask
+
+
+@pytest.mark.parametrize("kappa", [0.0, 0.6, 3.0])
+def test_signals_first_sweeps_follow_the_oracle_chain(H, ctx, oracle, kappa):
+    """fp64 device chain with a signal mask vs the oracle chain on the same Philox streams (src/Hmc.jl:267-314, :380-383),
+    HyperParams(opt) priors (alpha = nu = 2, :148-159), and the smoothed row N - back as pi_end (:893)."""
+    T = 180
+    y, mask = _signal_case(T)
+    hs = (0, 1, 6)
+    two, xi = np.full(3, 2.0), np.full(3, 3.21)
+    back = 6
+    o = _run(H, ctx, y, [1], [T], K=3, n_chains=2, burnin=2, nrun=7, seed=99, horizons=hs, precision=64,
+             flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_LOGLIK, is_signal=mask, kappa=kappa, alpha=two, nu=two, xi=xi,
+             pi_row_back=back)
+    assert o.events == 0
+    for c in range(2):
+        yf = [y[T - 1 + h] for h in hs]
+        r = oracle.gibbs(y[:T], 3, 2, 7, seed=99, chain=c, horizons=hs, y_future=yf, is_signal=mask[:T], kappa=kappa,
+                         alpha=two, nu=two, xi=xi, flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM, want_pib_full=True)
+        sl = slice(c * 7, (c + 1) * 7)
+        np.testing.assert_allclose(o.mu[0][:, sl].T, r.mu, rtol=1e-8)
+        np.testing.assert_allclose(o.sigma2[0][:, sl].T, r.sigma2, rtol=1e-8)
+        np.testing.assert_allclose(np.transpose(o.A[0][:, :, sl], (2, 1, 0)), r.A, rtol=1e-8)
+        np.testing.assert_allclose(o.pi_end[0][:, sl].T, r.pib_full[:, T - 1 - back, :], rtol=1e-7, atol=1e-12)
+        np.testing.assert_allclose(o.forecasts[0][:, sl].T, r.forecasts, rtol=1e-8, atol=1e-9)
+        np.testing.assert_allclose(o.loglik[0][sl], r.loglik, rtol=1e-9)
+        # horizon 0 = pib[N,:]' mu
+        np.testing.assert_allclose(o.forecasts[0][0, sl], (r.pi_end * r.mu).sum(1), rtol=1e-8)
+
+
+def test_signals_every_step_a_signal_and_ragged_batch(H, ctx, oracle):
+    """run_hmm.jl:170-172 (`Make everything a signal`) and windows of different lengths in one warp task."""
+    y, _ = synth_hmm(160, **K3_TRUTH)
+    mask = np.ones(len(y), dtype=np.uint8)
+    ws, we = [1, 11, 3], [150, 120, 43]
+    o = _run(H, ctx, y, ws, we, K=3, n_chains=1, burnin=1, nrun=5, seed=5, horizons=(1,), precision=64,
+             flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS, is_signal=mask, kappa=0.6)
+    for w, (s, e) in enumerate(zip(ws, we)):
+        r = oracle.gibbs(y[s - 1:e], 3, 1, 5, seed=5, chain=w, horizons=(1,), y_future=[y[e]], is_signal=mask[s - 1:e],
+                         kappa=0.6, flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM)
+        np.testing.assert_allclose(o.mu[w].T, r.mu, rtol=1e-8)
+        np.testing.assert_allclose(o.sigma2[w].T, r.sigma2, rtol=1e-8)
+        np.testing.assert_allclose(o.pi_end[w].T, r.pi_end, rtol=1e-7, atol=1e-12)
+
+
+def test_user_initial_states_and_init_series(H, ctx, oracle):
+    """X0 supplied by the caller, and makeParams / HyperParams read from another series than the chain runs on
+    (estimatesignals! initialises from the real sample and estimates on the perturbed copy, src/Hmc.jl:888-892)."""
+    rng = np.random.default_rng(8)
+    T = 140
+    y, _ = synth_hmm(T + 2, **K3_TRUTH)
+    X0 = rng.integers(1, 4, size=T)
+    o = _run(H, ctx, y, [1], [T], K=3, n_chains=1, burnin=1, nrun=5, seed=11, horizons=(1,), precision=64,
+             flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS, X0=X0)
+    r = oracle.gibbs(y[:T], 3, 1, 5, seed=11, chain=0, horizons=(1,), y_future=[y[T]], X0=X0,
+                     flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM)
+    np.testing.assert_allclose(o.mu[0].T, r.mu, rtol=1e-8)
+    np.testing.assert_allclose(o.sigma2[0].T, r.sigma2, rtol=1e-8)
+    # series 1 = perturbed copy; X0 and xi come from series 0
+    yp = y.copy()
+    yp[T - 5:T] += rng.normal(0, 1.5, size=5)
+    mask = np.zeros(len(y), dtype=np.uint8); mask[T - 5:T] = 1
+    o = _run(H, ctx, np.stack([y, yp]), [1], [T], K=3, n_chains=1, burnin=1, nrun=5, seed=11, horizons=(1,), precision=64,
+             flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS, win_series=[1], win_init_series=[0], is_signal=mask, kappa=0.3)
+    X0r, _, _ = oracle.make_params(y[:T], 3)
+    r = oracle.gibbs(yp[:T], 3, 1, 5, seed=11, chain=0, horizons=(1,), y_future=[yp[T]], X0=X0r, xi=np.full(3, y[:T].mean()),
+                     is_signal=mask[:T], kappa=0.3, flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM)
+    np.testing.assert_allclose(o.mu[0].T, r.mu, rtol=1e-8)
+    np.testing.assert_allclose(o.sigma2[0].T, r.sigma2, rtol=1e-8)
+    np.testing.assert_allclose(o.pi_end[0].T, r.pi_end, rtol=1e-7, atol=1e-12)
+    with pytest.raises(H.HmcGpuError):
+        _run(H, ctx, y, [1], [T], K=3, X0=np.full(T, 4))
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+def test_signals_posterior_matches_oracle_posterior(H, ctx, oracle, precision):
+    """Monte-Carlo parity of the signal-aware sampler: pooled posterior moments vs the oracle's, 12 signals at the end."""
+    T = 300
+    y, _ = synth_hmm(T + 12, **K3_TRUTH)
+    mask = np.zeros(len(y), dtype=np.uint8); mask[T - 12:T] = 1
+    two = np.full(3, 2.0)
+    nch, burn, nrun = 64, 400, 400
+    o = _run(H, ctx, y, [1], [T], K=3, n_chains=nch, burnin=burn, nrun=nrun, seed=7, horizons=(1, 12), precision=precision,
+             flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_SUMMARY, is_signal=mask, kappa=1.0, alpha=two, nu=two, pi_row_back=12)
+    assert o.events == 0
+    outs, _ = oracle.gibbs_batch([dict(y=y[:T], K=3, burnin=burn, nrun=nrun, seed=70, chain=c, horizons=(1, 12),
+                                       y_future=[y[T], y[T + 11]], is_signal=mask[:T], kappa=1.0, alpha=two, nu=two,
+                                       want_pib_full=True) for c in range(12)])
+    cat = lambda k: np.concatenate([getattr(r, k) for r in outs])
+    om, os2, oA, ofc = cat("mu"), cat("sigma2"), cat("A"), cat("forecasts")
+    opb = np.concatenate([r.pib_full[:, T - 13, :] for r in outs])
+
+    def close(g, ref, name):
+        se = 4 * np.sqrt(ref.var(0) / len(ref) + g.var(0) / len(g))
+        d = np.abs(g.mean(0) - ref.mean(0))
+        assert np.all(d <= 5 * se + 1e-4), (name, d, se)
+
+    close(o.mu[0].T, om, "mu")
+    close(o.sigma2[0].T, os2, "sigma2")
+    close(np.transpose(o.A[0], (2, 1, 0)).reshape(-1, 9), oA.reshape(-1, 9), "A")
+    close(o.pi_end[0].T, opb, "pib[N-12]")
+    close(o.forecasts[0].T, ofc, "forecasts")
+    F = np.concatenate([o.mu[0], o.sigma2[0], o.A[0].reshape(9, -1), o.pi_end[0], o.forecasts[0]])
+    np.testing.assert_allclose(o.summary_mean[0][:-1], F.mean(1), rtol=1e-6, atol=1e-7)
+
+
+def test_estimatesignals_mirror(H, ctx, tmp_path):
+    """Hmc.estimatesignals! (src/Hmc.jl:868-914) through the host mirror: shapes, signal bookkeeping, forecast rules
+    (:900-906) and the hassignals CSV layout (:707-721, :733-741)."""
+    y, _ = synth_hmm(260, **K3_TRUTH)
+    end, sigLen = 200, 12
+    opt = H.EstOpt(y, list(range(1, 261)), sampleRange=range(1, end + sigLen + 1), signalRange=range(end + 1, end + sigLen + 1),
+                   signalSave=range(end + 1, end + sigLen + 1), endIndex=end, horizons=[12, 24], D=3, burnin=300, Nrun=300,
+                   signalburnin=300, signalNrun=200, noise=1.0, noiseSamples=16, precision=32, series="test")
+    s = H.estimatesignals(opt, ctx)
+    n = 16 * 200
+    assert s.μ.shape == (n, 3) and s.σ.shape == (n, 3) and s.πb.shape == (n, 3) and s.A.shape == (n, 3, 3)
+    assert s.forecasts.shape == (n, 4) and s.signalvals.shape == (n, 12) and s.signalids.tolist() == np.repeat(np.arange(1, 17), 200).tolist()
+    assert opt.σsignal > 0 and s.events == 0
+    np.testing.assert_allclose(s.πb.sum(1), 1.0, atol=1e-4)
+    assert np.all(np.diff(s.μ, axis=1) > 0)
+    # signal values are the perturbed series, constant within a copy, different across copies
+    assert np.ptp(s.signalvals[:200], axis=0).max() == 0 and np.ptp(s.signalvals[::200], axis=0).min() > 0
+    sd = (s.signalvals[::200] - y[end:end + sigLen]).std()
+    assert 0.6 * opt.σsignal < sd < 1.4 * opt.σsignal
+    # h = 12 = sigLen: forecastsignal (:670-681) is an average of the signal and the state means
+    a = (1 / opt.σsignal) / (1 + 1 / opt.σsignal)
+    sig12 = s.signalvals[:, 11]
+    f0 = (s.forecasts[:, 0] - a * sig12) / (1 - a)
+    assert np.all(f0 > s.μ[:, 0] - 1e-3) and np.all(f0 < s.μ[:, 2] + 1e-3)
+    np.testing.assert_allclose(s.forecasts[:, 1], s.forecasts[:, 0] - y[end + 12 - 1], atol=1e-4)
+    # h = 24 > sigLen: 12 steps past the window end, scored against y[end + 24]
+    np.testing.assert_allclose(s.forecasts[:, 3], s.forecasts[:, 2] - y[end + 24 - 1], atol=1e-4)
+    paths = H.saveresults(s, opt, str(tmp_path), hassignals=True)
+    head = open(paths["filtered_means"]).readline().strip().split(",")
+    assert head == ["date", "signalid", "state_1", "state_2", "state_3"] + [f"signal_{i}" for i in range(1, 13)]
+    row = open(paths["forecasts"]).readlines()[1].strip().split(",")
+    assert row[1] == "1" and len(row) == 2 + 4 + 12

@@ -22,9 +22,10 @@ def test_library_exports_every_declared_symbol(H):
 def test_struct_layout_matches_header(H):
     # field order/size of the ctypes mirrors = the C structs (8-byte pointers, natural alignment)
     from hmc_jl_b200 import binding as B
-    assert ctypes.sizeof(B.Problem) == 176
+    assert ctypes.sizeof(B.Problem) == 192
     assert ctypes.sizeof(B.Result) == 11 * 8 + 2 * 8 + 5 * 8
     assert B.Problem.flags.offset == 172 and B.Problem.K.offset == 56
+    assert B.Problem.win_init_series.offset == 176 and B.Problem.pi_row_back.offset == 184 and B.Problem.is_signal_per_series.offset == 188
 
 
 def test_no_device_fails_loudly(H):
@@ -62,8 +63,13 @@ def test_estopt_mirror_defaults_and_validation(H):
     o = H.EstOpt(y, None)
     assert (o.D, o.burnin, o.Nrun, o.seed, list(o.horizons), o.endIndex) == (3, 1000, 1000, 1234, [12], 121)
     assert list(o.sampleRange)[:2] == [1, 2] and len(o.sampleRange) == 121 and len(o.signalRange) == 0
-    with pytest.raises(NotImplementedError):
-        H.EstOpt(y, None, signalRange=range(100, 102))
+    o = H.EstOpt(y, None, sampleRange=range(1, 124), signalRange=range(122, 124), signalSave=range(123, 124))
+    m = o.signal_mask()
+    assert m.sum() == 2 and m[121] == 1 and m[122] == 1 and m[120] == 0                   # 1-based 122:123
+    with pytest.raises(ValueError):                                                       # src/Hmc.jl:61
+        H.EstOpt(y, None, signalRange=range(130, 132))
+    with pytest.raises(ValueError):                                                       # src/Hmc.jl:62
+        H.EstOpt(y, None, sampleRange=range(1, 124), signalRange=range(122, 124), signalSave=range(120, 123))
     with pytest.raises(ValueError):
         H.EstOpt(y, None, sampleRange=range(1, 300))
 
@@ -78,6 +84,17 @@ def test_problem_spec_layouts(H):
     assert o.pib_mean.size == (40 + 46) * 3
     st = spec.struct()
     assert st.y_len == 50 and st.n_series == 3 and st.n_windows == 2 and st.n_h == 2
+    assert not st.is_signal and not st.X0 and not st.win_init_series and st.pi_row_back == 0
+    mask = np.zeros(50, dtype=np.uint8); mask[45:] = 1
+    X0 = [np.ones(40, dtype=np.int64), np.full(46, 2)]
+    spec = H.ProblemSpec(y, [1, 5], [40, 50], K=3, is_signal=mask, kappa=0.5, X0=X0, win_init_series=[0, 0], pi_row_back=5)
+    st = spec.struct()
+    assert st.is_signal[47] == 1 and st.is_signal[3] == 0 and st.kappa == 0.5 and st.pi_row_back == 5
+    assert st.X0[39] == 1 and st.X0[40] == 2 and st.win_init_series[1] == 0
+    with pytest.raises(ValueError):
+        H.ProblemSpec(y, [1, 5], [40, 50], K=3, X0=np.ones(10, dtype=np.int64))
+    with pytest.raises(ValueError):
+        H.ProblemSpec(y, [1, 5], [40, 50], K=3, is_signal=np.zeros(7))
 
 
 def test_saveresults_csv_layout(H, tmp_path):
