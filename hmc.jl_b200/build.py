@@ -23,6 +23,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 UNITS = [("hmcgpu", "hmcgpu.cu", [])] + [
     (f"gibbs_{r}_{k}", "gibbs_inst.cu", [f"-DHMC_R={r}", f"-DHMC_K={k}"] + (["-DHMC_WITH_PAIR"] if r == "float" else []))
     for r in ("float", "double") for k in (2, 3, 4)] + [
+    (f"gibbs_{r}_{k}", "gibbs_inst.cu", [f"-DHMC_R={r}", f"-DHMC_K={k}"]) for r in ("float", "double") for k in (5, 6, 7, 8)] + [
     (f"gibbs_wide_{r}", "gibbs_wide_inst.cu", [f"-DHMC_R={r}"]) for r in ("float", "double")]
 
 

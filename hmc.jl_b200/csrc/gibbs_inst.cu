@@ -11,6 +11,10 @@ namespace hmc {
 // calls f(kernel) with the variant the flags / window length select
 template <typename R, int K, bool WIDE, typename F> static auto with_variant(const GibbsLaunch& cfg, F f) {
     const bool smooth = cfg.flags & 8u /*HMCGPU_FLAG_SMOOTHED_MEAN*/, ll = cfg.flags & 16u /*HMCGPU_FLAG_LOGLIK*/;
+    if constexpr (K > 4) {   // K = 5..8: the plain sweep only (the host rejects smoothed means / signals for K > 4)
+        if (ll) return f(gibbs_sweeps_kernel<R, K, false, true, WIDE>);
+        return f(gibbs_sweeps_kernel<R, K, false, false, WIDE>);
+    } else {
     if (cfg.sig) {   // signals tier (mask, kappa-weighted statistics, pi_row_back); never combined with the smoothed means
         if (ll) return f(gibbs_sweeps_kernel<R, K, false, true, WIDE, true>);
         return f(gibbs_sweeps_kernel<R, K, false, false, WIDE, true>);
@@ -19,9 +23,17 @@ template <typename R, int K, bool WIDE, typename F> static auto with_variant(con
     if (smooth) return f(gibbs_sweeps_kernel<R, K, true, false, WIDE>);
     if (ll) return f(gibbs_sweeps_kernel<R, K, false, true, WIDE>);
     return f(gibbs_sweeps_kernel<R, K, false, false, WIDE>);
+    }
 }
 // packed transition counters: 32-bit rows hold fields of 32/K bits; longer windows use 64-bit rows
 template <int K> static bool wide_rows(const GibbsLaunch& cfg) { return (long long)cfg.max_T - 1 > TransPack<K, false>::kMaxT; }
+template <typename R, int K, typename F> static auto with_rows(const GibbsLaunch& cfg, F f) {
+    if constexpr (K > 4) return with_variant<R, K, true>(cfg, f);        // always 64-bit rows, flushed
+    else {
+        if (wide_rows<K>(cfg)) return with_variant<R, K, true>(cfg, f);
+        return with_variant<R, K, false>(cfg, f);
+    }
+}
 
 template <typename R, int K> cudaError_t launch_gibbs(const GibbsLaunch& cfg, const GibbsArgs& a, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.n_tasks + kGibbsThreads / 32 - 1) / (kGibbsThreads / 32));
@@ -34,8 +46,9 @@ template <typename R, int K> cudaError_t launch_gibbs(const GibbsLaunch& cfg, co
         return cudaGetLastError();
     };
     const bool smooth = cfg.flags & 8u;
-    if (wide_rows<K>(cfg)) return with_variant<R, K, true>(cfg, [&](auto kern) { return go(kern, gibbs_smem_bytes<R, K, true>(smooth, cfg.n_h)); });
-    return with_variant<R, K, false>(cfg, [&](auto kern) { return go(kern, gibbs_smem_bytes<R, K, false>(smooth, cfg.n_h)); });
+    const bool wr = K > 4 || wide_rows<K>(cfg);
+    const size_t smem = wr ? gibbs_smem_bytes<R, K, true>(smooth, cfg.n_h) : gibbs_smem_bytes<R, K, false>(smooth, cfg.n_h);
+    return with_rows<R, K>(cfg, [&](auto kern) { return go(kern, smem); });
 }
 
 template <typename R, int K> int gibbs_capacity_warps(const GibbsLaunch& cfg) {
@@ -44,8 +57,9 @@ template <typename R, int K> int gibbs_capacity_warps(const GibbsLaunch& cfg) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGibbsThreads, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
         return per_sm * cfg.sm_count * (kGibbsThreads / 32);
     };
-    if (wide_rows<K>(cfg)) return with_variant<R, K, true>(cfg, [&](auto kern) { return q(kern, gibbs_smem_bytes<R, K, true>(cfg.flags & 8u, cfg.n_h)); });
-    return with_variant<R, K, false>(cfg, [&](auto kern) { return q(kern, gibbs_smem_bytes<R, K, false>(cfg.flags & 8u, cfg.n_h)); });
+    const bool wr = K > 4 || wide_rows<K>(cfg);
+    const size_t smem = wr ? gibbs_smem_bytes<R, K, true>(cfg.flags & 8u, cfg.n_h) : gibbs_smem_bytes<R, K, false>(cfg.flags & 8u, cfg.n_h);
+    return with_rows<R, K>(cfg, [&](auto kern) { return q(kern, smem); });
 }
 
 template cudaError_t launch_gibbs<HMC_R, HMC_K>(const GibbsLaunch&, const GibbsArgs&, cudaStream_t);

@@ -47,11 +47,19 @@ __device__ __forceinline__ unsigned char* smem_base() {
 template <typename T> __device__ __forceinline__ T ld_stream(const T* p) { return __ldcg(p); }     // pif rows: L2 only
 template <typename T> __device__ __forceinline__ T ld_ro(const T* p) { return __ldg(p); }          // y: read-only, L1
 template <typename T> __device__ __forceinline__ void st_stream(T* p, T v) { __stcg(p, v); }
+// Batches of distinct series (yld > 1) stream y from HBM once per pass: the rows are pulled into L1 kYAhead steps ahead
+// of their use so the DRAM latency does not sit in front of every group of 4 steps.  (Windows of ONE series keep y in L1.)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+constexpr int kYAhead = 16;
 constexpr int kGibbsThreads = 128;
 #ifndef HMC_MINBLOCKS
 #define HMC_MINBLOCKS 5
 #endif
 constexpr int kGibbsMinBlocks = HMC_MINBLOCKS;   // 5 blocks x 128 threads per SM -> register cap 102, 20 resident warps
+// K = 5..8 keep K x K matrices per thread: 2 blocks per SM (shared-memory tables and rings allow no more), 255 registers
+template <int K> constexpr int gibbs_min_blocks() { return K <= 4 ? kGibbsMinBlocks : 2; }
+// cp.async ring depth: the ring of a warp is stages x 4 rows x K x 32 lanes
+template <typename R, int K> constexpr int gibbs_ring_stages() { return K <= 4 ? kRing : (sizeof(R) == 4 ? 3 : 2); }
 
 struct GibbsArgs {
     int n_slots;                 // chains incl. padding, multiple of 32
@@ -107,10 +115,13 @@ struct GibbsArgs {
 };
 
 // Transition counts n_ij of the sampled path, packed: one word per origin state, one bit-field per destination.
+// K > 4: always 64-bit rows; the fields (64/K bits, 8 at K = 8) are flushed into plain counters before they can overflow.
 template <int K, bool WIDE> struct TransPack {
-    using Row = typename std::conditional<WIDE, unsigned long long, unsigned int>::type;
-    static constexpr int kBits = (WIDE ? 64 : 32) / K;
+    static constexpr bool kWide = WIDE || K > 4;
+    using Row = typename std::conditional<kWide, unsigned long long, unsigned int>::type;
+    static constexpr int kBits = (kWide ? 64 : 32) / K;
     static constexpr long long kMaxT = (1ll << kBits) - 1;
+    static constexpr bool kFlush = K > 4;
     Row row[K];
     __device__ __forceinline__ void clear() {
 #pragma unroll
@@ -151,6 +162,7 @@ struct GibbsWarp {
     static_assert(!(SIG && SMOOTH), "the signals tier has no smoothed-mean variant");
     using Pack = TransPack<K, WIDE>;
     using Row = typename Pack::Row;
+    static constexpr int kRing = gibbs_ring_stages<R, K>();          // shadows the global default inside this class
 
     using Entry = GibbsEntry<R, K, WIDE>;
 
@@ -300,7 +312,7 @@ struct GibbsWarp {
     // allocation, and the per-sweep state of the caller is saved around the call instead of squeezing the hot loops.
     struct Vec { R v[K]; };
     struct FwdOut { Vec pf; R ll; int events; };
-    template <bool RAGGED, bool CHECKED>
+    template <bool RAGGED, bool CHECKED, bool STREAM = false>
     static __device__ __noinline__ FwdOut forward_pass(const Chain ch, const Emission<R, K> em, const Vec rho_in) {
         FwdOut o;
         R (&pf)[K] = o.pf.v;
@@ -416,6 +428,10 @@ struct GibbsWarp {
         };
         int j = 0;
         for (; j + 3 < ch.Tw; j += 4, yp += 4 * yld, pip += 4 * K * 32) {
+            if (STREAM && j + kYAhead + 3 < ch.Tw && (!ragged || j + kYAhead >= ch.off)) {   // rows of this lane's own window only
+#pragma unroll
+                for (int u = 0; u < 4; ++u) prefetch_l1(yp + (kYAhead + u) * yld);
+            }
             step(j, 0); step(j + 1, 1); step(j + 2, 2); step(j + 3, 3);
             if constexpr (SIG) sp += 4 * ch.sld;
         }
@@ -429,12 +445,14 @@ struct GibbsWarp {
     // backward state sampling (update_X! :459-484) fused with the next sweep's statistics (update_μσ! :254-258/:291-294,
     // update_A! :362-365) and, optionally, backwardupdate_P! (:442-457).
     // The i-th uniform consumed (i = 0 for X[N]) is word i&3 of Philox block i>>2 of this sweep.
-    struct BackOut { Back b; int xN; bool bad; };
-    template <bool RAGGED, bool GATED>
+    struct NoAcc {};
+    struct TransAcc { int n[K * K]; };                               // flushed transition counts (K > 4)
+    struct BackOut : std::conditional<Pack::kFlush, TransAcc, NoAcc>::type { Back b; int xN; bool bad; };
+    template <bool RAGGED, bool GATED, bool STREAM = false>
     static __device__ __noinline__ BackOut backward_pass(const Chain ch, const Vec pf_in, const RngKey key, const uint32_t sweep,
                                                          const unsigned flags, const bool save) {
         BackOut o;
-        Back& b = o.b;
+        Back b;                      // a local (registers): `o` is returned through memory when K > 4
         const R (&pf)[K] = pf_in.v;
         bool bad = false;
         int xN = 0;
@@ -444,6 +462,25 @@ struct GibbsWarp {
 #pragma unroll
         for (int i = 0; i < K - 1; ++i) { b.Sd[i] = R(0); b.Qd[i] = R(0); }
         b.tr.clear();
+        int since = 8;                                               // steps since the packed counters were last flushed (+ slack)
+        // The flushed counts are only touched every kMaxT steps: the rolled inner loops index them dynamically, which keeps
+        // them in local memory instead of 64 registers that would otherwise live through the hot loop.
+        if constexpr (Pack::kFlush) {
+#pragma unroll 1
+            for (int q = 0; q < K * K; ++q) o.n[q] = 0;
+        }
+        auto flush = [&]() {
+            if constexpr (Pack::kFlush) {
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    Row v = b.tr.row[r];
+#pragma unroll 1
+                    for (int c2 = 0; c2 < K; ++c2, v >>= Pack::kBits) o.n[r * K + c2] += (int)(v & (Row)Pack::kMaxT);
+                }
+                b.tr.clear();
+                since = 8;
+            }
+        };
         b.inc = 0; b.gate = R(1);
 #pragma unroll
         for (int s = 0; s < K; ++s) { b.Acol[s] = R(0); b.pb[s] = R(0); }
@@ -548,6 +585,11 @@ struct GibbsWarp {
 #pragma unroll
             for (int g = 0; g < kRing - 1; ++g) issue(g);
             for (int g = 0; g < n_groups; ++g, i += 4, yp -= 4 * ys, pip -= 4 * K * 32, pap -= SMOOTH ? 4 * K * 32 : 0, sp -= 4 * ss) {
+                if constexpr (Pack::kFlush) { if ((since += 4) > Pack::kMaxT) flush(); }
+                if (STREAM && i + kYAhead + 3 < T) {                       // rows of steps i+kYAhead .. i+kYAhead+3 (this lane's window)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) prefetch_l1(yp - (kYAhead + u + 1) * ys);
+                }
                 issue(g + kRing - 1);                                    // overwrites the stage consumed in iteration g-1
                 cp_async_wait<kRing - 1>();                              // group g has landed (for this lane's chunks)
                 __syncwarp();                                            // ... and for every other lane's
@@ -570,6 +612,7 @@ struct GibbsWarp {
         }
 #else
         for (; i + 3 < Tw; i += 4, yp -= 4 * ys, pip -= 4 * K * 32, pap -= SMOOTH ? 4 * K * 32 : 0, sp -= 4 * ss) {
+            if constexpr (Pack::kFlush) { if ((since += 4) > Pack::kMaxT) flush(); }
             R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3, s0, s1, s2, s3;
             load_row(0, c0, y0, s0); load_row(1, c1, y1, s1); load_row(2, c2, y2, s2); load_row(3, c3, y3, s3);
             w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
@@ -587,6 +630,8 @@ struct GibbsWarp {
             if (i + 2 < Tw) { HMC_BACK(2, w.z, p2, y2, s2) }
         }
 #undef HMC_BACK
+        flush();
+        o.b = b;
         o.xN = xN;
         o.bad = bad;
         return o;
@@ -615,6 +660,7 @@ struct GibbsWarp {
             ch.opi = nullptr; ch.ocs = 0;
         }
         const int T = ch.T;
+        const bool stream_y = a.yld != 1;     // distinct series per chain: y is streamed from HBM (prefetching passes)
         // padding lanes (T = 0) only exist in the last warp, which therefore counts as ragged
         ch.ragged = __any_sync(0xffffffffu, ch.off != 0);
         const R totS = reinterpret_cast<const R*>(a.totS)[slot], totQ = reinterpret_cast<const R*>(a.totQ)[slot];
@@ -668,7 +714,8 @@ struct GibbsWarp {
                 Vec rv;
 #pragma unroll
                 for (int s = 0; s < K; ++s) rv.v[s] = rho[s];
-                FwdOut fo = ch.ragged ? forward_pass<true, false>(ch, em, rv) : forward_pass<false, false>(ch, em, rv);
+                FwdOut fo = stream_y ? (ch.ragged ? forward_pass<true, false, true>(ch, em, rv) : forward_pass<false, false, true>(ch, em, rv))
+                                     : (ch.ragged ? forward_pass<true, false>(ch, em, rv) : forward_pass<false, false>(ch, em, rv));
                 R chk = fo.pf.v[0];
 #pragma unroll
                 for (int s = 1; s < K; ++s) chk += fo.pf.v[s];
@@ -763,6 +810,7 @@ struct GibbsWarp {
                 smem_tab[x * kGibbsThreads + threadIdx.x] = en;
             }
             int xN;
+            typename std::conditional<Pack::kFlush, TransAcc, NoAcc>::type flushed;
             {
                 Vec pv;
 #pragma unroll
@@ -771,20 +819,29 @@ struct GibbsWarp {
                 if (SMOOTH) {                                        // accumulates into memory: run gated in place
                     bo = backward_pass<true, true>(ch, pv, key, sweep, a.flags, save);
                 } else {
-                    bo = ch.ragged ? backward_pass<true, false>(ch, pv, key, sweep, a.flags, save)
-                                   : backward_pass<false, false>(ch, pv, key, sweep, a.flags, save);
+                    bo = stream_y ? (ch.ragged ? backward_pass<true, false, true>(ch, pv, key, sweep, a.flags, save)
+                                               : backward_pass<false, false, true>(ch, pv, key, sweep, a.flags, save))
+                                  : (ch.ragged ? backward_pass<true, false>(ch, pv, key, sweep, a.flags, save)
+                                               : backward_pass<false, false>(ch, pv, key, sweep, a.flags, save));
                     // quirk Q5 fired somewhere: redo the pass exactly (counter-based RNG: identical draws otherwise)
                     if (__builtin_expect(bo.bad, 0)) bo = backward_pass<true, true>(ch, pv, key, sweep, a.flags, save);
                 }
                 b = bo.b;
                 xN = bo.xN;
+                if constexpr (Pack::kFlush) {
+#pragma unroll
+                    for (int q = 0; q < K * K; ++q) flushed.n[q] = bo.n[q];
+                }
             }
 
             // ---- unpack the statistics for the next sweep's draws
 #pragma unroll
             for (int i = 0; i < K; ++i)
 #pragma unroll
-                for (int j = 0; j < K; ++j) trans[i][j] = b.tr.get(i, j);
+                for (int j = 0; j < K; ++j) {
+                    trans[i][j] = b.tr.get(i, j);
+                    if constexpr (Pack::kFlush) trans[i][j] += flushed.n[i * K + j];
+                }
             {
                 // occupation counts from the transition counts: n_i = sum_j n_ij + [X_N = i]
                 R sS = R(0), sQ = R(0);
@@ -836,12 +893,12 @@ struct GibbsWarp {
 
 template <typename R, int K, bool WIDE> __host__ __device__ constexpr size_t gibbs_smem_bytes(bool smooth, int n_h) {
     return sizeof(GibbsEntry<R, K, WIDE>) * K * kGibbsThreads                                    // selection tables
-           + (HMC_ASYNC ? sizeof(R) * (size_t)(kGibbsThreads / 32) * kRing * 4 * K * 32 : 0)      // cp.async rings
+           + (HMC_ASYNC ? sizeof(R) * (size_t)(kGibbsThreads / 32) * gibbs_ring_stages<R, K>() * 4 * K * 32 : 0)      // cp.async rings
            + (smooth ? sizeof(R) * (size_t)n_h * K * kGibbsThreads : 0);                          // A^h mu (in-sample forecasts)
 }
 
 template <typename R, int K, bool SMOOTH, bool LOGLIK, bool WIDE, bool SIG = false>
-__global__ void __launch_bounds__(kGibbsThreads, kGibbsMinBlocks) gibbs_sweeps_kernel(const GibbsArgs a) {
+__global__ void __launch_bounds__(kGibbsThreads, gibbs_min_blocks<K>()) gibbs_sweeps_kernel(const GibbsArgs a) {
     using W = GibbsWarp<R, K, SMOOTH, LOGLIK, WIDE, SIG>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename W::Entry* tab = reinterpret_cast<typename W::Entry*>(smem_raw);

@@ -161,8 +161,14 @@ extern "C" int hmcgpu_ctx_sync(hmcgpu_ctx* ctx) {
     return HMCGPU_OK;
 }
 
-static bool k_supported(int K) { return K >= 2 && K <= 32; }   // 2..4: thread-per-chain kernels; 5..32: lane-per-state kernel
-static bool k_thread(int K) { return K >= 2 && K <= 4; }
+static bool k_supported(int K) { return K >= 2 && K <= 32; }
+static bool k_thread(int K) { return K >= 2 && K <= 4; }       // every feature (smoothed means, signals, K-templated entry points)
+// sweeps: thread-per-chain kernels for K = 2..8, lane-per-state kernel for K = 9..32 (HMCGPU_LANE_KERNEL=1: also for 5..8)
+static bool k_thread_sweep(int K) {
+    if (K >= 2 && K <= 4) return true;
+    const char* e = getenv("HMCGPU_LANE_KERNEL");
+    return K >= 5 && K <= 8 && !(e && atoi(e) != 0);
+}
 
 #define DISPATCH_K(K, ...)                          \
     switch (K) {                                    \
@@ -174,10 +180,21 @@ static bool k_thread(int K) { return K >= 2 && K <= 4; }
 #ifdef HMC_DEV_F3   /* experiment builds: only the fp32 K=3 sweep kernels are linked */
 #define DISPATCH_RUN(pl, rc) do { if ((pl)->precision == 32) { if ((pl)->wide) rc = plan_run_t<float, 0>(pl); else if ((pl)->K == 3) rc = plan_run_t<float, 3>(pl); } } while (0)
 #else
+#define DISPATCH_K8(K, ...)                         \
+    switch (K) {                                    \
+        case 2: { constexpr int KK = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int KK = 3; __VA_ARGS__; } break; \
+        case 4: { constexpr int KK = 4; __VA_ARGS__; } break; \
+        case 5: { constexpr int KK = 5; __VA_ARGS__; } break; \
+        case 6: { constexpr int KK = 6; __VA_ARGS__; } break; \
+        case 7: { constexpr int KK = 7; __VA_ARGS__; } break; \
+        case 8: { constexpr int KK = 8; __VA_ARGS__; } break; \
+        default: break;                             \
+    }
 #define DISPATCH_RUN(pl, rc)                                                                                          \
     do {                                                                                                            \
         if ((pl)->wide) rc = ((pl)->precision == 32) ? plan_run_t<float, 0>(pl) : plan_run_t<double, 0>(pl);       \
-        else DISPATCH_K((pl)->K, { rc = ((pl)->precision == 32) ? plan_run_t<float, KK>(pl) : plan_run_t<double, KK>(pl); }) \
+        else DISPATCH_K8((pl)->K, { rc = ((pl)->precision == 32) ? plan_run_t<float, KK>(pl) : plan_run_t<double, KK>(pl); }) \
     } while (0)
 #endif
 
@@ -1039,9 +1056,9 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
 
     // slots: windows by decreasing T, chains consecutive; padded to a multiple of the task size (32 chains per warp task,
     // 64 for the fp32 paired kernel, which needs an even number of chains per window so that a pair shares its window)
-    pl->wide = !k_thread(K);
+    pl->wide = !k_thread_sweep(K);
     pl->sig = p->is_signal != nullptr || p->pi_row_back != 0;
-    pl->pair = !pl->wide && !pl->sig && p->precision == 32 && nc % 2 == 0 && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN);
+    pl->pair = !pl->wide && K <= 4 && !pl->sig && p->precision == 32 && nc % 2 == 0 && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN);
     // Two chains per thread cut the instruction count by 30 % but need 168 registers (12 warps per SM): measured slower
     // than the scalar kernel unless the batch is far wider than the machine, so it is opt-in.
     {
@@ -1363,7 +1380,7 @@ static int plan_run_t(hmcgpu_plan* pl) {
             a.task0 = g; a.task_stride = G; a.n_tasks = (pl->n_warps - g + G - 1) / G;
             if constexpr (K == 0) {
                 CU(ctx, (launch_gibbs_wide<R>(cfg, a, pl->K, pl->slot_pi_off.as<long long>(), gs)));
-            } else if constexpr (std::is_same<R, float>::value) {
+            } else if constexpr (std::is_same<R, float>::value && K <= 4) {
                 if (pl->pair) CU(ctx, (launch_gibbs_pair<K>(cfg, a, gs)));
                 else CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
             } else {

@@ -370,9 +370,14 @@ def test_wide_smoother_forecast_draws_match_oracle(ctx, oracle, K):
         np.testing.assert_allclose(Ad[b], o[3], rtol=1e-9)
 
 
-@pytest.mark.parametrize("K,T", [(5, 150), (8, 200), (16, 160), (32, 260)])
-def test_wide_gibbs_first_sweeps_follow_the_oracle_chain(H, ctx, oracle, K, T):
-    """fp64 lane-per-state chain vs the oracle chain on the same Philox streams (several chains: sub-warp groups)."""
+@pytest.mark.parametrize("K,T,lane", [(5, 150, 0), (6, 300, 0), (7, 700, 0), (8, 200, 0), (8, 900, 0), (5, 150, 1), (8, 200, 1),
+                                      (16, 160, 0), (32, 260, 0)])
+def test_wide_gibbs_first_sweeps_follow_the_oracle_chain(H, ctx, oracle, K, T, lane, monkeypatch):
+    """fp64 chain vs the oracle chain on the same Philox streams for K > 4 (several chains: sub-warp groups).  K = 5..8
+    run on the thread-per-chain kernel (packed transition counters flushed every 2^(64/K)-1 steps: T = 700 / 900 cross
+    that bound) or, with HMCGPU_LANE_KERNEL=1, on the lane-per-state kernel that serves K = 9..32."""
+    if lane:
+        monkeypatch.setenv("HMCGPU_LANE_KERNEL", "1")
     y, _ = synth_hmm(T + 12, seed=5 + K, **_truth(K))
     hs = (1, 12)
     nch = 5
