@@ -50,7 +50,10 @@ template <typename T> __device__ __forceinline__ void st_stream(T* p, T v) { __s
 // Batches of distinct series (yld > 1) stream y from HBM once per pass: the rows are pulled into L1 kYAhead steps ahead
 // of their use so the DRAM latency does not sit in front of every group of 4 steps.  (Windows of ONE series keep y in L1.)
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-constexpr int kYAhead = 16;
+#ifndef HMC_YAHEAD
+#define HMC_YAHEAD 16
+#endif
+constexpr int kYAhead = HMC_YAHEAD;
 constexpr int kGibbsThreads = 128;
 #ifndef HMC_MINBLOCKS
 #define HMC_MINBLOCKS 5
@@ -350,9 +353,9 @@ struct GibbsWarp {
                 for (int r = 0; r < K; ++r) A_l[r] = (float)ch.A[r][K - 1];
             }
         }
-        auto step = [&](int j, int u) {
+        auto step = [&](int j, int u, R ypre = R(0)) {
             if (!ragged || j >= ch.off) {
-                const R yt = ld_ro(yp + u * yld);
+                const R yt = STREAM ? ypre : ld_ro(yp + u * yld);   // STREAM: loaded one iteration ahead by the caller
                 R sw = R(1);                                         // signals: sd x (1+kappa) (:382) <=> z scaled by 1/(1+kappa)
                 if constexpr (SIG) sw = ld_ro(sp + u * ch.sld);
                 if constexpr (sizeof(R) == 4) {
@@ -427,16 +430,30 @@ struct GibbsWarp {
             }
         };
         int j = 0;
-        for (; j + 3 < ch.Tw; j += 4, yp += 4 * yld, pip += 4 * K * 32) {
-            if (STREAM && j + kYAhead + 3 < ch.Tw && (!ragged || j + kYAhead >= ch.off)) {   // rows of this lane's own window only
+        // STREAM: the observations of the next 4 steps are fetched into registers one iteration ahead (from lines that
+        // were pulled into L1 kYAhead steps ahead), so neither the DRAM nor the L1 latency sits in the dependent chain
+        R yn[4] = {R(0), R(0), R(0), R(0)};
+        auto load4 = [&](int jj, const R* p) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) prefetch_l1(yp + (kYAhead + u) * yld);
+            for (int u = 0; u < 4; ++u) yn[u] = (jj + u < ch.Tw && (!ragged || jj + u >= ch.off)) ? ld_ro(p + u * yld) : R(0);
+        };
+        if constexpr (STREAM) load4(0, yp);
+        for (; j + 3 < ch.Tw; j += 4, yp += 4 * yld, pip += 4 * K * 32) {
+            if constexpr (STREAM) {
+                if (j + kYAhead + 3 < ch.Tw && (!ragged || j + kYAhead >= ch.off)) {   // rows of this lane's own window only
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) prefetch_l1(yp + (kYAhead + u) * yld);
+                }
+                const R c0 = yn[0], c1 = yn[1], c2v = yn[2], c3 = yn[3];
+                load4(j + 4, yp + 4 * yld);
+                step(j, 0, c0); step(j + 1, 1, c1); step(j + 2, 2, c2v); step(j + 3, 3, c3);
+            } else {
+                step(j, 0); step(j + 1, 1); step(j + 2, 2); step(j + 3, 3);
             }
-            step(j, 0); step(j + 1, 1); step(j + 2, 2); step(j + 3, 3);
             if constexpr (SIG) sp += 4 * ch.sld;
         }
-        for (; j < ch.Tw; ++j, yp += yld, pip += K * 32) {
-            step(j, 0);
+        for (int u = 0; j < ch.Tw; ++j, ++u, yp += yld, pip += K * 32) {
+            step(j, 0, u == 0 ? yn[0] : u == 1 ? yn[1] : yn[2]);
             if constexpr (SIG) sp += ch.sld;
         }
         o.events = events;
@@ -471,11 +488,15 @@ struct GibbsWarp {
         }
         auto flush = [&]() {
             if constexpr (Pack::kFlush) {
+                Row tmp[K];
 #pragma unroll
-                for (int r = 0; r < K; ++r) {
-                    Row v = b.tr.row[r];
+                for (int r = 0; r < K; ++r) tmp[r] = b.tr.row[r];
 #pragma unroll 1
-                    for (int c2 = 0; c2 < K; ++c2, v >>= Pack::kBits) o.n[r * K + c2] += (int)(v & (Row)Pack::kMaxT);
+                for (int r = 0; r < K; ++r) {                        // rolled over rows (dynamic index -> local memory) ...
+                    const Row v = tmp[r];
+#pragma unroll
+                    for (int c2 = 0; c2 < K; ++c2)                   // ... K independent read-modify-writes per row
+                        o.n[r * K + c2] += (int)((v >> (Pack::kBits * c2)) & (Row)Pack::kMaxT);
                 }
                 b.tr.clear();
                 since = 8;
@@ -584,6 +605,12 @@ struct GibbsWarp {
             };
 #pragma unroll
             for (int g = 0; g < kRing - 1; ++g) issue(g);
+            R ynx[4] = {R(0), R(0), R(0), R(0)};
+            auto loady4 = [&](int ii, const R* p) {                      // observations of steps ii..ii+3 (rows below p)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ynx[u] = (!ragged || ii + u < T) ? ld_ro(p - (u + 1) * ys) : R(0);
+            };
+            if constexpr (STREAM) { if (n_groups > 0) loady4(i, yp); }
             for (int g = 0; g < n_groups; ++g, i += 4, yp -= 4 * ys, pip -= 4 * K * 32, pap -= SMOOTH ? 4 * K * 32 : 0, sp -= 4 * ss) {
                 if constexpr (Pack::kFlush) { if ((since += 4) > Pack::kMaxT) flush(); }
                 if (STREAM && i + kYAhead + 3 < T) {                       // rows of steps i+kYAhead .. i+kYAhead+3 (this lane's window)
@@ -599,10 +626,15 @@ struct GibbsWarp {
                 for (int s = 0; s < K; ++s) {
                     c0[s] = st[(3 * K + s) * 32]; c1[s] = st[(2 * K + s) * 32]; c2[s] = st[(1 * K + s) * 32]; c3[s] = st[s * 32];
                 }
-                y0 = (!ragged || i + 0 < T) ? ld_ro(yp - 1 * ys) : R(0);
-                y1 = (!ragged || i + 1 < T) ? ld_ro(yp - 2 * ys) : R(0);
-                y2 = (!ragged || i + 2 < T) ? ld_ro(yp - 3 * ys) : R(0);
-                y3 = (!ragged || i + 3 < T) ? ld_ro(yp - 4 * ys) : R(0);
+                if constexpr (STREAM) {                                  // fetched one group ahead (see forward_pass)
+                    y0 = ynx[0]; y1 = ynx[1]; y2 = ynx[2]; y3 = ynx[3];
+                    if (g + 1 < n_groups) loady4(i + 4, yp - 4 * ys);
+                } else {
+                    y0 = (!ragged || i + 0 < T) ? ld_ro(yp - 1 * ys) : R(0);
+                    y1 = (!ragged || i + 1 < T) ? ld_ro(yp - 2 * ys) : R(0);
+                    y2 = (!ragged || i + 2 < T) ? ld_ro(yp - 3 * ys) : R(0);
+                    y3 = (!ragged || i + 3 < T) ? ld_ro(yp - 4 * ys) : R(0);
+                }
                 const R s0 = load_sw(0), s1 = load_sw(1), s2 = load_sw(2), s3 = load_sw(3);
                 w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
                 HMC_BACK(0, w.x, c0, y0, s0) HMC_BACK(1, w.y, c1, y1, s1) HMC_BACK(2, w.z, c2, y2, s2) HMC_BACK(3, w.w, c3, y3, s3)
