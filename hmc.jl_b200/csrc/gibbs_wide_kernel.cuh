@@ -2,10 +2,13 @@
 //
 // One chain is owned by a group of W lanes (W = 8, 16 or 32, the smallest that holds K); lane s of the group holds
 // state s: its mean/variance, its filtered probability, its sufficient statistics, and it draws row s of A.  32/W
-// chains share a warp.  The K x K transition matrix and the transition counters of a chain live in shared memory; the
-// forward step is K broadcast-shuffles + K FMAs per lane, the normaliser and the emission max are group reductions, and
-// the backward categorical draw is a group prefix sum + ballot/popc.  Same arithmetic, same Philox streams and the same
-// buffers as the thread-per-chain kernel (gibbs_kernel.cuh), so the two are interchangeable behind the plan.
+// chains share a warp.  The K x K transition matrix and the transition counters of a chain live in shared memory (rows
+// padded to an odd stride so that both row and column accesses are conflict-free); for the forward recursion lane s
+// keeps COLUMN s of A in registers and the filtered vector is broadcast through a double-buffered shared-memory line
+// (one STS + W/4 LDS.128 per lane instead of K shuffles), the emission maximum is one CREDUX (W = 32) or a shuffle
+// tree, the normaliser a shuffle tree, and the backward categorical draw a group prefix sum + ballot/popc.  Same
+// arithmetic, same Philox streams and the same buffers as the thread-per-chain kernels (gibbs_kernel.cuh), so the two
+// are interchangeable behind the plan.
 // Reference lines as in gibbs_kernel.cuh (src/Hmc.jl:231-369 draws, :371-440 forward, :459-484 backward, :501-513 relabel).
 #pragma once
 #include "gibbs_kernel.cuh"
@@ -26,9 +29,15 @@ struct WideChain {
         return v;
     }
     static __device__ __forceinline__ R gmax(R v, unsigned m) {
+        if constexpr (W == 32 && sizeof(R) == 4) {                 // sm_100a: one warp-wide float max (CREDUX.MAX.F32)
+            float r;
+            asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"((float)v));
+            return (R)r;
+        } else {
 #pragma unroll
-        for (int o = W / 2; o > 0; o >>= 1) { const R w = __shfl_xor_sync(m, v, o, W); v = v > w ? v : w; }
-        return v;
+            for (int o = W / 2; o > 0; o >>= 1) { const R w = __shfl_xor_sync(m, v, o, W); v = v > w ? v : w; }
+            return v;
+        }
     }
     static __device__ __forceinline__ R gscan(R v, unsigned m, int s) {   // inclusive prefix sum over the group
 #pragma unroll
@@ -37,9 +46,11 @@ struct WideChain {
     }
 };
 
-// dynamic shared memory per chain group: A [K*K] R, scratch [W] R, transition counters [K*K] int; padded to 16 bytes
+// dynamic shared memory per chain group: broadcast lines [2][W] R (first: 16-byte aligned), A [K][K|1] R, transition
+// counters [K*K] int; padded to 16 bytes
+__host__ __device__ constexpr int wide_row_stride(int K) { return K | 1; }
 template <typename R> __host__ __device__ constexpr size_t wide_group_bytes(int K, int W) {
-    return (sizeof(R) * ((size_t)K * K + (size_t)W) + sizeof(int) * (size_t)K * K + 15) / 16 * 16;
+    return (sizeof(R) * ((size_t)K * wide_row_stride(K) + 2 * (size_t)W) + sizeof(int) * (size_t)K * K + 15) / 16 * 16;
 }
 
 template <typename R, int W, bool LOGLIK>
@@ -57,9 +68,10 @@ __global__ void __launch_bounds__(kWideThreads) gibbs_wide_kernel(const GibbsArg
     if (T <= 0) return;                                       // whole group leaves together (T is group-uniform)
     const bool act = s < K;
     unsigned char* base = wide_smem + (size_t)grp * wide_group_bytes<R>(K, W);
-    R* const Asm = reinterpret_cast<R*>(base);                                  // A[r*K + c]
-    R* const scratch = Asm + (size_t)K * K;                                     // [W]
-    int* const tr = reinterpret_cast<int*>(scratch + W);                        // n_rc of the path being sampled
+    const int KP = wide_row_stride(K);
+    R* const scratch = reinterpret_cast<R*>(base);                              // [2][W] broadcast lines
+    R* const Asm = scratch + 2 * W;                                             // A[r*KP + c]
+    int* const tr = reinterpret_cast<int*>(Asm + (size_t)K * KP);               // n_rc of the path being sampled
 
     const long long yld = a.yld;
     const R* __restrict__ const y0 = reinterpret_cast<const R*>(a.y) + a.ybase[slot];
@@ -104,14 +116,18 @@ __global__ void __launch_bounds__(kWideThreads) gibbs_wide_kernel(const GibbsArg
             R rowsum = R(0);
             for (int j = 0; j < K; ++j) {
                 const R g = gamma_mt<R>((R)(tr[s * K + j] + 1), key, sweep, (KIND_A << 16) | (uint32_t)(s * K + j));
-                Asm[s * K + j] = g;
+                Asm[s * KP + j] = g;
                 rowsum += g;
             }
             const R inv = R(1) / rowsum;
-            for (int j = 0; j < K; ++j) { Asm[s * K + j] *= inv; tr[s * K + j] = 0; }
+            for (int j = 0; j < K; ++j) { Asm[s * KP + j] *= inv; tr[s * K + j] = 0; }
         }
         rho = rho / WC::gsum(rho, gm);
         __syncwarp(gm);
+        // column s of A in registers (zero outside K x K): pred_s = sum_r pf_r A[r][s]
+        R Ac[W];
+#pragma unroll
+        for (int r = 0; r < W; ++r) Ac[r] = (act && r < K) ? Asm[r * KP + s] : R(0);
 
         // ---- 2. forward filter
         R q = R(0), cc = R(0), isd = R(1), nrm = R(0);
@@ -125,10 +141,30 @@ __global__ void __launch_bounds__(kWideThreads) gibbs_wide_kernel(const GibbsArg
         }
         R pf = rho;
         R ll = R(0);
+        constexpr bool kMaxScale = (W == 32) && (sizeof(R) == 4);
+        R pfn = rho;                                       // normalised filtered probability of the current row (kMaxScale)
+        float lc = 0.f;
+        // observations: batches of 8 steps, fetched into registers one batch ahead, their lines pulled into L1 two more
+        // batches ahead (every chain of a wide batch streams its own series from HBM)
+        // (W = 32 already keeps a 32-register column of A: there only the L1 prefetch is used, registers buy occupancy)
+        constexpr bool kPipe = W < 32;
+        R ybn[8];
+        if constexpr (kPipe) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ybn[j] = (j < T) ? y0[(long long)j * yld] : R(0);
+        }
         for (int t0 = 0; t0 < T; t0 += 8) {
           R yb8[8];
+          if (s < 8 && t0 + 24 + s < T) prefetch_l1(y0 + (long long)(t0 + 24 + s) * yld);
+          if constexpr (kPipe) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) yb8[j] = (t0 + j < T) ? y0[(long long)(t0 + j) * yld] : R(0);
+            for (int j = 0; j < 8; ++j) yb8[j] = ybn[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ybn[j] = (t0 + 8 + j < T) ? y0[(long long)(t0 + 8 + j) * yld] : R(0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) yb8[j] = (t0 + j < T) ? y0[(long long)(t0 + j) * yld] : R(0);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int t = t0 + j;
@@ -144,9 +180,43 @@ __global__ void __launch_bounds__(kWideThreads) gibbs_wide_kernel(const GibbsArg
                 const R z = (yt - mu) * isd;
                 e = (R)exp(-0.5 * (double)(z * z)) * nrm;
             }
-            R pred = R(0);
-            for (int r = 0; r < K; ++r) pred = fma(__shfl_sync(gm, pf, r, W), act ? Asm[r * K + s] : R(0), pred);
+            // broadcast pf through shared memory (double-buffered: one __syncwarp per step is enough)
+            R* const line = scratch + (t & 1) * W;
+            line[s] = pf;
+            __syncwarp(gm);
+            R acc[4] = {R(0), R(0), R(0), R(0)};
+            constexpr int kVec = 16 / (int)sizeof(R);                  // elements per 16-byte shared-memory load
+            using V = typename std::conditional<sizeof(R) == 4, float4, double2>::type;
+#pragma unroll
+            for (int r0 = 0; r0 < W; r0 += kVec) {
+                const V v = *reinterpret_cast<const V*>(line + r0);
+                if constexpr (sizeof(R) == 4) {
+                    acc[0] = fma((R)v.x, Ac[r0], acc[0]); acc[1] = fma((R)v.y, Ac[r0 + 1], acc[1]);
+                    acc[2] = fma((R)v.z, Ac[r0 + 2], acc[2]); acc[3] = fma((R)v.w, Ac[r0 + 3], acc[3]);
+                } else {
+                    acc[(r0 / 2) & 3] = fma((R)v.x, Ac[r0], acc[(r0 / 2) & 3]);
+                    acc[(r0 / 2 + 1) & 3] = fma((R)v.y, Ac[r0 + 1], acc[(r0 / 2 + 1) & 3]);
+                }
+            }
+            const R pred = (acc[0] + acc[1]) + (acc[2] + acc[3]);
             const R qq = pred * e;
+            if constexpr (kMaxScale) {
+                // W = 32, fp32: the recursion continues with qq rescaled by the exact power of two of its maximum (one
+                // CREDUX), so the 5-step shuffle sum is needed only for the STORED row and the log-likelihood and
+                // overlaps the next step instead of sitting in the dependent chain (measured: the largest stall).
+                const float mx = (float)WC::gmax(qq, gm);
+                const bool ok = (mx > 0.f) && (mx < 3.0e38f);
+                const float scale = __int_as_float(0x7f000000 - (__float_as_int(mx) & 0x7f800000));   // 2^-floor(log2 mx)
+                const R tot = WC::gsum(qq, gm);
+                pfn = ok ? qq * Real<R>::rcp(tot) : (act ? R(1) / R(K) : R(0));
+                pf = ok ? (R)((float)qq * scale) : pfn;
+                if (!ok && s == 0) ++events;
+                if (LOGLIK) {   // tot is relative to the scale lc = log2(sum of the previous recursion vector)
+                    ll += (R)((Real<float>::lg2((float)tot) - lc + (float)m2) * 0.6931471805599453f);
+                    lc = ok ? Real<float>::lg2((float)tot * scale) : 0.f;
+                }
+                if (act) pi0[(long long)t * K + s] = pfn;
+            } else {
             const R tot = WC::gsum(qq, gm);
             const bool ok = (tot > R(0)) && (tot < R(3.0e38));
             pf = ok ? qq * Real<R>::rcp(tot) : (act ? R(1) / R(K) : R(0));
@@ -156,8 +226,10 @@ __global__ void __launch_bounds__(kWideThreads) gibbs_wide_kernel(const GibbsArg
                 else ll += (R)log((double)tot);
             }
             if (act) pi0[(long long)t * K + s] = pf;
+            }
           }
         }
+        if constexpr (kMaxScale) pf = pfn;                 // pif[N,:], normalised
         __syncwarp(gm);
 
         // ---- 3. relabel and emit
@@ -179,7 +251,7 @@ __global__ void __launch_bounds__(kWideThreads) gibbs_wide_kernel(const GibbsArg
             }
             for (int r = 0; r < K; ++r) {
                 const int rr = __shfl_sync(gm, rank, r, W);
-                if (act) o[(size_t)(2 * K + rank * K + rr) * cs] = Asm[r * K + s];      // emitted A[rr][rank] = A[r][s]
+                if (act) o[(size_t)(2 * K + rank * K + rr) * cs] = Asm[r * KP + s];     // emitted A[rr][rank] = A[r][s]
             }
             const int f0 = 3 * K + K * K;
             R v = pf;
@@ -187,7 +259,7 @@ __global__ void __launch_bounds__(kWideThreads) gibbs_wide_kernel(const GibbsArg
             for (int j = 0; j < a.n_h; ++j) {
                 for (; h < a.h_sorted[j]; ++h) {
                     R nv = R(0);
-                    for (int r = 0; r < K; ++r) nv = fma(__shfl_sync(gm, v, r, W), act ? Asm[r * K + s] : R(0), nv);
+                    for (int r = 0; r < K; ++r) nv = fma(__shfl_sync(gm, v, r, W), act ? Asm[r * KP + s] : R(0), nv);
                     v = nv;
                 }
                 const R f = WC::gsum(act ? v * mu : R(0), gm);
@@ -208,14 +280,26 @@ __global__ void __launch_bounds__(kWideThreads) gibbs_wide_kernel(const GibbsArg
         // rows and observations are fetched 8 steps at a time (they do not depend on the sampled states), so one
         // HBM/L2 latency is paid per 8 steps instead of per step
         constexpr int kBatch = 8;
-        for (int i0 = 0; i0 < T; i0 += kBatch) {
-            R ptb[kBatch], ytb[kBatch];
+        R ptn[kBatch], ytn[kBatch];                       // the batch after the one being processed
+        auto fetch = [&](int i0) {
 #pragma unroll
             for (int j = 0; j < kBatch; ++j) {
                 const int t = T - 1 - (i0 + j);
-                ptb[j] = (t >= 0 && act && (i0 + j) > 0) ? pi0[(long long)t * K + s] : R(0);
-                ytb[j] = (t >= 0) ? y0[(long long)t * yld] : R(0);
+                ptn[j] = (t >= 0 && act && (i0 + j) > 0) ? pi0[(long long)t * K + s] : R(0);
+                ytn[j] = (t >= 0) ? y0[(long long)t * yld] : R(0);
             }
+        };
+        if constexpr (kPipe) fetch(0);
+        for (int i0 = 0; i0 < T; i0 += kBatch) {
+            R ptb[kBatch], ytb[kBatch];
+            if constexpr (!kPipe) fetch(i0);
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) { ptb[j] = ptn[j]; ytb[j] = ytn[j]; }
+            {   // lines of the batch after next: lanes 0..7 of the group take one row each (y and the first line of the pif row)
+                const int t = T - 1 - (i0 + 2 * kBatch + s);
+                if (s < kBatch && t >= 0) { prefetch_l1(y0 + (long long)t * yld); prefetch_l1(pi0 + (long long)t * K); }
+            }
+            if constexpr (kPipe) fetch(i0 + kBatch);
 #pragma unroll
             for (int j = 0; j < kBatch; ++j) {
                 const int i = i0 + j;
@@ -250,7 +334,7 @@ __global__ void __launch_bounds__(kWideThreads) gibbs_wide_kernel(const GibbsArg
                 }
                 xn = x;
                 gate = __shfl_sync(gm, pt, x, W);
-                Acol = act ? Asm[s * K + x] : R(0);
+                Acol = act ? Asm[s * KP + x] : R(0);
             }
         }
         __syncwarp(gm);

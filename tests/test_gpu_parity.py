@@ -423,6 +423,42 @@ def test_wide_gibbs_fp32_posterior_matches_oracle(H, ctx, oracle):
     np.testing.assert_allclose(m[3 * K + K * K:3 * K + K * K + 4], ofc, atol=0.3)
 
 
+@pytest.mark.parametrize("K", [12, 20])
+def test_lane_kernel_fp32_posterior_and_loglik(H, ctx, oracle, K):
+    """fp32 lane-per-state kernel (W = 16 for K = 12, W = 32 with the max-rescaled recursion for K = 20): pooled posterior
+    means and the per-draw log-likelihood vs the oracle's."""
+    tr = _truth(K)
+    y, _ = synth_hmm(312, seed=3, **tr)
+    burn, nrun = 200, 100
+    o = _run(H, ctx, y, [1], [300], K=K, n_chains=64, burnin=burn, nrun=nrun, seed=4, horizons=(1, 12), precision=32,
+             flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY | H.FLAG_DRAWS | H.FLAG_LOGLIK)
+    m = o.summary_mean[0]
+    assert o.events == 0 and np.isfinite(m).all()
+    outs, _ = oracle.gibbs_batch([dict(y=y[:300], K=K, burnin=burn, nrun=nrun, seed=8, chain=c, horizons=(1, 12),
+                                       y_future=[y[300], y[311]]) for c in range(32)])
+    om = np.concatenate([r.mu for r in outs]).mean(0)
+    oA = np.concatenate([r.A for r in outs]).mean(0)
+    ofc = np.concatenate([r.forecasts for r in outs]).mean(0)
+    oll = np.concatenate([r.loglik for r in outs])
+    np.testing.assert_allclose(m[0:K], om, atol=0.4)
+    A = m[2 * K:2 * K + K * K].reshape(K, K).T
+    np.testing.assert_allclose(A, oA, atol=0.06)
+    np.testing.assert_allclose(A.sum(1), 1.0, atol=1e-4)
+    np.testing.assert_allclose(o.pi_end[0].sum(0), 1.0, atol=1e-4)
+    np.testing.assert_allclose(m[3 * K + K * K:3 * K + K * K + 4], ofc, atol=0.4)
+    assert abs(o.loglik[0].mean() - oll.mean()) < 0.02 * abs(oll.mean())
+    # the log-likelihood of a draw is a deterministic function of its parameters: re-filter a few draws with the oracle
+    for d in (0, 17, 63 * nrun + 5):
+        mu, s2 = o.mu[0][:, d], o.sigma2[0][:, d]
+        Ad = o.A[0][:, :, d].T                     # stored [s][r] -> A[r, s]
+        lls = []
+        for _ in range(1):
+            f = oracle.forward(y[:300], Ad, mu, s2, np.full(K, 1.0 / K), want_Pf=False)
+            lls.append(f.loglik)
+        # rho of the draw is not returned: the first step's prior differs, everything else is identical
+        assert abs(o.loglik[0][d] - lls[0]) < 6.0
+
+
 def test_insample_forecast_means(H, ctx, oracle):
     """forecastinsample (src/Hmc.jl:683-699): per-date posterior mean of pib[j,t,:]' A_j^h mu_j.  fp64 device chain vs the
     oracle chain on the same Philox streams (pib_full + per-draw mu, A from the oracle), plus an fp32 Monte-Carlo check."""
