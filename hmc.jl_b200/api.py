@@ -338,3 +338,35 @@ def forecastinsample(opt: EstOpt, horizon_index: int = -1, ctx: Optional[B.Conte
     for k in range(opt.D):
         table[f"s{k + 1}"] = o.pib_mean[0][:, k]
     return table
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Offline analytics of the reference, on the arrays the GPU path returns instead of on CSV files
+
+def signal_summaries(samples):
+    """Per-signal posterior means — what Hmc.runaggregate produces for a signals directory (groups = [:date, :signalid],
+    src/Hmc.jl:1062-1075).  Returns (signalids [S], dict name -> [S, columns])."""
+    ids = np.unique(samples.signalids)
+    R = samples.μ.shape[0]
+    tabs = {"filtered_means": samples.μ, "filtered_variances": samples.σ, "filtered_state_probs": samples.πb,
+            "filtered_trans_probs": np.transpose(samples.A, (0, 2, 1)).reshape(R, -1), "forecasts": samples.forecasts}
+    return ids, {k: np.stack([v[samples.signalids == i].mean(0) for i in ids]) for k, v in tabs.items()}
+
+
+def calcdispersion(samples):
+    """Mirror of Hmc.calcdispersion (src/Hmc.jl:1078-1090) for one end date: mean and standard deviation (n-1, like
+    Statistics.std) ACROSS the perturbed copies of the per-copy posterior means.  dict name -> (mean [cols], std [cols])."""
+    _, per_signal = signal_summaries(samples)
+    return {k: (v.mean(0), v.std(0, ddof=1) if len(v) > 1 else np.full(v.shape[1], np.nan)) for k, v in per_signal.items()}
+
+
+def calccorr(samples, D: int):
+    """Mirror of the per-date block of Hmc.calccorr (src/Hmc.jl:1092-1129): correlation matrix across draws of
+    [μ_1..D, σ_1..D, π_1..D, trans_i_j (column-major), first forecast].  Returns (names, matrix)."""
+    R = samples.μ.shape[0]
+    pib = samples.πb if samples.πb.ndim == 2 else samples.πb[:, -1, :]
+    cols = np.concatenate([samples.μ, samples.σ, pib, np.transpose(samples.A, (0, 2, 1)).reshape(R, D * D),
+                           samples.forecasts[:, :1]], axis=1)
+    names = [f"μ{i}" for i in range(1, D + 1)] + [f"σ{i}" for i in range(1, D + 1)] + [f"π{i}" for i in range(1, D + 1)] \
+        + [f"trans_{i}_{j}" for j in range(1, D + 1) for i in range(1, D + 1)] + ["forecast"]
+    return names, np.corrcoef(cols, rowvar=False)

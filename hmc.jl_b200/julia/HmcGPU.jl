@@ -6,6 +6,11 @@
 #     samples = HmcGPU.estimatemodel(opt)            # same NamedTuple fields: μ, σ, πb, A, forecasts, obsdates
 #     Hmc.saveresults(samples, opt, p; hassignals = false)
 #
+# and for the noisy-signal blocks (code/run_hmm.jl:133, :151, :174: `samples = Hmc.estimatesignals!(opt)`):
+#
+#     samples = HmcGPU.estimatesignals!(opt)         # μ, σ, πb, A, forecasts, obsdates, signalvals, signalids
+#     Hmc.saveresults(samples, opt, p; hassignals = true)
+#
 # NOTE: Julia is not installed in the build environment of this repository, so this file has never been executed
 # there.  It binds exactly the C ABI that tests/ exercise through Python ctypes (hmc.jl_b200/binding.py); the struct
 # layouts below mirror include/hmcgpu.h field by field (checked for the ctypes mirror in tests/test_host.py).
@@ -29,6 +34,7 @@ struct Problem
     xi::Ptr{Float64}; alpha::Ptr{Float64}; nu::Ptr{Float64}; beta0::Ptr{Float64}; beta::Ptr{Float64}
     kappa::Float64; is_signal::Ptr{UInt8}; horizons::Ptr{Int32}; n_h::Int32
     X0::Ptr{Int64}; precision::Int32; flags::UInt32
+    win_init_series::Ptr{Int32}; pi_row_back::Int32; is_signal_per_series::Int32
 end
 
 # struct hmcgpu_result
@@ -66,9 +72,15 @@ Returns per-window arrays in the reference's layouts: μ[w] (R×D), σ[w] (R×D)
 forecasts[w] (R×2|H|) with R = n_chains*Nrun (chain-major).  The output buffers are Julia column-major already
 (hmcgpu_result), so they are wrapped without a copy.
 """
-function estimate(ctx::Context, rawdata::Vector{Float64}, win_start::Vector{Int32}, win_end::Vector{Int32};
+function estimate(ctx::Context, rawdata::VecOrMat{Float64}, win_start::Vector{Int32}, win_end::Vector{Int32};
                   D::Int = 3, n_chains::Int = 1, burnin::Int = 1_000, Nrun::Int = 1_000, seed::Integer = 1234,
-                  horizons::Vector{Int32} = Int32[12], precision::Int = 64)
+                  horizons::Vector{Int32} = Int32[12], precision::Int = 64,
+                  win_series::Vector{Int32} = Int32[], win_init_series::Vector{Int32} = Int32[],
+                  is_signal::Vector{UInt8} = UInt8[], kappa::Float64 = 1.0, pi_row_back::Int = 0,
+                  xi::Vector{Float64} = Float64[], alpha::Vector{Float64} = Float64[], nu::Vector{Float64} = Float64[])
+    # rawdata: one series (Vector) or y_len × n_series (Matrix, column = series): exactly the library's column-major layout
+    y_len, n_series = size(rawdata, 1), size(rawdata, 2)
+    ptr_or_null(v) = isempty(v) ? Ptr{eltype(v)}(C_NULL) : pointer(v)
     nw, nh, R = length(win_start), length(horizons), n_chains * Nrun
     mu = Array{Float64}(undef, R, D, nw); sig = similar(mu); pie = similar(mu)
     A = Array{Float64}(undef, R, D, D, nw)
@@ -76,10 +88,11 @@ function estimate(ctx::Context, rawdata::Vector{Float64}, win_start::Vector{Int3
     status = zeros(Int32, n_chains, nw)
     res = Result(pointer(mu), pointer(sig), pointer(A), pointer(pie), nh > 0 ? pointer(fc) : C_NULL, C_NULL,
                  C_NULL, C_NULL, C_NULL, C_NULL, pointer(status), 0.0, 0.0, 0, 0, 0, 0, 0)
-    rc = GC.@preserve rawdata win_start win_end horizons mu sig A pie fc status begin
-        prob = Problem(pointer(rawdata), length(rawdata), 1, nw, C_NULL, pointer(win_start), pointer(win_end), C_NULL,
-                       D, n_chains, burnin, Nrun, UInt64(seed), C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, 1.0, C_NULL,
-                       pointer(horizons), nh, C_NULL, precision, FLAG_REF_Q1 | FLAG_DRAWS)
+    rc = GC.@preserve rawdata win_start win_end horizons mu sig A pie fc status win_series win_init_series is_signal xi alpha nu begin
+        prob = Problem(pointer(rawdata), y_len, n_series, nw, ptr_or_null(win_series), pointer(win_start), pointer(win_end), C_NULL,
+                       D, n_chains, burnin, Nrun, UInt64(seed), ptr_or_null(xi), ptr_or_null(alpha), ptr_or_null(nu), C_NULL, C_NULL,
+                       kappa, ptr_or_null(is_signal), pointer(horizons), nh, C_NULL, precision, FLAG_REF_Q1 | FLAG_DRAWS,
+                       ptr_or_null(win_init_series), pi_row_back, 0)
         ccall((:hmcgpu_estimate, LIB), Cint, (Ptr{Cvoid}, Ref{Problem}, Ref{Result}), ctx.h, prob, res)
     end
     rc < 0 && throw(HmcGpuError(rc, lasterror(ctx)))
@@ -93,14 +106,73 @@ GPU drop-in for `Hmc.estimatemodel(opt)` (src/Hmc.jl:850-865).  `opt` is an `Hmc
 Nrun×1×D array holding the end-of-window row: `saveresults` reads `samples.πb[:, end, :]` (src/Hmc.jl:744), which works
 unchanged; the Nrun×N×D tensor of the reference (3.5 GB per end date in production) is never materialised.
 """
+signalmask(opt) = (m = zeros(UInt8, length(opt.rawdata)); m[collect(opt.signalRange)] .= 0x01; m)
+
 function estimatemodel(opt; ctx::Context = Context(0), n_chains::Int = 1, precision::Int = 64)
-    isempty(opt.signalRange) || error("signalRange: the noisy-signal tier (estimatesignals!) is not implemented on the GPU path")
     sr = opt.sampleRange
-    r = estimate(ctx, Vector{Float64}(opt.rawdata), Int32[first(sr)], Int32[last(sr)]; D = opt.D, n_chains = n_chains,
-                 burnin = opt.burnin, Nrun = opt.Nrun, seed = opt.seed, horizons = Int32.(opt.horizons), precision = precision)
+    # a non-empty signalRange still goes through the signal branches with hp = HyperParams(Y, D), i.e. κ = 1.0 (src/Hmc.jl:853)
+    mask = isempty(opt.signalRange) ? UInt8[] : signalmask(opt)
+    y = Vector{Float64}(opt.rawdata)
+    r = estimate(ctx, y, Int32[first(sr)], Int32[last(sr)]; D = opt.D, n_chains = n_chains,
+                 burnin = opt.burnin, Nrun = opt.Nrun, seed = opt.seed, horizons = Int32.(opt.horizons), precision = precision,
+                 is_signal = mask, kappa = 1.0)
     R = n_chains * opt.Nrun
+    fc = r.forecasts[:, :, 1]
+    if last(sr) != opt.endIndex      # :861 scores the forecast from the window END against yobs(endIndex + h)
+        for (k, h) in enumerate(opt.horizons)
+            fc[:, 2k] = fc[:, 2k - 1] .- (opt.endIndex + h <= length(y) ? y[opt.endIndex + h] : NaN)
+        end
+    end
     return (μ = r.μ[:, :, 1], σ = r.σ[:, :, 1], πb = reshape(r.πbend[:, :, 1], R, 1, opt.D), A = r.A[:, :, :, 1],
-            forecasts = r.forecasts[:, :, 1], obsdates = fill(opt.dates[opt.endIndex], R))
+            forecasts = fc, obsdates = fill(opt.dates[opt.endIndex], R))
+end
+
+"""
+    estimatesignals!(opt; ctx = Context(0), n_chains = 1, precision = 64)
+
+GPU drop-in for `Hmc.estimatesignals!(opt)` (src/Hmc.jl:868-914).  The `opt.noiseSamples` perturbed copies of the sample
+are estimated side by side as independent chains (the reference chains them serially on one state, each with its own
+`signalburnin`); priors are `HyperParams(opt)` (α = ν = 2, ξ = mean of the real sample, κ = opt.noise), X0 comes from
+`makeParams` on the real data, `πb` is the smoothed row at `opt.endIndex` (:893), forecasts follow :900-906.
+Same logic as `estimatesignals` in hmc.jl_b200/api.py, which is the version the GPU tests exercise.
+"""
+function estimatesignals!(opt; ctx::Context = Context(0), n_chains::Int = 1, precision::Int = 64)
+    if isapprox(opt.σsignal, 0)
+        base = estimatemodel(opt; ctx = ctx, n_chains = n_chains, precision = precision)
+        opt.σsignal = sum(base.σ) / length(base.σ) * opt.noise
+    end
+    sr, D, S = opt.sampleRange, opt.D, opt.noiseSamples
+    y = Vector{Float64}(opt.rawdata)
+    sig = collect(opt.signalRange)
+    series = repeat(y, 1, S + 1)                                   # column 1 = real data, 2..S+1 perturbed copies
+    series[sig, 2:end] .+= randn(length(sig), S) .* opt.σsignal    # :890
+    sigLen = (isempty(sig) ? opt.endIndex : last(sig)) - opt.endIndex
+    hs = Int32[max(h - sigLen, 0) for h in opt.horizons]
+    xi = fill(sum(y[sr]) / length(sr), D)
+    r = estimate(ctx, series, fill(Int32(first(sr)), S), fill(Int32(last(sr)), S); D = D, n_chains = n_chains,
+                 burnin = opt.signalburnin, Nrun = opt.signalNrun, seed = opt.seed, horizons = hs, precision = precision,
+                 win_series = Int32.(1:S), win_init_series = zeros(Int32, S), is_signal = signalmask(opt), kappa = opt.noise,
+                 pi_row_back = last(sr) - opt.endIndex, xi = xi, alpha = fill(2.0, D), nu = fill(2.0, D))
+    R = n_chains * opt.signalNrun
+    cat2(a) = reduce(vcat, [a[:, :, w] for w in 1:S])
+    fc = cat2(r.forecasts)
+    for (k, h) in enumerate(opt.horizons)
+        yreal = opt.endIndex + h <= length(y) ? y[opt.endIndex + h] : NaN
+        if sigLen == h                                              # forecastsignal (:670-681), `noise` = σsignal (:904)
+            a = (1 / opt.σsignal) / (1 + 1 / opt.σsignal)
+            signal = repeat(series[opt.endIndex + h, 2:end], inner = R)
+            fc[:, 2k - 1] = a .* signal .+ (1 - a) .* fc[:, 2k - 1]
+            fc[:, 2k] = fc[:, 2k - 1] .- yreal
+        elseif sigLen > h
+            fc[:, 2k - 1:2k] .= NaN                                 # left unassigned by the reference
+        else
+            fc[:, 2k] = fc[:, 2k - 1] .- yreal
+        end
+    end
+    save = collect(opt.signalSave)
+    return (μ = cat2(r.μ), σ = cat2(r.σ), πb = cat2(r.πbend), A = reduce(vcat, [r.A[:, :, :, w] for w in 1:S]), forecasts = fc,
+            obsdates = fill(opt.dates[opt.endIndex], S * R),
+            signalvals = repeat(permutedims(series[save, 2:end]), inner = (R, 1)), signalids = repeat(1:S, inner = R))
 end
 
 end # module

@@ -134,3 +134,28 @@ def test_write_summaries_matches_reference_summary_columns(H, tmp_path):
     assert sorted(hdr) == sorted(g["columns"]["filtered_trans_probs"])          # same names (the goldens predate the :727 order)
     row = open(paths["filtered_means"]).read().splitlines()[2].split(",")
     assert row[0] == "1980-01-01" and [float(v) for v in row[1:]] == m[1, 0:3].tolist()
+
+
+def test_dispersion_and_correlation_analytics(H):
+    """calcdispersion / calccorr mirrors (src/Hmc.jl:1078-1129) on synthetic draw arrays."""
+    from types import SimpleNamespace
+    rng = np.random.default_rng(0)
+    S, R, D = 5, 40, 3
+    n = S * R
+    mu = np.sort(rng.normal(size=(n, D)), axis=1) + np.repeat(np.arange(S), R)[:, None]
+    s = SimpleNamespace(μ=mu, σ=rng.uniform(0.5, 2, size=(n, D)), πb=rng.dirichlet(np.ones(D), size=n),
+                        A=rng.dirichlet(np.ones(D), size=(n, D)), forecasts=np.stack([mu.sum(1), rng.normal(size=n)], 1),
+                        signalids=np.repeat(np.arange(1, S + 1), R))
+    ids, per = H.signal_summaries(s)
+    assert ids.tolist() == [1, 2, 3, 4, 5] and per["filtered_means"].shape == (S, D) and per["filtered_trans_probs"].shape == (S, 9)
+    np.testing.assert_allclose(per["filtered_means"][2], mu[2 * R:3 * R].mean(0))
+    disp = H.calcdispersion(s)
+    m, sd = disp["filtered_means"]
+    np.testing.assert_allclose(m, per["filtered_means"].mean(0))
+    np.testing.assert_allclose(sd, per["filtered_means"].std(0, ddof=1))
+    names, C = H.calccorr(s, D)
+    assert len(names) == 3 * D + D * D + 1 and C.shape == (len(names), len(names)) and names[9] == "trans_1_1" and names[10] == "trans_2_1"
+    np.testing.assert_allclose(np.diag(C), 1.0)
+    assert C[names.index("μ1"), names.index("forecast")] > 0.5
+    np.testing.assert_allclose(C[9, 0], np.corrcoef(s.A[:, 0, 0], mu[:, 0])[0, 1])      # trans_1_1 = A[1,1]
+    np.testing.assert_allclose(C[10, 0], np.corrcoef(s.A[:, 1, 0], mu[:, 0])[0, 1])     # trans_2_1 = A[2,1]
