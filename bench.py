@@ -202,7 +202,8 @@ def workload_config(args, world):
                              "c5": f"C5: independent series of T={args.length}, K={args.states}, one chain each",
                              "sig": "S1 noisy-signal Monte Carlo (estimatesignals!, src/Hmc.jl:868-914): 64 end dates x 100 perturbed "
                                     "copies, 12 signals after each end date (kappa = 1), smoothed state probabilities at the end date"}[args.workload],
-                "K": getattr(args, "K_run", K), "chains": args.chains, "burnin": args.burnin, "nrun": args.nrun, "precision": f"fp{args.precision}"}
+                "K": getattr(args, "K_run", K), "chains": getattr(args, "chains_run", args.chains), "burnin": args.burnin, "nrun": args.nrun,
+                "precision": f"fp{args.precision}", "l2": "pif spill working set exceeds the 126 MB L2; no flush needed"}
     return {"workload": "C2 rolling estimation: 500 expanding windows T=101..600 of one synthetic K=3 series (len 612, "
                         "default_rng(1234)), burnin+nrun Gibbs sweeps, forecasts h=1..12, per-window posterior summaries",
             "K": K, "windows": 500, "chains_per_window": args.chains * world, "burnin": args.burnin, "nrun": args.nrun,
@@ -285,6 +286,7 @@ def main():
         win_series = np.arange(n_ser, dtype=np.int32)
         n_chains = 1
         args.K_run = Kw
+    args.chains_run = int(len(ws_all) * n_chains)      # chains in the whole job
     shard = H.shard_windows(we_all - ws_all + 1, world)[rank]
     ws, we = ws_all[shard], we_all[shard]
     spec = H.ProblemSpec(y, ws, we, K=getattr(args, "K_run", K), n_chains=n_chains, burnin=args.burnin, nrun=args.nrun, seed=1234, horizons=HORIZONS,
@@ -359,6 +361,18 @@ def main():
                         "of all sweep launches; real DRAM traffic is 14-21 B per state-step (< 32 algorithmic: y and part of pif "
                         "hit L1/L2) and the kernel is FP32/INT issue-bound (DESIGN.md section 6)"}
 
+    # ---- second roofline (north_star: the slower of HBM traffic and FP32/MUFU issue): warp-instruction issue rate.
+    # instructions per warp-step come from the ncu capture of the same kernel (smsp__inst_executed.sum / warp-steps,
+    # profiles/r1_gibbs_sweeps_ncu_full_alltasks.txt); the peak is 4 schedulers x 1 warp-instr/clk x SMs at the SM clock
+    # sampled under load during this run.
+    wi = {3: 107.0}.get(getattr(args, "K_run", K)) if args.precision == 32 and args.workload == "c2" else None
+    issue = None
+    if wi is not None and clocks.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        ach = wi * (float(steps_per_run) * args.steps / 32.0) / (sweep_ms / 1e3)
+        pk = sms * 4 * clocks["sm_mhz"] * 1e6
+        issue = {"bound": "issue", "achieved": ach / 1e9, "peak": pk / 1e9, "unit": "Gwarp-inst/s", "frac": ach / pk,
+                 "warp_inst_per_warp_step": wi, "mufu_per_state_step": 4, "peak_source": "SMs x 4 x sampled SM clock"}
     if rank == 0:
         cb = None
         if not args.no_cpu_baseline and world == 1 and args.workload == "c2":
@@ -369,7 +383,7 @@ def main():
                 "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                         "ms_per_step": 1e3 * e2e_s / args.steps},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_issue": issue, "cpu_baseline": cb,
                 "check": {"mu_mean_longest_window": res.summary_mean[int(np.argmax(we - ws))][0:getattr(args, "K_run", K)].tolist(),
                           "events": int(res.events)}}
         print(json.dumps(line), flush=True)
