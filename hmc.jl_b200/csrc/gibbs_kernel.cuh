@@ -60,7 +60,16 @@ constexpr int kGibbsThreads = 128;
 #endif
 constexpr int kGibbsMinBlocks = HMC_MINBLOCKS;   // 5 blocks x 128 threads per SM -> register cap 102, 20 resident warps
 // K = 5..8 keep K x K matrices per thread: 2 blocks per SM (shared-memory tables and rings allow no more), 255 registers
-template <int K> constexpr int gibbs_min_blocks() { return K <= 4 ? kGibbsMinBlocks : 2; }
+#ifndef HMC_MINBLOCKS_F64
+#define HMC_MINBLOCKS_F64 3
+#endif
+#ifndef HMC_MINBLOCKS_SIG
+#define HMC_MINBLOCKS_SIG 4
+#endif
+// fp64 state needs twice the registers: 3 blocks per SM (168 registers) instead of spilling at 96
+template <typename R, int K, bool SIG> constexpr int gibbs_min_blocks() {
+    return K > 4 ? 2 : (sizeof(R) == 8 ? HMC_MINBLOCKS_F64 : (SIG ? HMC_MINBLOCKS_SIG : kGibbsMinBlocks));
+}
 // cp.async ring depth: the ring of a warp is stages x 4 rows x K x 32 lanes
 template <typename R, int K> constexpr int gibbs_ring_stages() { return K <= 4 ? kRing : (sizeof(R) == 4 ? 3 : 2); }
 
@@ -930,7 +939,7 @@ template <typename R, int K, bool WIDE> __host__ __device__ constexpr size_t gib
 }
 
 template <typename R, int K, bool SMOOTH, bool LOGLIK, bool WIDE, bool SIG = false>
-__global__ void __launch_bounds__(kGibbsThreads, gibbs_min_blocks<K>()) gibbs_sweeps_kernel(const GibbsArgs a) {
+__global__ void __launch_bounds__(kGibbsThreads, gibbs_min_blocks<R, K, SIG>()) gibbs_sweeps_kernel(const GibbsArgs a) {
     using W = GibbsWarp<R, K, SMOOTH, LOGLIK, WIDE, SIG>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename W::Entry* tab = reinterpret_cast<typename W::Entry*>(smem_raw);
