@@ -567,6 +567,35 @@ def test_signals_every_step_a_signal_and_ragged_batch(H, ctx, oracle):
         np.testing.assert_allclose(o.pi_end[w].T, r.pi_end, rtol=1e-7, atol=1e-12)
 
 
+def test_signals_per_series_masks_and_long_window(H, ctx, oracle):
+    """One mask per series (many end dates, each with its own signalRange, in one call: y is streamed per chain) and a
+    window long enough for the 64-bit packed transition counters (T > 1023 at K = 3)."""
+    rng = np.random.default_rng(3)
+    y0, _ = synth_hmm(1312, **K3_TRUTH)
+    ends = [1300, 1180, 90]
+    ys = np.stack([y0 + (rng.normal(0, 0.7, size=len(y0)) if i else 0.0) for i in range(3)])
+    mask = np.zeros_like(ys, dtype=np.uint8)
+    for i, e in enumerate(ends):
+        mask[i, e - 12:e] = 1
+        mask[i, 5 + i] = 1
+    two = np.full(3, 2.0)
+    o = _run(H, ctx, ys, [1, 1, 1], ends, K=3, n_chains=2, burnin=1, nrun=3, seed=21, horizons=(0, 12), precision=64,
+             flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_LOGLIK, win_series=[0, 1, 2], is_signal=mask, kappa=0.8, alpha=two, nu=two,
+             pi_row_back=12)
+    assert o.events == 0
+    for w, e in enumerate(ends):
+        for c in range(2):
+            r = oracle.gibbs(ys[w, :e], 3, 1, 3, seed=21, chain=w * 2 + c, horizons=(0, 12), y_future=[ys[w, e - 1], ys[w, e + 11]],
+                             is_signal=mask[w, :e], kappa=0.8, alpha=two, nu=two, flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM,
+                             want_pib_full=True)
+            sl = slice(c * 3, (c + 1) * 3)
+            np.testing.assert_allclose(o.mu[w][:, sl].T, r.mu, rtol=1e-7)
+            np.testing.assert_allclose(o.sigma2[w][:, sl].T, r.sigma2, rtol=1e-7)
+            np.testing.assert_allclose(np.transpose(o.A[w][:, :, sl], (2, 1, 0)), r.A, rtol=1e-7)
+            np.testing.assert_allclose(o.pi_end[w][:, sl].T, r.pib_full[:, e - 13, :], rtol=1e-6, atol=1e-12)
+            np.testing.assert_allclose(o.loglik[w][sl], r.loglik, rtol=1e-9)
+
+
 def test_user_initial_states_and_init_series(H, ctx, oracle):
     """X0 supplied by the caller, and makeParams / HyperParams read from another series than the chain runs on
     (estimatesignals! initialises from the real sample and estimates on the perturbed copy, src/Hmc.jl:888-892)."""
