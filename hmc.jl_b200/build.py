@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-HEADERS = [os.path.join(CSRC, f) for f in ("gibbs_kernel.cuh", "gibbs_pair_kernel.cuh", "gibbs_wide_kernel.cuh", "hmm_device.cuh", "rng.cuh")] + [
+HEADERS = [os.path.join(CSRC, f) for f in ("gibbs_kernel.cuh", "gibbs_pair_kernel.cuh", "gibbs_wide_kernel.cuh", "gibbs_scan_kernel.cuh", "hmm_device.cuh", "rng.cuh")] + [
     os.path.join(HERE, "..", "include", "hmcgpu.h")]
 LIB = os.path.join(HERE, "lib", "libhmcgpu.so")
 TAG = os.environ.get("HMC_TAG")             # experiment knob: build/load a side library lib/libhmcgpu_<tag>.so ...

@@ -2,6 +2,9 @@
 // compiled with -DHMC_R=<float|double> -DHMC_K=<2|3|4> (hmc.jl_b200/build.py builds the six units in parallel).
 #include <algorithm>
 #include "gibbs_kernel.cuh"
+#if HMC_K <= 4
+#include "gibbs_scan_kernel.cuh"
+#endif
 #ifdef HMC_WITH_PAIR
 #include "gibbs_pair_kernel.cuh"
 #endif
@@ -83,5 +86,24 @@ template <int K> cudaError_t launch_gibbs_pair(const GibbsLaunch& cfg, const Gib
 template cudaError_t launch_gibbs_pair<HMC_K>(const GibbsLaunch&, const GibbsArgs&, cudaStream_t);
 #endif
 template int gibbs_capacity_warps<HMC_R, HMC_K>(const GibbsLaunch&);
+
+#if HMC_K <= 4
+// narrow batches: one warp per chain, time-parallel (gibbs_scan_kernel.cuh); covers every slot in one launch
+template <typename R, int K> cudaError_t launch_gibbs_scan(const GibbsLaunch& cfg, const GibbsArgs& a, cudaStream_t st) {
+    const unsigned grid = (unsigned)((a.n_slots + kScanThreads / 32 - 1) / (kScanThreads / 32));
+    const size_t smem = (kScanThreads / 32) * scan_warp_bytes<R, K>(cfg.max_T);
+    auto go = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, kScanThreads, smem, st>>>(a, cfg.max_T);
+        return cudaGetLastError();
+    };
+    if (cfg.flags & 16u) return go(gibbs_scan_kernel<R, K, true>);
+    return go(gibbs_scan_kernel<R, K, false>);
+}
+template cudaError_t launch_gibbs_scan<HMC_R, HMC_K>(const GibbsLaunch&, const GibbsArgs&, cudaStream_t);
+#endif
 
 }  // namespace hmc

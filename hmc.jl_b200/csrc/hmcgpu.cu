@@ -3,6 +3,7 @@
 #include "../../include/hmcgpu.h"
 #include "gibbs_wide_kernel.cuh"
 #include "gibbs_pair_kernel.cuh"
+#include "gibbs_scan_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -970,6 +971,7 @@ struct hmcgpu_plan {
         events, cshift, xi, xi_user, chain_id, out, yfut_w, yfut, win_slot0, win_pib_off, totS, totQ, slot_pi_off;
     DevBuf sigmask, sigmask_tm, sigw, sbase, wsbase, wbase_init, X0, x0_off, cntM, Sm, Qm, totSm, totQm, totM;    // signals tier / user initial states
     bool sig = false;    // SIG kernels: signal mask and / or pi_row_back
+    bool scan = false;   // narrow batch: one warp per chain, time-parallel (gibbs_scan_kernel.cuh)
     bool wide = false;
     bool pair = false;   // fp32 paired kernel: a task is 64 chain slots (two chains per thread)
     int n_groups = 1, n_bufs = 1;
@@ -1065,6 +1067,16 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         const char* e = getenv("HMCGPU_PAIR");
         pl->pair = pl->pair && e && atoi(e) != 0;
     }
+    // Narrow batches (the reference's own regime: one chain per end date) cannot fill the GPU with a thread per chain:
+    // below kScanMaxChains chains the time-parallel warp-per-chain kernel is used (K <= 4, plain sweep, window in smem).
+    {
+        long long lim = 12288;
+        if (const char* e = getenv("HMCGPU_SCAN_MAX_CHAINS")) lim = atoll(e);
+        const int tmax = p->precision == 32 ? (K == 2 ? scan_max_T<float, 2>() : K == 3 ? scan_max_T<float, 3>() : scan_max_T<float, 4>())
+                                            : (K == 2 ? scan_max_T<double, 2>() : K == 3 ? scan_max_T<double, 3>() : scan_max_T<double, 4>());
+        pl->scan = !pl->wide && K <= 4 && !pl->sig && !pl->pair && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN) &&
+                   (long long)nw * nc <= lim && pl->max_T <= tmax;
+    }
     const int ts = pl->pair ? 64 : 32;
     const long long n_real = (long long)nw * nc;
     const int n_slots = (int)((n_real + ts - 1) / ts * ts);
@@ -1114,7 +1126,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         }
 
     // task groups: interleaved subsets of the (longest-first) warp tasks, each driven through its own stream
-    pl->n_groups = pl->wide ? 1 : (n_warps >= 1024 ? 4 : (n_warps >= 256 ? 2 : 1));
+    pl->n_groups = (pl->wide || pl->scan) ? 1 : (n_warps >= 1024 ? 4 : (n_warps >= 256 ? 2 : 1));
     if (const char* e = getenv("HMCGPU_GROUPS")) pl->n_groups = std::max(1, std::min(8, atoi(e)));
     pl->n_groups = std::min(pl->n_groups, n_warps);
     // double-buffered draw chunks let the groups drift apart (not with the smoothing accumulators, which are shared)
@@ -1263,7 +1275,8 @@ template <typename R, int K>
 static int plan_run_t(hmcgpu_plan* pl) {
     hmcgpu_ctx* ctx = pl->ctx;
     cudaStream_t st = ctx->stream;
-    const int ns = pl->n_slots, G = pl->n_groups, L = sweeps_per_launch();
+    const int ns = pl->n_slots, G = pl->n_groups;
+    const int L = (pl->scan && !getenv("HMCGPU_SWEEPS_PER_LAUNCH")) ? 64 : sweeps_per_launch();   // a scan sweep is a few µs
     const int Kr = pl->K;                                    // runtime K (the template K is 0 for the lane-per-state kernel)
     pl->n_launches = 0; pl->n_sweep_launches = 0; pl->sweep_ms = 0.0;
     size_t ev_used = 0;
@@ -1380,9 +1393,12 @@ static int plan_run_t(hmcgpu_plan* pl) {
             a.task0 = g; a.task_stride = G; a.n_tasks = (pl->n_warps - g + G - 1) / G;
             if constexpr (K == 0) {
                 CU(ctx, (launch_gibbs_wide<R>(cfg, a, pl->K, pl->slot_pi_off.as<long long>(), gs)));
-            } else if constexpr (std::is_same<R, float>::value && K <= 4) {
-                if (pl->pair) CU(ctx, (launch_gibbs_pair<K>(cfg, a, gs)));
-                else CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
+            } else if constexpr (K <= 4) {
+                if (pl->scan) CU(ctx, (launch_gibbs_scan<R, K>(cfg, a, gs)));
+                else if constexpr (std::is_same<R, float>::value) {
+                    if (pl->pair) CU(ctx, (launch_gibbs_pair<K>(cfg, a, gs)));
+                    else CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
+                } else CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
             } else {
                 CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
             }

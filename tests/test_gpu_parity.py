@@ -18,6 +18,14 @@ pytestmark = pytest.mark.gpu
 RTOL64, RTOL32 = 1e-5, 1e-3
 
 
+@pytest.fixture(autouse=True, params=["auto", "thread"])
+def _sweep_kernel_choice(request, monkeypatch):
+    """Narrow batches (most tests) are served by the time-parallel warp-per-chain kernel; every test also runs with that
+    kernel disabled so that the thread-per-chain kernels see the same small, ragged cases."""
+    if request.param == "thread":
+        monkeypatch.setenv("HMCGPU_SCAN_MAX_CHAINS", "0")
+
+
 def test_native_library_is_loaded(H, ctx):
     assert os.path.samefile(H.lib_path(), os.path.join(os.path.dirname(H.__file__), "lib", "libhmcgpu.so"))
     assert H.load().hmcgpu_device_count() >= 1
