@@ -350,6 +350,10 @@ struct ScanWarp {
                     }
                     if (LOGLIK) o[(size_t)(f0 + 2 * a.n_h) * cs] = ll;
                 }
+                // lane j owns horizon j: it fetches the realised value up front and stores the pair at the end, so the
+                // serial v <- v·A chain never waits for a global load
+                const R yr = (lane < a.n_h) ? reinterpret_cast<const R*>(a.yfut)[(size_t)a.h_slot[lane] * ns + slot] : R(0);
+                R myf = R(0);
                 int h = 0;
                 for (int j = 0; j < a.n_h; ++j) {                   // forecasts pib_T' A^h μ (:658-667, :858-862)
                     for (; h < a.h_sorted[j]; ++h) {
@@ -367,11 +371,11 @@ struct ScanWarp {
                     R f = v[0] * mu[0];
 #pragma unroll
                     for (int s = 1; s < K; ++s) f = fma(v[s], mu[s], f);
-                    if (lane == 0) {
-                        const R yr = reinterpret_cast<const R*>(a.yfut)[(size_t)a.h_slot[j] * ns + slot];
-                        o[(size_t)(f0 + 2 * a.h_slot[j]) * cs] = f;
-                        o[(size_t)(f0 + 2 * a.h_slot[j] + 1) * cs] = f - yr;
-                    }
+                    if (lane == j) myf = f;
+                }
+                if (lane < a.n_h) {
+                    o[(size_t)(f0 + 2 * a.h_slot[lane]) * cs] = myf;
+                    o[(size_t)(f0 + 2 * a.h_slot[lane] + 1) * cs] = myf - yr;
                 }
             }
 
@@ -395,12 +399,16 @@ struct ScanWarp {
             }
             // this lane draws X_t for t in [t0, tw): the owner of step T-1 leaves that step out (it is X[N])
             const int tw = (lane == lastlane) ? T - 1 : t1;
+            unsigned long long rec[K], recc = 0ull;                 // recorded paths: per entering state until coalescence, common after
+#pragma unroll
+            for (int h = 0; h < K; ++h) rec[h] = 0ull;
             unsigned F = 0x3210u;                                   // phase 1: composite map of the chunk (identity if it has no steps)
             if (lane <= lastlane) {
                 // the K walks (one per entering state) advance together; once they have coalesced one walk is enough
+                // the walked paths are recorded (2 bits per step; chunks of up to 32 steps) so that phase 3 only decodes
                 int x[K];
 #pragma unroll
-                for (int h = 0; h < K; ++h) x[h] = (lane == lastlane) ? xN : h;
+                for (int h = 0; h < K; ++h) { x[h] = (lane == lastlane) ? xN : h; rec[h] = 0ull; }
                 int t = tw - 1;
                 for (; t >= t0; --t) {
                     bool same = true;
@@ -408,12 +416,13 @@ struct ScanWarp {
                     for (int h = 1; h < K; ++h) same = same && (x[h] == x[0]);
                     if (same) break;
                     const R u = us[t];
+                    const int sh = 2 * ((tw - 1 - t) & 31);
 #pragma unroll
-                    for (int h = 0; h < K; ++h) x[h] = draw_step(pis, As, t, x[h], u);
+                    for (int h = 0; h < K; ++h) { x[h] = draw_step(pis, As, t, x[h], u); rec[h] |= (unsigned long long)x[h] << sh; }
                 }
                 if (t >= t0) {
                     int x0 = x[0];
-                    for (; t >= t0; --t) x0 = draw_step(pis, As, t, x0, us[t]);
+                    for (; t >= t0; --t) { x0 = draw_step(pis, As, t, x0, us[t]); recc |= (unsigned long long)x0 << (2 * ((tw - 1 - t) & 31)); }
 #pragma unroll
                     for (int h = 0; h < K; ++h) x[h] = x0;
                 }
@@ -436,8 +445,12 @@ struct ScanWarp {
             for (int i = 0; i < K; ++i) { tr[i] = 0ull; sdl[i] = R(0); qdl[i] = R(0); }
             {
                 int xn = g;
+                unsigned long long path = recc;
+#pragma unroll
+                for (int h = 0; h < K; ++h) path |= (g == h) ? rec[h] : 0ull;
+                const bool recorded = C <= 32;                      // longer chunks are walked again
                 for (int t = tw - 1; t >= t0; --t) {
-                    const int x = draw_step(pis, As, t, xn, us[t]);
+                    const int x = recorded ? (int)((path >> (2 * (tw - 1 - t))) & 3ull) : draw_step(pis, As, t, xn, us[t]);
                     const R d = ld_ro(y0 + (long long)t * yld) - c, dd = d * d;
                     const unsigned long long inc = 1ull << (16 * xn);
 #pragma unroll

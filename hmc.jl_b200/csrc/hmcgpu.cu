@@ -769,8 +769,12 @@ __global__ void __launch_bounds__(256) window_init_kernel(int K, const double* _
     const double sd = sqrt(block_reduce<double>(ss, shd, add) / (N - 1));             // Statistics.std (:177)
     double med = block_select(yi, ld, N, N / 2, shu);
     if (!(N & 1)) med = 0.5 * (block_select(yi, ld, N, N / 2 - 1, shu) + med);
-    const double R = mx - mn, lo = med - 0.25 * R, hi = med + 0.25 * R;               // :175-176
-    if ((int)threadIdx.x < K) mu0[threadIdx.x] = (K > 1) ? lo + (hi - lo) * ((double)threadIdx.x / (double)(K - 1)) : med;
+    // :175-176.  Rounded operation by operation (no FMA contraction), like the oracle: with an odd window length and an
+    // even K the median observation sits exactly on the boundary between two initial states, and which side it falls on
+    // is decided by the last bit of these grid points.
+    const double R = mx - mn, lo = __dsub_rn(med, __dmul_rn(0.25, R)), hi = __dadd_rn(med, __dmul_rn(0.25, R));
+    if ((int)threadIdx.x < K)
+        mu0[threadIdx.x] = (K > 1) ? __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), (double)threadIdx.x / (double)(K - 1))) : med;
     __syncthreads();
     for (int i = threadIdx.x; i < N; i += blockDim.x) {                               // :185-187 findmax of the pdfs
         if (X0u) { x0[i] = (unsigned char)(X0u[x0_off[w] + i] - 1); continue; }

@@ -178,6 +178,31 @@ def test_gibbs_first_sweeps_follow_the_oracle_chain(H, ctx, oracle):
             np.testing.assert_allclose(o.loglik[0][sl], r.loglik, rtol=1e-9)
 
 
+@pytest.mark.parametrize("K,T", [(2, 37), (3, 2), (3, 33), (3, 1500), (4, 334)])
+def test_chunk_shapes_follow_the_oracle_chain(H, ctx, oracle, K, T):
+    """Window lengths that stress the time-parallel kernel's chunking (idle lanes, one step per lane, chunks longer than
+    the 32-step path record) and K = 2, 4; the same cases run on the thread-per-chain kernel through the module fixture.
+    (K = 4 uses even window lengths: with an odd length the median observation lies exactly on the boundary between the
+    initial states 2 and 3 of makeParams, src/Hmc.jl:175-187, and its initial label is decided by rounding.)"""
+    tr = K3_TRUTH if K == 3 else _truth(K)
+    y, _ = synth_hmm(T + 3, seed=9 + K, **tr)
+    o = _run(H, ctx, y, [1, 2], [T, T + 1], K=K, n_chains=2, burnin=1, nrun=4, seed=5, horizons=(1, 2), precision=64,
+             flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_LOGLIK)
+    for w, (s, e) in enumerate(((1, T), (2, T + 1))):
+        if K % 2 == 0 and (e - s + 1) % 2 == 1:
+            continue
+        for c in range(2):
+            r = oracle.gibbs(y[s - 1:e], K, 1, 4, seed=5, chain=w * 2 + c, horizons=(1, 2), y_future=[y[e], y[e + 1]],
+                             flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM)
+            sl = slice(c * 4, (c + 1) * 4)
+            np.testing.assert_allclose(o.mu[w][:, sl].T, r.mu, rtol=1e-7, atol=1e-9)
+            np.testing.assert_allclose(o.sigma2[w][:, sl].T, r.sigma2, rtol=1e-7)
+            np.testing.assert_allclose(np.transpose(o.A[w][:, :, sl], (2, 1, 0)), r.A, rtol=1e-7, atol=1e-12)
+            np.testing.assert_allclose(o.pi_end[w][:, sl].T, r.pi_end, rtol=1e-6, atol=1e-12)
+            np.testing.assert_allclose(o.forecasts[w][:, sl].T, r.forecasts, rtol=1e-7, atol=1e-8)
+            np.testing.assert_allclose(o.loglik[w][sl], r.loglik, rtol=1e-8)
+
+
 def test_gibbs_reference_integration_test(H, ctx):
     """The reference's only test (test/runtests.jl:20-57) through the estimatemodel mirror, fp64 and fp32."""
     y, _ = synth_hmm(500, [[0.5, 0.5], [0.2, 0.8]], [-5.0, 4.0], [1.0, 0.5], seed=123)
