@@ -1078,6 +1078,10 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         if (const char* e = getenv("HMCGPU_SCAN_MAX_CHAINS")) lim = atoll(e);
         const int tmax = p->precision == 32 ? (K == 2 ? scan_max_T<float, 2>() : K == 3 ? scan_max_T<float, 3>() : scan_max_T<float, 4>())
                                             : (K == 2 ? scan_max_T<double, 2>() : K == 3 ? scan_max_T<double, 3>() : scan_max_T<double, 4>());
+        // long windows leave room for fewer resident warps (the window lives in shared memory): scale the bound with them
+        const size_t wb = (size_t)(p->precision / 8) * ((size_t)pl->max_T * (K + 1) + 4 * K);
+        const long long blocks = std::max<long long>(1, std::min<long long>(5, (long long)((227 * 1024) / (4 * wb + 1024))));
+        lim = lim * blocks / 5;
         pl->scan = !pl->wide && K <= 4 && !pl->sig && !pl->pair && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN) &&
                    (long long)nw * nc <= lim && pl->max_T <= tmax;
     }
