@@ -100,6 +100,10 @@ template <typename R, int K> cudaError_t launch_gibbs_scan(const GibbsLaunch& cf
         kern<<<grid, kScanThreads, smem, st>>>(a, cfg.max_T);
         return cudaGetLastError();
     };
+    if (cfg.sig) {
+        if (cfg.flags & 16u) return go(gibbs_scan_kernel<R, K, true, true>);
+        return go(gibbs_scan_kernel<R, K, false, true>);
+    }
     if (cfg.flags & 16u) return go(gibbs_scan_kernel<R, K, true>);
     return go(gibbs_scan_kernel<R, K, false>);
 }

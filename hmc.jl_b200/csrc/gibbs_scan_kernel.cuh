@@ -17,7 +17,9 @@
 //
 // Same Philox streams, same draw order and the same buffers as the thread-per-chain kernel (gibbs_kernel.cuh): the two
 // are interchangeable behind the plan and the fp64 chain follows the oracle's chain (the scans only change the
-// association of the products that bring the filtered vector to a chunk boundary).  K <= 4, no smoothing / signals.
+// association of the products that bring the filtered vector to a chunk boundary).  K <= 4; plain sweep and the signals
+// tier (SIG: signal mask, kappa-weighted statistics, pi_row_back — estimatesignals! runs 100 copies x ONE chain); no
+// smoothed-mean accumulators.
 #pragma once
 #include "gibbs_kernel.cuh"
 
@@ -30,7 +32,7 @@ template <typename R, int K> __host__ __device__ constexpr size_t scan_warp_byte
     return (sizeof(R) * ((size_t)max_T * K + (size_t)max_T + 4 * K) + 15) / 16 * 16;
 }
 
-template <typename R, int K, bool LOGLIK>
+template <typename R, int K, bool LOGLIK, bool SIG = false>
 struct ScanWarp {
     static constexpr unsigned kFull = 0xffffffffu;
 
@@ -87,9 +89,10 @@ struct ScanWarp {
     // A[i][j].  Arithmetic, order of operations and streams are those of draw_params (hmm_device.cuh): same results.
     static __device__ __forceinline__ int draw_params_warp(const int lane, const int (&cnt)[K], const R (&Sd)[K], const R (&Qd)[K],
                                                           const int (&trans)[K][K], R c, const Hyper<R, K>& hp, const RngKey& key,
-                                                          uint32_t sweep, R (&sig2)[K], R (&mu)[K], R (&rho)[K], R (&A)[K][K]) {
+                                                          uint32_t sweep, R (&sig2)[K], R (&mu)[K], R (&rho)[K], R (&A)[K][K],
+                                                          const SigStats<R, K>& sg) {
         int events = 0;
-        R ga[K], gb[K];
+        R ga[K], gb[K], neff[K], sumd[K], ntot[K];
         R shape = R(1);
         uint32_t purpose = (KIND_RHO << 16);
         bool mine = false;
@@ -99,12 +102,27 @@ struct ScanWarp {
             const R dbar = cnt[i] > 0 ? Sd[i] / n : R(0);
             R s2 = Qd[i] - n * dbar * dbar;
             s2 = s2 > R(0) ? s2 : R(0);
-            const R totalbar = cnt[i] > 0 ? dbar + c : R(0);
-            const R dev = totalbar - hp.xi[i];
+            R totalbar = cnt[i] > 0 ? dbar + c : R(0);
+            R ne = n, extra = R(0);
             ga[i] = hp.alpha[i] + R(0.5) * n;
+            sumd[i] = Sd[i]; ntot[i] = n;
+            if constexpr (SIG) {                                   // signals: same formulas as draw_params<SIG> (:267-314)
+                const R m = (R)sg.m[i];
+                const R sbar = sg.m[i] > 0 ? sg.Sm[i] / m : R(0);
+                R sm2 = sg.Qm[i] - m * sbar * sbar;
+                sm2 = sm2 > R(0) ? sm2 : R(0);
+                sumd[i] = Sd[i] + sg.Sm[i]; ntot[i] = n + m;
+                totalbar = (cnt[i] + sg.m[i]) > 0 ? sumd[i] / ntot[i] + c : R(0);
+                ne = n + m * sg.k1;
+                ga[i] += R(0.5) * m;
+                extra = R(0.5) * sg.k1 * sm2;
+            }
+            const R dev = totalbar - hp.xi[i];
             R b = hp.beta[i] + R(0.5) * s2;
-            b += R(0.5) * n * hp.nu[i] / (n + hp.nu[i]) * (dev * dev);
+            if constexpr (SIG) b += extra;
+            b += R(0.5) * ne * hp.nu[i] / (ne + hp.nu[i]) * (dev * dev);
             gb[i] = b;
+            neff[i] = ne;
             if (lane == i) { shape = ga[i]; purpose = (KIND_SIGMA << 16) | (uint32_t)i; mine = ga[i] > R(0) && b > R(0); }
             if (lane == K + i) { shape = R(1); purpose = (KIND_RHO << 16) | (uint32_t)i; mine = true; }
 #pragma unroll
@@ -125,8 +143,8 @@ struct ScanWarp {
         }
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            const R n = (R)cnt[i];
-            const R sum_y = Sd[i] + n * c;
+            const R n = neff[i];
+            const R sum_y = sumd[i] + ntot[i] * c;
             const R m = (sum_y + hp.nu[i] * hp.xi[i]) / (n + hp.nu[i]);
             const R sd = M<R>::sqrt(sig2[i] / (n + hp.nu[i]));
             mu[i] = m + sd * __shfl_sync(kFull, z, i);
@@ -147,6 +165,28 @@ struct ScanWarp {
             for (int j = 0; j < K; ++j) A[i][j] /= tot;
         }
         return events;
+    }
+
+    // emission of row t; signal rows (sw < 0) use sd x (1+kappa) (:382): z scaled by |sw| = 1/(1+kappa).  Returns the log2
+    // of the factor divided out (fp32), including the 1/(1+kappa) of the signal pdf.
+    static __device__ __forceinline__ R emission(const Emission<R, K>& em, R y, R sw, R (&e)[K]) {
+        if constexpr (!SIG) {
+            return em.eval(y, e);
+        } else if constexpr (sizeof(R) == 8) {
+            em.eval_scaled(y, sw, e);
+            return R(0);
+        } else {
+            const float a = fabsf((float)sw);
+            float l[K];
+#pragma unroll
+            for (int s = 0; s < K; ++s) { const float d = ((float)y - em.mu[s]) * a; l[s] = fmaf(d * d, em.q[s], em.c[s]); }
+            float m = l[0];
+#pragma unroll
+            for (int s = 1; s < K; ++s) m = fmaxf(m, l[s]);
+#pragma unroll
+            for (int s = 0; s < K; ++s) e[s] = Real<float>::ex2(l[s] - m);
+            return (R)(m + Real<float>::lg2(a));
+        }
     }
 
     // one backward draw: X_t | X_{t+1} = xn  (src/Hmc.jl:466-481 in the pif form, quirk Q5 included)
@@ -195,6 +235,24 @@ struct ScanWarp {
             for (int j = 0; j < K; ++j) trans[i][j] = a.trans[(i * K + j) * ns + slot];
         }
         int events = 0;
+        SigStats<R, K> sg;                                          // statistics of the signals (SIG; cnt/Sd/Qd: observations)
+        const R* s0 = nullptr;                                      // emission z-scale of row t: s0[t*sld], sign = signal flag
+        long long sld = 0;
+        if constexpr (SIG) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                sg.m[i] = a.cntM[i * ns + slot];
+                sg.Sm[i] = reinterpret_cast<const R*>(a.Sm)[i * ns + slot];
+                sg.Qm[i] = reinterpret_cast<const R*>(a.Qm)[i * ns + slot];
+            }
+            sg.k1 = (R)(1.0 / (1.0 + a.kappa));
+            sld = a.sld;
+            s0 = reinterpret_cast<const R*>(a.sigw) + a.sbase[slot];
+        }
+        auto sw_at = [&](int t) -> R {
+            if constexpr (SIG) return ld_ro(s0 + (long long)t * sld);
+            else return R(1);
+        };
 
         for (int sw = 0; sw < a.n_sweeps; ++sw) {
             const long long gs = a.sweep0 + sw;
@@ -202,7 +260,7 @@ struct ScanWarp {
             // ---- 1. conjugate draws (identical in every lane: same statistics, same counters)
 #pragma unroll
             for (int i = 0; i < K; ++i) hp.beta[i] = (R)(gs == 0 ? a.beta0[i] : a.beta[i]);
-            events += draw_params_warp(lane, cnt, Sd, Qd, trans, c, hp, key, sweep, sig2, mu, rho, A);
+            events += draw_params_warp(lane, cnt, Sd, Qd, trans, c, hp, key, sweep, sig2, mu, rho, A, sg);
             if (lane < K) {
 #pragma unroll
                 for (int r = 0; r < K; ++r) As[lane * 4 + r] = A[r][lane];
@@ -227,7 +285,7 @@ struct ScanWarp {
                 for (int j = 0; j < K; ++j) P[i][j] = (i == j) ? R(1) : R(0);
             for (int t = t0; t < t1; ++t) {                         // phase 1: product of the chunk's A diag(e_t)
                 R e[K], N[K][K];
-                em.eval(ld_ro(y0 + (long long)t * yld), e);
+                emission(em, ld_ro(y0 + (long long)t * yld), sw_at(t), e);
                 matmul(P, A, N);
 #pragma unroll
                 for (int i = 0; i < K; ++i)
@@ -275,7 +333,7 @@ struct ScanWarp {
             bool bad = false;
             for (int t = t0; t < t1; ++t) {                         // phase 3: the ordinary recursion over the chunk
                 R e[K];
-                const R m2 = em.eval(ld_ro(y0 + (long long)t * yld), e);
+                const R m2 = emission(em, ld_ro(y0 + (long long)t * yld), sw_at(t), e);
                 bool ok;
                 const R tot = forward_step<R, K>(A, e, pf, ok);
                 bad = bad || !ok;
@@ -301,7 +359,7 @@ struct ScanWarp {
                 int ev = 0;
                 for (int t = 0; t < T; ++t) {
                     R e[K];
-                    const R m2 = em.eval(ld_ro(y0 + (long long)t * yld), e);
+                    const R m2 = emission(em, ld_ro(y0 + (long long)t * yld), sw_at(t), e);
                     bool ok;
                     const R tot = forward_step<R, K>(A, e, pf, ok);
                     if (!ok) {
@@ -325,6 +383,19 @@ struct ScanWarp {
             }
             if (LOGLIK) ll = wsum(ll);
             __syncwarp();
+            R pend[K];                                              // what the draw reports as pi_end
+#pragma unroll
+            for (int s = 0; s < K; ++s) pend[s] = pf[s];
+            if constexpr (SIG) {
+                // samples.πb[:, endIndex, :] (:893): the smoothed marginal pi_back rows before the end of the window
+                const int nback = a.pi_back < T - 1 ? a.pi_back : T - 1;
+                for (int i = 1; i <= nback; ++i) {
+                    R row[K];
+#pragma unroll
+                    for (int s = 0; s < K; ++s) row[s] = pis[(T - 1 - i) * K + s];
+                    smooth_step<R, K>(A, row, pend);
+                }
+            }
 
             // ---- 3. relabel (:501-513) and emit the draw in increasing-μ order (lane 0 writes)
             int rank[K];
@@ -344,7 +415,7 @@ struct ScanWarp {
                     for (int s = 0; s < K; ++s) {
                         o[(size_t)(rank[s]) * cs] = mu[s];
                         o[(size_t)(K + rank[s]) * cs] = sig2[s];
-                        o[(size_t)(2 * K + K * K + rank[s]) * cs] = pf[s];
+                        o[(size_t)(2 * K + K * K + rank[s]) * cs] = pend[s];
 #pragma unroll
                         for (int r = 0; r < K; ++r) o[(size_t)(2 * K + rank[s] * K + rank[r]) * cs] = A[r][s];
                     }
@@ -440,9 +511,10 @@ struct ScanWarp {
             if (lane >= lastlane) g = xN;
             // phase 3: the actual path of this chunk and its statistics
             unsigned long long tr[K];
-            R sdl[K], qdl[K];
+            R sdl[K], qdl[K], sml[K], qml[K];                       // observations / signals (SIG)
+            int mil[K];
 #pragma unroll
-            for (int i = 0; i < K; ++i) { tr[i] = 0ull; sdl[i] = R(0); qdl[i] = R(0); }
+            for (int i = 0; i < K; ++i) { tr[i] = 0ull; sdl[i] = R(0); qdl[i] = R(0); sml[i] = R(0); qml[i] = R(0); mil[i] = 0; }
             {
                 int xn = g;
                 unsigned long long path = recc;
@@ -453,17 +525,26 @@ struct ScanWarp {
                     const int x = recorded ? (int)((path >> (2 * (tw - 1 - t))) & 3ull) : draw_step(pis, As, t, xn, us[t]);
                     const R d = ld_ro(y0 + (long long)t * yld) - c, dd = d * d;
                     const unsigned long long inc = 1ull << (16 * xn);
+                    const bool obs = !SIG || !(sw_at(t) < R(0));
 #pragma unroll
                     for (int i = 0; i < K; ++i)
-                        if (x == i) { tr[i] += inc; sdl[i] += d; qdl[i] += dd; }
+                        if (x == i) {
+                            tr[i] += inc;
+                            if (obs) { sdl[i] += d; qdl[i] += dd; }
+                            else { sml[i] += d; qml[i] += dd; mil[i] += 1; }
+                        }
                     xn = x;
                 }
             }
             if (lane == lastlane) {                                 // X[N] itself: occupancy and sums, no outgoing transition
                 const R d = ld_ro(y0 + (long long)(T - 1) * yld) - c, dd = d * d;
+                const bool obs = !SIG || !(sw_at(T - 1) < R(0));
 #pragma unroll
                 for (int i = 0; i < K; ++i)
-                    if (xN == i) { sdl[i] += d; qdl[i] += dd; }
+                    if (xN == i) {
+                        if (obs) { sdl[i] += d; qdl[i] += dd; }
+                        else { sml[i] += d; qml[i] += dd; mil[i] += 1; }
+                    }
             }
 #pragma unroll
             for (int i = 0; i < K; ++i) {
@@ -473,6 +554,13 @@ struct ScanWarp {
                 int n = (xN == i) ? 1 : 0;
 #pragma unroll
                 for (int j = 0; j < K; ++j) { trans[i][j] = (int)((row >> (16 * j)) & 0xffffull); n += trans[i][j]; }
+                if constexpr (SIG) {                              // split the occupancy into observations and signals
+                    sg.m[i] = (int)wsum((R)mil[i]);
+                    sg.Sm[i] = wsum(sml[i]);
+                    sg.Qm[i] = wsum(qml[i]);
+                    if (sg.m[i] == 0) { sg.Sm[i] = R(0); sg.Qm[i] = R(0); }
+                    n -= sg.m[i];
+                }
                 cnt[i] = n;
                 if (n == 0) { Sd[i] = R(0); Qd[i] = R(0); }
             }
@@ -487,19 +575,24 @@ struct ScanWarp {
                 reinterpret_cast<R*>(a.Qd)[i * ns + slot] = Qd[i];
 #pragma unroll
                 for (int j = 0; j < K; ++j) a.trans[(i * K + j) * ns + slot] = trans[i][j];
+                if constexpr (SIG) {
+                    a.cntM[i * ns + slot] = sg.m[i];
+                    reinterpret_cast<R*>(a.Sm)[i * ns + slot] = sg.Sm[i];
+                    reinterpret_cast<R*>(a.Qm)[i * ns + slot] = sg.Qm[i];
+                }
             }
             a.events[slot] += events;
         }
     }
 };
 
-template <typename R, int K, bool LOGLIK>
+template <typename R, int K, bool LOGLIK, bool SIG = false>
 __global__ void __launch_bounds__(kScanThreads) gibbs_scan_kernel(const GibbsArgs a, const int max_T) {
     extern __shared__ __align__(16) unsigned char scan_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.x * (kScanThreads / 32) + warp;
     if (slot >= a.n_slots) return;
-    ScanWarp<R, K, LOGLIK>::run(a, slot, lane, scan_smem + (size_t)warp * scan_warp_bytes<R, K>(max_T), max_T);
+    ScanWarp<R, K, LOGLIK, SIG>::run(a, slot, lane, scan_smem + (size_t)warp * scan_warp_bytes<R, K>(max_T), max_T);
 }
 
 template <typename R, int K> cudaError_t launch_gibbs_scan(const GibbsLaunch& cfg, const GibbsArgs& a, cudaStream_t st);

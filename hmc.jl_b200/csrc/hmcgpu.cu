@@ -1082,7 +1082,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         const size_t wb = (size_t)(p->precision / 8) * ((size_t)pl->max_T * (K + 1) + 4 * K);
         const long long blocks = std::max<long long>(1, std::min<long long>(5, (long long)((227 * 1024) / (4 * wb + 1024))));
         lim = lim * blocks / 5;
-        pl->scan = !pl->wide && K <= 4 && !pl->sig && !pl->pair && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN) &&
+        pl->scan = !pl->wide && K <= 4 && !pl->pair && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN) &&
                    (long long)nw * nc <= lim && pl->max_T <= tmax;
     }
     const int ts = pl->pair ? 64 : 32;
