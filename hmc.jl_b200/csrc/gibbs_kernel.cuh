@@ -865,7 +865,9 @@ struct GibbsWarp {
                                   : (ch.ragged ? backward_pass<true, false>(ch, pv, key, sweep, a.flags, save)
                                                : backward_pass<false, false>(ch, pv, key, sweep, a.flags, save));
                     // quirk Q5 fired somewhere: redo the pass exactly (counter-based RNG: identical draws otherwise)
-                    if (__builtin_expect(bo.bad, 0)) bo = backward_pass<true, true>(ch, pv, key, sweep, a.flags, save);
+                    // (warp-uniform: the pass stages rows through the warp's cp.async ring and synchronises the warp, so every
+                    //  lane must take part; lanes that had no Q5 case get identical results from the gated pass)
+                    if (__builtin_expect(__any_sync(0xffffffffu, bo.bad), 0)) bo = backward_pass<true, true>(ch, pv, key, sweep, a.flags, save);
                 }
                 b = bo.b;
                 xN = bo.xN;

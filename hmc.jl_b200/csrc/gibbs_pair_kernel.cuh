@@ -446,7 +446,7 @@ struct GibbsPair {
                 }
             BackOut bo = ch.ragged ? backward_pass<true, false>(ch, fo.pf, key[0], key[1], sweep, a.flags)
                                    : backward_pass<false, false>(ch, fo.pf, key[0], key[1], sweep, a.flags);
-            if (__builtin_expect(bo.bad, 0)) bo = backward_pass<true, true>(ch, fo.pf, key[0], key[1], sweep, a.flags);
+            if (__builtin_expect(__any_sync(0xffffffffu, bo.bad), 0)) bo = backward_pass<true, true>(ch, fo.pf, key[0], key[1], sweep, a.flags);   // warp-uniform (shared ring)
 
             // ---- unpack the statistics for the next sweep's draws
 #pragma unroll

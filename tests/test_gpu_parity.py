@@ -350,6 +350,31 @@ def test_full_size_properties_fp32(H, ctx):
     assert np.abs(m[big, 0:3] - K3_TRUTH["mu"]).max() < 1.2     # only 60 burn-in sweeps
 
 
+def test_zero_normaliser_events_are_counted_and_survived(H, ctx, monkeypatch):
+    """An observation so far out that every fp64 emission underflows (total = 0) — a tight variance prior (alpha = 1e4)
+    keeps the sampler from absorbing the outlier into one state's variance: the reference only warns (src/Hmc.jl:435)
+    and carries NaNs on; the device counts the event, resets that row to the uniform vector and goes on.  Both sweep
+    kernels (time-parallel: serial checked fallback; thread-per-chain: checked re-run) must agree over the first sweeps
+    (this posterior is degenerate — variances from 1e-4 to 800, probabilities of exactly 0 and 1 — so any last-bit
+    difference eventually sends the two chains to different modes); the fp32 path rescales and sees no event at all."""
+    y, _ = synth_hmm(212, **K3_TRUTH)
+    y[120] = 4.0e3
+    tight = np.full(3, 1.0e4)
+    outs = {}
+    for mode in ("scan", "thread"):
+        monkeypatch.setenv("HMCGPU_SCAN_MAX_CHAINS", "100000" if mode == "scan" else "0")
+        outs[mode] = _run(H, ctx, y, [1], [200], K=3, n_chains=3, burnin=0, nrun=3, seed=3, horizons=(1,), precision=64,
+                          flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_LOGLIK, alpha=tight)
+        o = outs[mode]
+        assert o.events == 3 and (o.status > 0).all()                       # every chain hit it (every sweep)
+        assert np.isfinite(o.mu).all() and np.isfinite(o.sigma2).all() and np.isfinite(o.A).all() and np.isfinite(o.pi_end).all()
+    np.testing.assert_allclose(outs["scan"].mu, outs["thread"].mu, rtol=1e-7)
+    np.testing.assert_allclose(outs["scan"].pi_end, outs["thread"].pi_end, rtol=1e-6, atol=1e-12)
+    o32 = _run(H, ctx, y, [1], [200], K=3, n_chains=3, burnin=2, nrun=6, seed=3, horizons=(1,), precision=32,
+               flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS, alpha=tight)
+    assert o32.events == 0 and np.isfinite(o32.mu).all()
+
+
 def test_error_paths(H, ctx):
     y = np.arange(50.0)
     with pytest.raises(H.HmcGpuError) as e:
