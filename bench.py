@@ -94,13 +94,32 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# Rank 0 prints ONE JSON line on stdout.  Libraries (NCCL's version banner, ...) write to file descriptor 1 directly, so
+# the descriptor is pointed at stderr for the whole run and the line goes to a private duplicate of the real stdout.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def dist_setup(n_gpus):
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     dist = None
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: NCCL's version banner (printed from NCCL_DEBUG=VERSION upwards, WARN
-        # included) and any other NCCL log line go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # (NCCL prints its version banner on stdout from NCCL_DEBUG=VERSION upwards; stdout is redirected, see emit_line)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -192,7 +211,7 @@ def run_reference(args):
                                                                    "Julia is not installed so the reference itself cannot run"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def workload_config(args, world):
@@ -231,6 +250,7 @@ def main():
                     help="dram__bytes_read+write per sweep-kernel launch from the ncu --set full capture "
                          "(profiles/r1_gibbs_sweeps_ncu_full.txt: one task group of 1000 warp tasks x 16 sweeps = 1.79e8 state-steps)")
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -400,7 +420,7 @@ def main():
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_issue": issue, "one_chain_per_end_date": literal, "cpu_baseline": cb,
                 "check": {"mu_mean_longest_window": res.summary_mean[int(np.argmax(we - ws))][0:getattr(args, "K_run", K)].tolist(),
                           "events": int(res.events)}}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
