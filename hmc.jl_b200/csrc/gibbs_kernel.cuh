@@ -54,6 +54,24 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 #define HMC_YAHEAD 16
 #endif
 constexpr int kYAhead = HMC_YAHEAD;
+// The pif spill of a warp task is tiled by groups of 4 time steps: tile q holds rows 4q..4q+3 (rows right-aligned to a
+// multiple of 4: row j of the warp frame sits at j + pad, pad = (4 - Tw % 4) % 4), element (state k, lane, row r) at
+// (k*32 + lane)*4 + r.  A lane's 4 rows of one state are 16 (fp32) / 32 (fp64) contiguous bytes: the forward pass
+// stores them with one (two) 128-bit STG per state and group, the backward pass reads them back from the cp.async ring
+// with one (two) LDS.128 — instead of 4 scalar accesses each.
+__device__ __forceinline__ void st_quad(float* p, float a, float b, float c, float d) { __stcg(reinterpret_cast<float4*>(p), make_float4(a, b, c, d)); }
+__device__ __forceinline__ void st_quad(double* p, double a, double b, double c, double d) {
+    __stcg(reinterpret_cast<double2*>(p), make_double2(a, b));
+    __stcg(reinterpret_cast<double2*>(p) + 1, make_double2(c, d));
+}
+__device__ __forceinline__ void ld_quad_shared(const float* p, float& a, float& b, float& c, float& d) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    a = v.x; b = v.y; c = v.z; d = v.w;
+}
+__device__ __forceinline__ void ld_quad_shared(const double* p, double& a, double& b, double& c, double& d) {
+    const double2 v = *reinterpret_cast<const double2*>(p), w = *(reinterpret_cast<const double2*>(p) + 1);
+    a = v.x; b = v.y; c = w.x; d = w.y;
+}
 constexpr int kGibbsThreads = 128;
 #ifndef HMC_MINBLOCKS
 #define HMC_MINBLOCKS 5
@@ -187,7 +205,7 @@ struct GibbsWarp {
         bool ragged;              // some lane of the warp has a shorter window (or is padding): steps are guarded
         long long yld;
         const R* y0;              // row j -> y0[j*yld]
-        R* pi0;                   // row j, state k -> pi0[(j*K + k)*32]
+        R* pi0;                   // row j, state k -> pi0[((j + pad) >> 2)*4*K*32 + k*128 + ((j + pad) & 3)]  (lane*4 folded in)
         R* pacc0;
         R* facc0;                 // in-sample forecast sums (SMOOTH): row j, horizon h -> facc0[(j*n_hi + h)*32]
         unsigned mh_off;          // shared memory (bytes): this thread's A^h mu vectors, mh[(h*K + s)*kGibbsThreads]
@@ -362,11 +380,13 @@ struct GibbsWarp {
                 for (int r = 0; r < K; ++r) A_l[r] = (float)ch.A[r][K - 1];
             }
         }
-        auto step = [&](int j, int u, R ypre = R(0)) {
+        R buf[4][K];                                                 // the 4 rows of the current tile (stored together)
+        // one step at row j = position u of its tile; yo / so: offsets (in rows) of y and of the z-scale from yp / sp
+        auto step = [&](int j, int u, int yo, R ypre, bool preloaded) {
             if (!ragged || j >= ch.off) {
-                const R yt = STREAM ? ypre : ld_ro(yp + u * yld);   // STREAM: loaded one iteration ahead by the caller
+                const R yt = preloaded ? ypre : ld_ro(yp + yo * yld);   // STREAM: loaded one iteration ahead by the caller
                 R sw = R(1);                                         // signals: sd x (1+kappa) (:382) <=> z scaled by 1/(1+kappa)
-                if constexpr (SIG) sw = ld_ro(sp + u * ch.sld);
+                if constexpr (SIG) sw = ld_ro(sp + yo * ch.sld);
                 if constexpr (sizeof(R) == 4) {
                     const f2 y2 = splat2((float)yt);
                     const f2 sw2 = splat2((float)sw);
@@ -435,10 +455,28 @@ struct GibbsWarp {
                     if (LOGLIK) ll += (R)log((double)tot);
                 }
 #pragma unroll
-                for (int s = 0; s < K; ++s) st_stream(pip + (u * K + s) * 32, pf[s]);
+                for (int s = 0; s < K; ++s) buf[u][s] = pf[s];
             }
         };
+        auto store_tile = [&]() {
+#pragma unroll
+            for (int s = 0; s < K; ++s) st_quad(pip + s * 128, buf[0][s], buf[1][s], buf[2][s], buf[3][s]);
+        };
+        const int pad = (4 - (ch.Tw & 3)) & 3;
         int j = 0;
+        {   // tile 0: its first `pad` positions are padding (rows are right-aligned to a multiple of 4)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int s = 0; s < K; ++s) buf[u][s] = R(0);
+                const int jj = u - pad;
+                if (jj >= 0 && jj < ch.Tw) step(jj, u, jj, R(0), false);
+            }
+            store_tile();
+            j = (4 - pad < ch.Tw) ? 4 - pad : ch.Tw;
+            yp += (long long)j * yld; pip += 4 * K * 32;
+            if constexpr (SIG) sp += (long long)j * ch.sld;
+        }
         // STREAM: the observations of the next 4 steps are fetched into registers one iteration ahead (from lines that
         // were pulled into L1 kYAhead steps ahead), so neither the DRAM nor the L1 latency sits in the dependent chain
         R yn[4] = {R(0), R(0), R(0), R(0)};
@@ -446,7 +484,7 @@ struct GibbsWarp {
 #pragma unroll
             for (int u = 0; u < 4; ++u) yn[u] = (jj + u < ch.Tw && (!ragged || jj + u >= ch.off)) ? ld_ro(p + u * yld) : R(0);
         };
-        if constexpr (STREAM) load4(0, yp);
+        if constexpr (STREAM) load4(j, yp);
         for (; j + 3 < ch.Tw; j += 4, yp += 4 * yld, pip += 4 * K * 32) {
             if constexpr (STREAM) {
                 if (j + kYAhead + 3 < ch.Tw && (!ragged || j + kYAhead >= ch.off)) {   // rows of this lane's own window only
@@ -455,16 +493,13 @@ struct GibbsWarp {
                 }
                 const R c0 = yn[0], c1 = yn[1], c2v = yn[2], c3 = yn[3];
                 load4(j + 4, yp + 4 * yld);
-                step(j, 0, c0); step(j + 1, 1, c1); step(j + 2, 2, c2v); step(j + 3, 3, c3);
+                step(j, 0, 0, c0, true); step(j + 1, 1, 1, c1, true); step(j + 2, 2, 2, c2v, true); step(j + 3, 3, 3, c3, true);
             } else {
-                step(j, 0); step(j + 1, 1); step(j + 2, 2); step(j + 3, 3);
+                step(j, 0, 0, R(0), false); step(j + 1, 1, 1, R(0), false); step(j + 2, 2, 2, R(0), false); step(j + 3, 3, 3, R(0), false);
             }
+            store_tile();
             if constexpr (SIG) sp += 4 * ch.sld;
-        }
-        for (int u = 0; j < ch.Tw; ++j, ++u, yp += yld, pip += K * 32) {
-            step(j, 0, u == 0 ? yn[0] : u == 1 ? yn[1] : yn[2]);
-            if constexpr (SIG) sp += ch.sld;
-        }
+        }                                                            // (no tail: the rows end on a tile boundary)
         o.events = events;
         return o;
     }
@@ -524,7 +559,11 @@ struct GibbsWarp {
             for (int i = 0; i < K - 1; ++i) { b.Sm[i] = R(0); b.Qm[i] = R(0); b.Mi[i] = 0; }
             b.nback = ch.pi_back < T - 1 ? ch.pi_back : (T > 0 ? T - 1 : 0);
         }
-        const R* pip = ch.pi0 + (size_t)(Tw - 1) * K * 32;
+        const int pad = (4 - (Tw & 3)) & 3;                          // tiles of 4 rows, right-aligned (see st_quad)
+        auto row_ptr = [&](int jrow) -> const R* {                   // state 0 of row jrow (state s: + s*128)
+            const int jp = jrow + pad;
+            return ch.pi0 + (size_t)(jp >> 2) * (4 * K * 32) + (jp & 3);
+        };
         R* pap = SMOOTH ? ch.pacc0 + (size_t)(Tw - 1) * K * 32 : nullptr;
         uint4 w = rng_block(key, sweep, (KIND_STATES << 16), 0u);
         if (T > 0) {
@@ -571,7 +610,11 @@ struct GibbsWarp {
         };
         auto load_row = [&](int u, R (&pt)[K], R& yt, R& st) {
 #pragma unroll
-            for (int s = 0; s < K; ++s) pt[s] = ld_stream(pip + (s - (u + 1) * K) * 32);
+            {
+                const R* rp = row_ptr(Tw - 1 - (i + u));
+#pragma unroll
+                for (int s = 0; s < K; ++s) pt[s] = ld_stream(rp + s * 128);
+            }
             yt = (!ragged || i + u < T) ? ld_ro(yp - (u + 1) * ys) : R(0);
             st = load_sw(u);
         };
@@ -588,7 +631,7 @@ struct GibbsWarp {
             if (Tw > 2) { HMC_BACK(1, w.z, p1, y1, s1) }
             if (Tw > 3) { HMC_BACK(2, w.w, p2, y2, s2) }
             const int done = Tw > 3 ? 3 : Tw - 1;
-            i += done; yp -= done * ys; pip -= (size_t)done * K * 32; if (SMOOTH) pap -= (size_t)done * K * 32;
+            i += done; yp -= done * ys; if (SMOOTH) pap -= (size_t)done * K * 32;
             if constexpr (SIG) sp -= done * ss;
         }
 #if HMC_ASYNC
@@ -602,7 +645,7 @@ struct GibbsWarp {
             R* const ring = reinterpret_cast<R*>(smem_base() + ch.ring_off);
             const int n_groups = (Tw - i) / 4;                          // full groups (i == 4 here when there are any)
             // group g (0-based) holds rows [jlo, jlo+3], jlo = Tw - 8 - 4g  (the rows of steps i = 4+4g .. 7+4g, highest first)
-            const R* gsrc = ch.pi0 - lane + (long long)(Tw - 8) * K * 32;   // row block of group 0, lane 0
+            const R* gsrc = ch.pi0 - lane * 4 + (long long)(Tw + pad - 8) * K * 32;   // tile of group 0, lane 0
             auto issue = [&](int g) {
                 if (g < n_groups) {
                     const char* src = reinterpret_cast<const char*>(gsrc - (long long)g * kGroupElems);
@@ -620,7 +663,7 @@ struct GibbsWarp {
                 for (int u = 0; u < 4; ++u) ynx[u] = (!ragged || ii + u < T) ? ld_ro(p - (u + 1) * ys) : R(0);
             };
             if constexpr (STREAM) { if (n_groups > 0) loady4(i, yp); }
-            for (int g = 0; g < n_groups; ++g, i += 4, yp -= 4 * ys, pip -= 4 * K * 32, pap -= SMOOTH ? 4 * K * 32 : 0, sp -= 4 * ss) {
+            for (int g = 0; g < n_groups; ++g, i += 4, yp -= 4 * ys, pap -= SMOOTH ? 4 * K * 32 : 0, sp -= 4 * ss) {
                 if constexpr (Pack::kFlush) { if ((since += 4) > Pack::kMaxT) flush(); }
                 if (STREAM && i + kYAhead + 3 < T) {                       // rows of steps i+kYAhead .. i+kYAhead+3 (this lane's window)
 #pragma unroll
@@ -629,12 +672,10 @@ struct GibbsWarp {
                 issue(g + kRing - 1);                                    // overwrites the stage consumed in iteration g-1
                 cp_async_wait<kRing - 1>();                              // group g has landed (for this lane's chunks)
                 __syncwarp();                                            // ... and for every other lane's
-                const R* st = ring + (g % kRing) * kGroupElems + lane;
+                const R* st = ring + (g % kRing) * kGroupElems + lane * 4;
                 R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3;
 #pragma unroll
-                for (int s = 0; s < K; ++s) {
-                    c0[s] = st[(3 * K + s) * 32]; c1[s] = st[(2 * K + s) * 32]; c2[s] = st[(1 * K + s) * 32]; c3[s] = st[s * 32];
-                }
+                for (int s = 0; s < K; ++s) ld_quad_shared(st + s * 128, c3[s], c2[s], c1[s], c0[s]);   // position 3 = highest row = first step
                 if constexpr (STREAM) {                                  // fetched one group ahead (see forward_pass)
                     y0 = ynx[0]; y1 = ynx[1]; y2 = ynx[2]; y3 = ynx[3];
                     if (g + 1 < n_groups) loady4(i + 4, yp - 4 * ys);
@@ -652,7 +693,7 @@ struct GibbsWarp {
             cp_async_wait<0>();
         }
 #else
-        for (; i + 3 < Tw; i += 4, yp -= 4 * ys, pip -= 4 * K * 32, pap -= SMOOTH ? 4 * K * 32 : 0, sp -= 4 * ss) {
+        for (; i + 3 < Tw; i += 4, yp -= 4 * ys, pap -= SMOOTH ? 4 * K * 32 : 0, sp -= 4 * ss) {
             if constexpr (Pack::kFlush) { if ((since += 4) > Pack::kMaxT) flush(); }
             R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3, s0, s1, s2, s3;
             load_row(0, c0, y0, s0); load_row(1, c1, y1, s1); load_row(2, c2, y2, s2); load_row(3, c3, y3, s3);
@@ -685,7 +726,7 @@ struct GibbsWarp {
         ch.Tw = a.warp_T[warp];
         ch.off = ch.Tw - ch.T;
         ch.yld = a.yld;
-        ch.pi0 = reinterpret_cast<R*>(a.pi) + a.warp_pi_off[warp] + lane;
+        ch.pi0 = reinterpret_cast<R*>(a.pi) + a.warp_pi_off[warp] + lane * 4;
         ch.pacc0 = SMOOTH ? reinterpret_cast<R*>(a.pib_acc) + a.warp_pi_off[warp] + lane : nullptr;
         ch.n_hi = (SMOOTH && a.fc_acc) ? a.n_h : 0;
         ch.facc0 = ch.n_hi ? reinterpret_cast<R*>(a.fc_acc) + a.warp_pi_off[warp] / K * ch.n_hi + lane : nullptr;

@@ -1118,7 +1118,8 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         for (int l = 0; l < ts; ++l) m = std::max(m, Ts[wp * ts + l]);
         warp_T[wp] = m;
         warp_off[wp] = pi_elems;
-        if (!pl->wide) pi_elems += (long long)m * K * ts;
+        // thread-per-chain kernels: rows right-aligned to tiles of 4 time steps (gibbs_kernel.cuh, st_quad)
+        if (!pl->wide) pi_elems += (long long)(pl->pair ? m : (m + 3) / 4 * 4) * K * ts;
         else for (int l = 0; l < ts; ++l) { slot_off[wp * ts + l] = pi_elems; pi_elems += (long long)Ts[wp * ts + l] * K; }
     }
     // forecasts: realised y at end+h per window (NaN outside the series), horizons sorted ascending
