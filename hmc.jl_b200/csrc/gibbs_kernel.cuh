@@ -731,6 +731,14 @@ struct GibbsWarp {
         ch.n_hi = (SMOOTH && a.fc_acc) ? a.n_h : 0;
         ch.facc0 = ch.n_hi ? reinterpret_cast<R*>(a.fc_acc) + a.warp_pi_off[warp] / K * ch.n_hi + lane : nullptr;
         ch.mh_off = (unsigned)(gibbs_smem_bytes<R, K, WIDE>(false, 0) + threadIdx.x * sizeof(R));
+        // realised future observations of this chain (forecast errors), cached once per launch: yf[j*threads + tid] for the
+        // j-th sorted horizon — the per-draw global loads sat in front of every forecast store
+        const unsigned yf_off = (unsigned)(gibbs_smem_bytes<R, K, WIDE>(false, 0) + (SMOOTH ? sizeof(R) * (size_t)a.n_h * K * kGibbsThreads : 0)
+                                           + threadIdx.x * sizeof(R));
+        {
+            R* yf = reinterpret_cast<R*>(smem_base() + yf_off);
+            for (int j = 0; j < a.n_h; ++j) yf[j * kGibbsThreads] = reinterpret_cast<const R*>(a.yfut)[(size_t)a.h_slot[j] * ns + slot];
+        }
         ch.y0 = reinterpret_cast<const R*>(a.y) + a.ybase[slot] - (long long)ch.off * ch.yld;
         ch.c = reinterpret_cast<const R*>(a.cshift)[slot];
         ch.tab_off = (unsigned)(threadIdx.x * sizeof(Entry));
@@ -849,7 +857,7 @@ struct GibbsWarp {
                     R f = v[0] * mu[0];
 #pragma unroll
                     for (int s = 1; s < K; ++s) f = fma(v[s], mu[s], f);
-                    const R yr = reinterpret_cast<const R*>(a.yfut)[(size_t)a.h_slot[j] * ns + slot];
+                    const R yr = reinterpret_cast<const R*>(smem_base() + yf_off)[j * kGibbsThreads];
                     o[(size_t)(f0 + 2 * a.h_slot[j]) * cs] = f;
                     o[(size_t)(f0 + 2 * a.h_slot[j] + 1) * cs] = f - yr;
                 }
@@ -978,7 +986,8 @@ struct GibbsWarp {
 template <typename R, int K, bool WIDE> __host__ __device__ constexpr size_t gibbs_smem_bytes(bool smooth, int n_h) {
     return sizeof(GibbsEntry<R, K, WIDE>) * K * kGibbsThreads                                    // selection tables
            + (HMC_ASYNC ? sizeof(R) * (size_t)(kGibbsThreads / 32) * gibbs_ring_stages<R, K>() * 4 * K * 32 : 0)      // cp.async rings
-           + (smooth ? sizeof(R) * (size_t)n_h * K * kGibbsThreads : 0);                          // A^h mu (in-sample forecasts)
+           + (smooth ? sizeof(R) * (size_t)n_h * K * kGibbsThreads : 0)                           // A^h mu (in-sample forecasts)
+           + sizeof(R) * (size_t)n_h * kGibbsThreads;                                             // realised y at end+h, per thread
 }
 
 template <typename R, int K, bool SMOOTH, bool LOGLIK, bool WIDE, bool SIG = false>
