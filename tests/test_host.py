@@ -159,3 +159,21 @@ def test_dispersion_and_correlation_analytics(H):
     assert C[names.index("μ1"), names.index("forecast")] > 0.5
     np.testing.assert_allclose(C[9, 0], np.corrcoef(s.A[:, 0, 0], mu[:, 0])[0, 1])      # trans_1_1 = A[1,1]
     np.testing.assert_allclose(C[10, 0], np.corrcoef(s.A[:, 1, 0], mu[:, 0])[0, 1])     # trans_2_1 = A[2,1]
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU port on the host cores; no GPU involved): exactly one JSON line on stdout with
+    the contract's keys, whatever the libraries print."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--burnin", "2", "--nrun", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
