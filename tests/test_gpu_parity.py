@@ -747,3 +747,12 @@ def test_estimatesignals_mirror(H, ctx, tmp_path):
     assert head == ["date", "signalid", "state_1", "state_2", "state_3"] + [f"signal_{i}" for i in range(1, 13)]
     row = open(paths["forecasts"]).readlines()[1].strip().split(",")
     assert row[1] == "1" and len(row) == 2 + 4 + 12
+
+
+def test_differential_fuzz_of_the_two_sweep_kernels():
+    """Random shapes (K, ragged windows, chains, signal masks, kappa, pi_row_back, user X0) through the time-parallel and the
+    thread-per-chain kernels in fp64: identical chains (scripts/fuzz_kernels.py; 300 cases were run when it was written)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_kernels.py"), "40", "7"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
