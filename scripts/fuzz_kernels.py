@@ -1,6 +1,7 @@
-"""Differential fuzzing of the two sweep kernels on the GPU box: random shapes (K, window lengths, ragged batches, chains,
-signal masks, kappa, pi_row_back, user X0) are estimated with the time-parallel warp-per-chain kernel and with the
-thread-per-chain kernel in fp64; the chains must coincide (same Philox streams).  python scripts/fuzz_kernels.py [n] [seed]"""
+"""Differential fuzzing of the sweep kernels on the GPU box: random shapes (K, window lengths, ragged batches, chains,
+signal masks, kappa, pi_row_back, user X0) are estimated in fp64 with two kernels that must produce the same chains (same
+Philox streams): K = 2..4 time-parallel warp-per-chain vs thread-per-chain; K = 5..8 thread-per-chain vs lane-per-state.
+python scripts/fuzz_kernels.py [n] [seed]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,7 +13,7 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 ctx = H.Context(0)
 bad = 0
 for case in range(n_cases):
-    K = int(rng.integers(2, 5))
+    K = int(rng.integers(2, 9))
     L = int(rng.integers(8, 900))
     mu = np.sort(rng.normal(0, 4, K)); s2 = rng.uniform(0.3, 2.0, K)
     A = rng.dirichlet(np.ones(K) * 0.5, K) * 0.3 + np.eye(K) * 0.7
@@ -27,7 +28,7 @@ for case in range(n_cases):
     kw = dict(K=K, n_chains=int(rng.integers(1, 4)), burnin=int(rng.integers(0, 2)), nrun=int(rng.integers(2, 5)), seed=int(rng.integers(1, 10**6)),
               horizons=tuple(sorted(set(rng.integers(0, 13, 2).tolist()))), precision=64,
               flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_LOGLIK | H.FLAG_SUMMARY, win_series=rng.integers(0, n_ser, nw))
-    if rng.random() < 0.5:                                     # signals tier
+    if K <= 4 and rng.random() < 0.5:                           # signals tier
         per_series = rng.random() < 0.5 and n_ser > 1
         mask = (rng.random((n_ser, L + 14) if per_series else (L + 14,)) < rng.choice([0.02, 0.3, 1.0])).astype(np.uint8)
         kw.update(is_signal=mask, kappa=float(rng.choice([0.0, 0.5, 2.0])), pi_row_back=int(rng.integers(0, min(6, int((we - ws).min()) + 1))),
@@ -35,10 +36,13 @@ for case in range(n_cases):
     if rng.random() < 0.3:
         kw.update(X0=[rng.integers(1, K + 1, int(e - s + 1)) for s, e in zip(ws, we)])
     outs = {}
-    for mode in ("scan", "thread"):
-        os.environ["HMCGPU_SCAN_MAX_CHAINS"] = "1000000" if mode == "scan" else "0"
+    for mode in ("first", "second"):
+        if K <= 4:
+            os.environ["HMCGPU_SCAN_MAX_CHAINS"] = "1000000" if mode == "first" else "0"
+        else:
+            os.environ["HMCGPU_LANE_KERNEL"] = "0" if mode == "first" else "1"
         outs[mode] = H.estimate(ctx, H.ProblemSpec(y, ws, we, **kw))
-    a, b = outs["scan"], outs["thread"]
+    a, b = outs["first"], outs["second"]
     ok = a.events == b.events
     for k in ("mu", "sigma2", "A", "pi_end", "forecasts", "loglik"):
         for w in range(nw):
