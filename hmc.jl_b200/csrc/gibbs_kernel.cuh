@@ -81,12 +81,15 @@ constexpr int kGibbsMinBlocks = HMC_MINBLOCKS;   // 5 blocks x 128 threads per S
 #ifndef HMC_MINBLOCKS_F64
 #define HMC_MINBLOCKS_F64 3
 #endif
+#ifndef HMC_MINBLOCKS_K56
+#define HMC_MINBLOCKS_K56 3
+#endif
 #ifndef HMC_MINBLOCKS_SIG
 #define HMC_MINBLOCKS_SIG 4
 #endif
 // fp64 state needs twice the registers: 3 blocks per SM (168 registers) instead of spilling at 96
 template <typename R, int K, bool SIG> constexpr int gibbs_min_blocks() {
-    return K > 4 ? 2 : (sizeof(R) == 8 ? HMC_MINBLOCKS_F64 : (SIG ? HMC_MINBLOCKS_SIG : kGibbsMinBlocks));
+    return K > 6 ? 2 : (K > 4 ? HMC_MINBLOCKS_K56 : (sizeof(R) == 8 ? HMC_MINBLOCKS_F64 : (SIG ? HMC_MINBLOCKS_SIG : kGibbsMinBlocks)));
 }
 // cp.async ring depth: the ring of a warp is stages x 4 rows x K x 32 lanes
 template <typename R, int K> constexpr int gibbs_ring_stages() { return K <= 4 ? kRing : (sizeof(R) == 4 ? 3 : 2); }
