@@ -10,10 +10,11 @@
 //   the usual ones) and stores the rows in shared memory.
 //
 //   backward sampling (update_X!, :459-484): X_t = f_t(X_{t+1}) where f_t is the K -> K map "categorical draw from
-//   pif[t,:]·A[:,x] with this step's uniform".  Phase 1: every lane walks its chunk once per possible entering state,
-//   which gives the chunk's composite map.  Phase 2: suffix scan of the maps (4-bit packed, function composition).
-//   Phase 3: each lane now knows the state entering its chunk from above and re-walks it once, accumulating the next
-//   sweep's sufficient statistics (:254-258, :291-294, :362-365); warp reductions pool them.
+//   pif[t,:]·A[:,x] with this step's uniform".  Phase 1: every lane walks its chunk for all K possible entering states
+//   at once (one walk after they have coalesced), recording the paths, which gives the chunk's composite map.  Phase 2:
+//   suffix scan of the maps (4-bit packed, function composition).  Phase 3: each lane now knows the state entering its
+//   chunk from above, decodes the recorded path of that state (chunks longer than 32 steps are walked again) and
+//   accumulates the next sweep's sufficient statistics (:254-258, :291-294, :362-365); warp reductions pool them.
 //
 // Same Philox streams, same draw order and the same buffers as the thread-per-chain kernel (gibbs_kernel.cuh): the two
 // are interchangeable behind the plan and the fp64 chain follows the oracle's chain (the scans only change the
