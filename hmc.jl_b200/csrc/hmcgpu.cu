@@ -1508,6 +1508,11 @@ extern "C" int hmcgpu_plan_fetch(hmcgpu_plan* pl, hmcgpu_result* r) {
         if (r->summary_mean) r->summary_mean[i] = m;
         if (r->summary_var) r->summary_var[i] = std::max(0.0, sumsq[i] / n - m * m);
     }
+    if (!sum.empty() && !(pl->flags & HMCGPU_FLAG_LOGLIK))      // the log-likelihood field is only produced with HMCGPU_FLAG_LOGLIK
+        for (int w = 0; w < nw; ++w) {
+            if (r->summary_mean) r->summary_mean[(size_t)w * pl->F + pl->F - 1] = 0.0;
+            if (r->summary_var) r->summary_var[(size_t)w * pl->F + pl->F - 1] = 0.0;
+        }
     for (size_t i = 0; i < pibsum.size(); ++i) r->pib_mean[i] = pibsum[i] / n;
     for (size_t i = 0; i < fcsum.size(); ++i) r->insample_forecast_mean[i] = fcsum[i] / n;
     // slot order -> caller order

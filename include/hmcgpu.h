@@ -106,7 +106,8 @@ typedef struct hmcgpu_problem {
  * States are emitted in increasing-μ order (:501-513).
  * Summary fields per window, F = 3K + K*K + 2*n_h + 1 in the order
  *   mu[K], sigma2[K], A[K*K] (index s*K+r), pi_end[K], forecasts[2*n_h], loglik:
- *   summary_mean[w*F + f], summary_var[w*F + f]  (population variance over the R pooled draws)
+ *   summary_mean[w*F + f], summary_var[w*F + f]  (population variance over the R pooled draws; the loglik field is 0
+ *   unless HMCGPU_FLAG_LOGLIK is set)
  * pib_mean: per window N_w x K column-major, concatenated: offset_w = K * sum_{v<w} N_v.
  * insample_forecast_mean: per window N_w x n_h column-major, concatenated (offset_w = n_h * sum_{v<w} N_v): the posterior
  *   mean of pib[t,:]' A^h mu for every date t of the window and every horizon (forecastinsample, src/Hmc.jl:683-699);

@@ -303,6 +303,34 @@ def test_expanding_windows_ragged_batch_and_sharding_invariance(H, ctx):
     np.testing.assert_array_equal(one.mu[0], full.mu[7])
 
 
+def test_estimate_multi_shards_windows_and_gathers_on_the_host(H, ctx):
+    """hmcgpu_estimate_multi: windows sharded over a device list (here device 0 twice: two host threads, two contexts), every
+    per-window output scattered back into the caller's arrays — identical to the single-context call, with and without the
+    signals-tier inputs (mask, X0, init series) and with the smoothed means."""
+    rng = np.random.default_rng(2)
+    y0, _ = synth_hmm(260, **K3_TRUTH)
+    ys = np.stack([y0, y0 + rng.normal(0, 0.3, size=len(y0))])
+    ws = np.array([1, 5, 2, 40, 1], dtype=np.int32); we = np.array([200, 180, 120, 240, 90], dtype=np.int32)
+    mask = np.zeros(len(y0), dtype=np.uint8); mask[60:66] = 1
+    X0 = [rng.integers(1, 4, int(e - s + 1)) for s, e in zip(ws, we)]
+    cases = [dict(flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_SUMMARY | H.FLAG_LOGLIK),
+             dict(flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_SUMMARY, is_signal=mask, kappa=0.7, X0=X0, win_init_series=[0] * 5, pi_row_back=2),
+             dict(flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY | H.FLAG_SMOOTHED_MEAN)]
+    for extra in cases:
+        kw = dict(K=3, n_chains=2, burnin=3, nrun=5, seed=9, horizons=(1, 12), precision=64, win_series=[1, 0, 1, 1, 0], **extra)
+        one = _run(H, ctx, ys, ws, we, **kw)
+        multi = H.estimate_multi([0, 0], H.ProblemSpec(ys, ws, we, **kw))
+        for k in ("mu", "sigma2", "A", "pi_end", "forecasts", "loglik", "summary_mean", "summary_var"):
+            if getattr(one, k) is not None:
+                np.testing.assert_array_equal(getattr(multi, k), getattr(one, k), err_msg=k)
+        if one.pib_mean is not None:
+            for a, b in zip(multi.pib_mean, one.pib_mean):
+                np.testing.assert_array_equal(a, b)
+            for a, b in zip(multi.insample_forecast_mean, one.insample_forecast_mean):
+                np.testing.assert_array_equal(a, b)
+        assert multi.state_steps == one.state_steps and multi.events == one.events
+
+
 def test_multiple_series_time_major_layout(H, ctx):
     rng = np.random.default_rng(3)
     ys = np.stack([synth_hmm(150, seed=s, **K3_TRUTH)[0] for s in range(5)])
