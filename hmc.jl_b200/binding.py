@@ -24,7 +24,7 @@ ERR_ARG, ERR_CUDA, ERR_ALLOC, ERR_UNSUPPORTED, ERR_NODEVICE = -1, -2, -3, -4, -5
 SYMBOLS = [
     "hmcgpu_version", "hmcgpu_device_count", "hmcgpu_ctx_create", "hmcgpu_ctx_destroy", "hmcgpu_last_error",
     "hmcgpu_ctx_sync", "hmcgpu_estimate", "hmcgpu_estimate_multi", "hmcgpu_plan_create", "hmcgpu_plan_run",
-    "hmcgpu_plan_fetch", "hmcgpu_plan_destroy", "hmcgpu_filter", "hmcgpu_smooth", "hmcgpu_sample_states",
+    "hmcgpu_plan_fetch", "hmcgpu_plan_destroy", "hmcgpu_filter", "hmcgpu_filter_masked", "hmcgpu_smooth", "hmcgpu_sample_states",
     "hmcgpu_draw_params", "hmcgpu_forecast", "hmcgpu_philox",
 ]
 
@@ -90,6 +90,8 @@ def load(build_if_missing: bool = True):
     L.hmcgpu_plan_destroy.restype = None
     L.hmcgpu_filter.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _dp, C.c_int64,
                                 _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+    L.hmcgpu_filter_masked.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _dp, C.c_int64, _u8p, C.c_double,
+                                       _dp, _dp, _dp, _dp, _dp, _dp, _dp]
     L.hmcgpu_smooth.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _dp, _dp, _dp]
     L.hmcgpu_sample_states.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, _dp, _dp, _dp, _dp, _i64p]
     L.hmcgpu_draw_params.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, _i64p, _dp, _dp, _i64p,
@@ -137,9 +139,10 @@ class Context:
         return rc
 
     # ---- deterministic pieces -------------------------------------------------------------------------------
-    def filter(self, y, A, mu, sigma2, rho, precision=64, want_totals=True):
+    def filter(self, y, A, mu, sigma2, rho, precision=64, want_totals=True, is_signal=None, kappa=1.0):
         """Batched forward filter (forwardupdate_P!, src/Hmc.jl:371-440). A [B,K,K], mu/sigma2/rho [B,K];
-        y [T] shared or [B,T].  Returns pif [B,T,K], totals [B,T], loglik [B]."""
+        y [T] shared or [B,T]; is_signal [T] (optional) flags the rows emitted with sd*(1+kappa) (:382).
+        Returns pif [B,T,K], totals [B,T], loglik [B]."""
         A, mu, sigma2, rho, y = map(_f64, (A, mu, sigma2, rho, y))
         B, K = mu.shape
         T = y.shape[-1]
@@ -147,8 +150,15 @@ class Context:
         pif = np.empty((B, T, K))
         totals = np.empty((B, T)) if want_totals else None
         ll = np.empty(B)
-        self._check(self.L.hmcgpu_filter(self.h, precision, K, B, T, _p(y), stride, _p(A), _p(mu), _p(sigma2), _p(rho),
-                                         _p(pif), _p(totals), _p(ll)))
+        if is_signal is None:
+            self._check(self.L.hmcgpu_filter(self.h, precision, K, B, T, _p(y), stride, _p(A), _p(mu), _p(sigma2), _p(rho),
+                                             _p(pif), _p(totals), _p(ll)))
+        else:
+            sig = np.ascontiguousarray(is_signal, dtype=np.uint8)
+            if sig.shape != (T,):
+                raise ValueError("is_signal must have one flag per time step")
+            self._check(self.L.hmcgpu_filter_masked(self.h, precision, K, B, T, _p(y), stride, _p(sig, _u8p), float(kappa), _p(A), _p(mu),
+                                                    _p(sigma2), _p(rho), _p(pif), _p(totals), _p(ll)))
         return SimpleNamespace(pif=pif, totals=totals, loglik=ll)
 
     def smooth(self, A, pif, precision=64):

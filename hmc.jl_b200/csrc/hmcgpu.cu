@@ -202,11 +202,12 @@ static bool k_thread_sweep(int K) {
 // ============================================================================================ deterministic entry points
 // One thread per batch element; host arrays are fp64 row-major and are converted on the fly.
 
+// sig (may be NULL): signal flag per time step, shared by the batch; signal rows use sd*(1+kappa) (src/Hmc.jl:382)
 template <typename R, int K>
 __global__ void filter_kernel(long long B, long long T, const double* __restrict__ y, long long ystride,
                               const double* __restrict__ A, const double* __restrict__ mu, const double* __restrict__ sig2,
                               const double* __restrict__ rho, double* __restrict__ pif, double* __restrict__ totals,
-                              double* __restrict__ loglik) {
+                              double* __restrict__ loglik, const unsigned char* __restrict__ sig, double kappa) {
     const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (b >= B) return;
     R a[K][K], m[K], s2[K], pf[K];
@@ -220,9 +221,30 @@ __global__ void filter_kernel(long long B, long long T, const double* __restrict
     em.prepare(m, s2);
     const double* yb = y + b * ystride;
     double ll = 0.0;
+    const R k1 = (R)(1.0 / (1.0 + kappa));
     for (long long t = 0; t < T; ++t) {
         R e[K];
-        const R m2 = em.eval((R)yb[t], e);
+        R m2;
+        if (sig && sig[t]) {                                  // z scaled by 1/(1+kappa), pdf by the same factor
+            if constexpr (sizeof(R) == 8) {
+                em.eval_scaled((R)yb[t], k1, e);
+                m2 = R(0);
+            } else {
+                // fp32: the scaled series point (y - mu)*k1 = (y*k1 - mu*k1) is not an affine image of y for all states at
+                // once, so evaluate the quadratic directly
+                float l[K];
+#pragma unroll
+                for (int s = 0; s < K; ++s) { const float d = ((float)yb[t] - (float)em.mu[s]) * (float)k1; l[s] = fmaf(d * d, (float)em.q[s], (float)em.c[s]); }
+                float mx = l[0];
+#pragma unroll
+                for (int s = 1; s < K; ++s) mx = fmaxf(mx, l[s]);
+#pragma unroll
+                for (int s = 0; s < K; ++s) e[s] = (R)Real<float>::ex2(l[s] - mx);
+                m2 = (R)(mx + Real<float>::lg2((float)k1));
+            }
+        } else {
+            m2 = em.eval((R)yb[t], e);
+        }
         bool ok;
         const R tot = forward_step<R, K>(a, e, pf, ok);
         if (!ok) {
@@ -555,10 +577,12 @@ static int check_common(hmcgpu_ctx* ctx, int K, long long B, long long T) {
 
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
-extern "C" int hmcgpu_filter(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, int64_t T, const double* y,
-                             int64_t ystride, const double* A, const double* mu, const double* sigma2, const double* rho,
-                             double* pif, double* totals, double* loglik) {
+static int filter_impl(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, int64_t T, const double* y,
+                       int64_t ystride, const uint8_t* is_signal, double kappa, const double* A, const double* mu,
+                       const double* sigma2, const double* rho, double* pif, double* totals, double* loglik) {
     TRY(check_common(ctx, K, B, T));
+    if (is_signal && !k_thread(K)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "the signal mask is only implemented for K <= 4");
+    if (is_signal && !(kappa >= 0.0)) return fail(ctx, HMCGPU_ERR_ARG, "kappa must be >= 0");
     if (!y || !A || !mu || !sigma2 || !rho || !pif) return fail(ctx, HMCGPU_ERR_ARG, "NULL input");
     if (precision != 32 && precision != 64) return fail(ctx, HMCGPU_ERR_ARG, "precision must be 32 or 64");
     if (ystride != 0 && ystride < T) return fail(ctx, HMCGPU_ERR_ARG, "y_batch_stride < T");
@@ -570,18 +594,32 @@ extern "C" int hmcgpu_filter(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int6
     TRY(x.up((double*)nullptr, (size_t)B * T * K, &dp));
     if (totals) TRY(x.up((double*)nullptr, (size_t)B * T, &dt));
     if (loglik) TRY(x.up((double*)nullptr, (size_t)B, &dl));
+    unsigned char* dsig = nullptr;
+    if (is_signal) TRY(x.up(reinterpret_cast<const unsigned char*>(is_signal), (size_t)T, &dsig));
     if (!k_thread(K)) {
         if (precision == 32) filter_kernel_generic<float><<<grid_for(B, 64), 64, 0, ctx->stream>>>(K, B, T, dy, ystride, dA, dmu, ds, dr, dp, dt, dl);
         else filter_kernel_generic<double><<<grid_for(B, 64), 64, 0, ctx->stream>>>(K, B, T, dy, ystride, dA, dmu, ds, dr, dp, dt, dl);
     }
     DISPATCH_K(K, {
-        if (precision == 32) filter_kernel<float, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dy, ystride, dA, dmu, ds, dr, dp, dt, dl);
-        else filter_kernel<double, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dy, ystride, dA, dmu, ds, dr, dp, dt, dl);
+        if (precision == 32) filter_kernel<float, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dy, ystride, dA, dmu, ds, dr, dp, dt, dl, dsig, kappa);
+        else filter_kernel<double, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, T, dy, ystride, dA, dmu, ds, dr, dp, dt, dl, dsig, kappa);
     });
     CU(ctx, cudaGetLastError());
     TRY(x.down(pif, dp, (size_t)B * T * K)); TRY(x.down(totals, dt, (size_t)B * T)); TRY(x.down(loglik, dl, (size_t)B));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return HMCGPU_OK;
+}
+
+extern "C" int hmcgpu_filter(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, int64_t T, const double* y,
+                             int64_t ystride, const double* A, const double* mu, const double* sigma2, const double* rho,
+                             double* pif, double* totals, double* loglik) {
+    return filter_impl(ctx, precision, K, B, T, y, ystride, nullptr, 1.0, A, mu, sigma2, rho, pif, totals, loglik);
+}
+
+extern "C" int hmcgpu_filter_masked(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, int64_t T, const double* y,
+                                    int64_t ystride, const uint8_t* is_signal, double kappa, const double* A, const double* mu,
+                                    const double* sigma2, const double* rho, double* pif, double* totals, double* loglik) {
+    return filter_impl(ctx, precision, K, B, T, y, ystride, is_signal, kappa, A, mu, sigma2, rho, pif, totals, loglik);
 }
 
 extern "C" int hmcgpu_smooth(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, int64_t T, const double* A,

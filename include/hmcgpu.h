@@ -9,7 +9,7 @@
  *   hmcgpu_estimate / hmcgpu_plan_*  <- estimatemodel (:850-865) = makeParams (:161-195) + HyperParams (:132-142)
  *                                       + gibbssample! (:517-562, gibbssweep! :486-515) + forecast loop (:858-862);
  *                                       called from code/run_hmm.jl:119
- *   hmcgpu_filter                    <- forwardupdate_P! (:371-440)   (fixed parameters -> pif, totals, loglik)
+ *   hmcgpu_filter / _filter_masked   <- forwardupdate_P! (:371-440)   (fixed parameters -> pif, totals, loglik; signal rows)
  *   hmcgpu_smooth                    <- backwardupdate_P! (:442-457)  (marginals pib)
  *   hmcgpu_sample_states             <- update_X! (:459-484)          (injected uniforms -> state path)
  *   hmcgpu_draw_params               <- update_μσ! draws (:302-335), update_ρ! (:350-356), update_A! (:358-369)
@@ -163,6 +163,12 @@ int hmcgpu_filter(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, int6
                   const double* y, int64_t y_batch_stride,
                   const double* A, const double* mu, const double* sigma2, const double* rho,
                   double* pif, double* totals, double* loglik);
+/* Same with the signal branch of forwardupdate_P! (:380-383, :396, :424): is_signal [T] flags the rows emitted with
+ * sd*(1+kappa) (one mask for the whole batch; NULL = hmcgpu_filter).  K <= 4. */
+int hmcgpu_filter_masked(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, int64_t T,
+                         const double* y, int64_t y_batch_stride, const uint8_t* is_signal, double kappa,
+                         const double* A, const double* mu, const double* sigma2, const double* rho,
+                         double* pif, double* totals, double* loglik);
 /* Smoothed marginals pib [B][T][K] from pif [B][T][K] and A [B][K][K]. */
 int hmcgpu_smooth(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, int64_t T,
                   const double* A, const double* pif, double* pib);

@@ -81,6 +81,23 @@ def test_filter_shared_series_and_extreme_observations(ctx, oracle):
 
 
 @pytest.mark.parametrize("precision,rtol", [(64, RTOL64), (32, RTOL32)])
+def test_filter_with_signal_rows_matches_oracle(ctx, oracle, precision, rtol):
+    """hmcgpu_filter_masked: signal rows are emitted with sd*(1+kappa) (src/Hmc.jl:380-383), first row included."""
+    rng = np.random.default_rng(77)
+    K, B, T = 3, 11, 300
+    A, mu, s2, rho = random_params(rng, B, K)
+    y = rng.normal(0, 3, size=T)
+    mask = (rng.random(T) < 0.3).astype(np.uint8); mask[0] = 1
+    for kappa in (0.0, 0.6, 3.0):
+        g = ctx.filter(y, A, mu, s2, rho, precision=precision, is_signal=mask, kappa=kappa)
+        for b in range(B):
+            f = oracle.forward(y, A[b], mu[b], s2[b], rho[b], is_signal=mask, kappa=kappa, want_Pf=False)
+            np.testing.assert_allclose(g.pif[b], f.pif, rtol=rtol, atol=rtol * 1e-3)
+            assert abs(g.loglik[b] - f.loglik) <= rtol * abs(f.loglik)
+            np.testing.assert_allclose(np.log(g.totals[b]), np.log(f.totals), rtol=0, atol=10 * rtol)
+
+
+@pytest.mark.parametrize("precision,rtol", [(64, RTOL64), (32, RTOL32)])
 def test_smoother_matches_oracle(ctx, oracle, precision, rtol):
     rng = np.random.default_rng(21)
     K, B, T = 3, 9, 500
