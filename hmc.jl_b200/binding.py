@@ -25,7 +25,7 @@ SYMBOLS = [
     "hmcgpu_version", "hmcgpu_device_count", "hmcgpu_ctx_create", "hmcgpu_ctx_destroy", "hmcgpu_last_error",
     "hmcgpu_ctx_sync", "hmcgpu_estimate", "hmcgpu_estimate_multi", "hmcgpu_plan_create", "hmcgpu_plan_run",
     "hmcgpu_plan_fetch", "hmcgpu_plan_destroy", "hmcgpu_filter", "hmcgpu_filter_masked", "hmcgpu_smooth", "hmcgpu_sample_states",
-    "hmcgpu_draw_params", "hmcgpu_forecast", "hmcgpu_philox",
+    "hmcgpu_draw_params", "hmcgpu_draw_params_signals", "hmcgpu_forecast", "hmcgpu_philox",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -96,6 +96,8 @@ def load(build_if_missing: bool = True):
     L.hmcgpu_sample_states.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, _dp, _dp, _dp, _dp, _i64p]
     L.hmcgpu_draw_params.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, _i64p, _dp, _dp, _i64p,
                                      _dp, _dp, _dp, _dp, C.c_uint64, C.c_uint32, C.c_uint32, _dp, _dp, _dp, _dp]
+    L.hmcgpu_draw_params_signals.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, _i64p, _dp, _dp, _i64p, _dp, _dp, C.c_double,
+                                             _i64p, _dp, _dp, _dp, _dp, C.c_uint64, C.c_uint32, C.c_uint32, _dp, _dp, _dp, _dp]
     L.hmcgpu_forecast.argtypes = [C.c_void_p, C.c_int32, C.c_int64, _dp, _dp, _dp, _i32p, C.c_int32, _dp, _dp]
     L.hmcgpu_philox.argtypes = [C.c_void_p, C.c_int64, _u32p, _u32p, _u32p]
     _lib = L
@@ -176,15 +178,22 @@ class Context:
         self._check(self.L.hmcgpu_sample_states(self.h, K, B, T, _p(A), _p(pif), _p(piN), _p(u), _p(X, _i64p)))
         return X
 
-    def draw_params(self, Ni, S, S2, trans, xi, alpha, nu, beta, seed, chain0, sweep, precision=64):
+    def draw_params(self, Ni, S, S2, trans, xi, alpha, nu, beta, seed, chain0, sweep, precision=64, Mi=None, Sm=None, Sm2=None, kappa=1.0):
         Ni = np.ascontiguousarray(Ni, dtype=np.int64)
         trans = np.ascontiguousarray(trans, dtype=np.int64)
         S, S2, xi, alpha, nu, beta = map(_f64, (S, S2, xi, alpha, nu, beta))
         B, K = Ni.shape
         s2, mu, rho, A = np.empty((B, K)), np.empty((B, K)), np.empty((B, K)), np.empty((B, K, K))
-        self._check(self.L.hmcgpu_draw_params(self.h, precision, K, B, _p(Ni, _i64p), _p(S), _p(S2), _p(trans, _i64p),
-                                              _p(xi), _p(alpha), _p(nu), _p(beta), seed, chain0, sweep,
-                                              _p(s2), _p(mu), _p(rho), _p(A)))
+        if Mi is None:
+            self._check(self.L.hmcgpu_draw_params(self.h, precision, K, B, _p(Ni, _i64p), _p(S), _p(S2), _p(trans, _i64p),
+                                                  _p(xi), _p(alpha), _p(nu), _p(beta), seed, chain0, sweep,
+                                                  _p(s2), _p(mu), _p(rho), _p(A)))
+        else:
+            Mi = np.ascontiguousarray(Mi, dtype=np.int64)
+            Sm, Sm2 = _f64(Sm), _f64(Sm2)
+            self._check(self.L.hmcgpu_draw_params_signals(self.h, precision, K, B, _p(Ni, _i64p), _p(S), _p(S2), _p(Mi, _i64p), _p(Sm),
+                                                          _p(Sm2), float(kappa), _p(trans, _i64p), _p(xi), _p(alpha), _p(nu), _p(beta),
+                                                          seed, chain0, sweep, _p(s2), _p(mu), _p(rho), _p(A)))
         return s2, mu, rho, A
 
     def forecast(self, mu, A, pi, horizons, yreal):

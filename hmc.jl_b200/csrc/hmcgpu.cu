@@ -318,9 +318,11 @@ __global__ void sample_states_kernel(long long B, long long T, const double* __r
     }
 }
 
+// Mi / Sm / Sm2 (may be NULL): counts, sums and centred sums of squares of the noisy signals per state (src/Hmc.jl:267-300)
 template <typename R, int K>
 __global__ void draw_params_kernel(long long B, const long long* __restrict__ Ni, const double* __restrict__ S,
-                                   const double* __restrict__ S2, const long long* __restrict__ trans,
+                                   const double* __restrict__ S2, const long long* __restrict__ Mi, const double* __restrict__ Sm,
+                                   const double* __restrict__ Sm2, double kappa, const long long* __restrict__ trans,
                                    const double* __restrict__ xi, const double* __restrict__ alpha, const double* __restrict__ nu,
                                    const double* __restrict__ beta, unsigned k0, unsigned k1, unsigned chain0, unsigned sweep,
                                    double* __restrict__ sig2o, double* __restrict__ muo, double* __restrict__ rhoo,
@@ -343,7 +345,20 @@ __global__ void draw_params_kernel(long long B, const long long* __restrict__ Ni
         for (int j = 0; j < K; ++j) tr[i][j] = (int)trans[(b * K + i) * K + j] - 1;  // API counts include the +1 prior
     }
     const RngKey key{k0, k1, chain0 + (unsigned)b};
-    draw_params<R, K>(cnt, Sd, Qd, tr, R(0), hp, key, sweep, sig2, mu, rho, A);
+    if (Mi) {
+        SigStats<R, K> sg;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            sg.m[i] = (int)Mi[b * K + i];
+            const double m = (double)sg.m[i], sbar = sg.m[i] > 0 ? Sm[b * K + i] / m : 0.0;
+            sg.Sm[i] = (R)Sm[b * K + i];
+            sg.Qm[i] = (R)(Sm2[b * K + i] + m * sbar * sbar);
+        }
+        sg.k1 = (R)(1.0 / (1.0 + kappa));
+        draw_params<R, K, true>(cnt, Sd, Qd, tr, R(0), hp, key, sweep, sig2, mu, rho, A, &sg);
+    } else {
+        draw_params<R, K>(cnt, Sd, Qd, tr, R(0), hp, key, sweep, sig2, mu, rho, A);
+    }
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         sig2o[b * K + i] = (double)sig2[i]; muo[b * K + i] = (double)mu[i]; rhoo[b * K + i] = (double)rho[i];
@@ -662,11 +677,15 @@ extern "C" int hmcgpu_sample_states(hmcgpu_ctx* ctx, int32_t K, int64_t B, int64
     return HMCGPU_OK;
 }
 
-extern "C" int hmcgpu_draw_params(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, const int64_t* Ni,
-                                  const double* S, const double* S2, const int64_t* trans, const double* xi,
-                                  const double* alpha, const double* nu, const double* beta, uint64_t seed,
-                                  uint32_t chain0, uint32_t sweep, double* sigma2, double* mu, double* rho, double* A) {
+static int draw_params_impl(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, const int64_t* Ni,
+                            const double* S, const double* S2, const int64_t* Mi, const double* Sm, const double* Sm2, double kappa,
+                            const int64_t* trans, const double* xi,
+                            const double* alpha, const double* nu, const double* beta, uint64_t seed,
+                            uint32_t chain0, uint32_t sweep, double* sigma2, double* mu, double* rho, double* A) {
     TRY(check_common(ctx, K, B, 1));
+    if (Mi && (!Sm || !Sm2)) return fail(ctx, HMCGPU_ERR_ARG, "Mi given without Sm / Sm2");
+    if (Mi && !k_thread(K)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "signal statistics are only implemented for K <= 4");
+    if (Mi && !(kappa >= 0.0)) return fail(ctx, HMCGPU_ERR_ARG, "kappa must be >= 0");
     if (!Ni || !S || !S2 || !trans || !xi || !alpha || !nu || !beta || !sigma2 || !mu || !rho || !A)
         return fail(ctx, HMCGPU_ERR_ARG, "NULL input");
     if (precision != 32 && precision != 64) return fail(ctx, HMCGPU_ERR_ARG, "precision must be 32 or 64");
@@ -679,20 +698,44 @@ extern "C" int hmcgpu_draw_params(hmcgpu_ctx* ctx, int32_t precision, int32_t K,
     TRY(x.up(xi, (size_t)K, &dxi)); TRY(x.up(alpha, (size_t)K, &dal)); TRY(x.up(nu, (size_t)K, &dnu)); TRY(x.up(beta, (size_t)K, &dbe));
     TRY(x.up((double*)nullptr, (size_t)B * K, &o1)); TRY(x.up((double*)nullptr, (size_t)B * K, &o2));
     TRY(x.up((double*)nullptr, (size_t)B * K, &o3)); TRY(x.up((double*)nullptr, (size_t)B * K * K, &o4));
+    long long* dM = nullptr;
+    double *dSm = nullptr, *dSm2 = nullptr;
+    if (Mi) {
+        TRY(x.up(reinterpret_cast<const long long*>(Mi), (size_t)B * K, &dM));
+        TRY(x.up(Sm, (size_t)B * K, &dSm)); TRY(x.up(Sm2, (size_t)B * K, &dSm2));
+    }
     const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
     if (!k_thread(K)) {
         if (precision == 32) draw_params_kernel_generic<float><<<grid_for(B, 64), 64, 0, ctx->stream>>>(K, B, dN, dS, dS2, dT, dxi, dal, dnu, dbe, k0, k1, chain0, sweep, o1, o2, o3, o4);
         else draw_params_kernel_generic<double><<<grid_for(B, 64), 64, 0, ctx->stream>>>(K, B, dN, dS, dS2, dT, dxi, dal, dnu, dbe, k0, k1, chain0, sweep, o1, o2, o3, o4);
     }
     DISPATCH_K(K, {
-        if (precision == 32) draw_params_kernel<float, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, dN, dS, dS2, dT, dxi, dal, dnu, dbe, k0, k1, chain0, sweep, o1, o2, o3, o4);
-        else draw_params_kernel<double, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, dN, dS, dS2, dT, dxi, dal, dnu, dbe, k0, k1, chain0, sweep, o1, o2, o3, o4);
+        if (precision == 32) draw_params_kernel<float, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, dN, dS, dS2, dM, dSm, dSm2, kappa, dT, dxi, dal, dnu, dbe, k0, k1, chain0, sweep, o1, o2, o3, o4);
+        else draw_params_kernel<double, KK><<<grid_for(B, 64), 64, 0, ctx->stream>>>(B, dN, dS, dS2, dM, dSm, dSm2, kappa, dT, dxi, dal, dnu, dbe, k0, k1, chain0, sweep, o1, o2, o3, o4);
     });
     CU(ctx, cudaGetLastError());
     TRY(x.down(sigma2, o1, (size_t)B * K)); TRY(x.down(mu, o2, (size_t)B * K)); TRY(x.down(rho, o3, (size_t)B * K));
     TRY(x.down(A, o4, (size_t)B * K * K));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return HMCGPU_OK;
+}
+
+extern "C" int hmcgpu_draw_params(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, const int64_t* Ni,
+                                  const double* S, const double* S2, const int64_t* trans, const double* xi,
+                                  const double* alpha, const double* nu, const double* beta, uint64_t seed,
+                                  uint32_t chain0, uint32_t sweep, double* sigma2, double* mu, double* rho, double* A) {
+    return draw_params_impl(ctx, precision, K, B, Ni, S, S2, nullptr, nullptr, nullptr, 1.0, trans, xi, alpha, nu, beta, seed, chain0,
+                            sweep, sigma2, mu, rho, A);
+}
+
+extern "C" int hmcgpu_draw_params_signals(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B, const int64_t* Ni,
+                                          const double* S, const double* S2, const int64_t* Mi, const double* Sm, const double* Sm2,
+                                          double kappa, const int64_t* trans, const double* xi, const double* alpha,
+                                          const double* nu, const double* beta, uint64_t seed, uint32_t chain0, uint32_t sweep,
+                                          double* sigma2, double* mu, double* rho, double* A) {
+    if (!Mi) return fail(ctx, HMCGPU_ERR_ARG, "Mi is NULL");
+    return draw_params_impl(ctx, precision, K, B, Ni, S, S2, Mi, Sm, Sm2, kappa, trans, xi, alpha, nu, beta, seed, chain0, sweep,
+                            sigma2, mu, rho, A);
 }
 
 extern "C" int hmcgpu_forecast(hmcgpu_ctx* ctx, int32_t K, int64_t B, const double* mu, const double* A, const double* pi,

@@ -12,7 +12,8 @@
  *   hmcgpu_filter / _filter_masked   <- forwardupdate_P! (:371-440)   (fixed parameters -> pif, totals, loglik; signal rows)
  *   hmcgpu_smooth                    <- backwardupdate_P! (:442-457)  (marginals pib)
  *   hmcgpu_sample_states             <- update_X! (:459-484)          (injected uniforms -> state path)
- *   hmcgpu_draw_params               <- update_μσ! draws (:302-335), update_ρ! (:350-356), update_A! (:358-369)
+ *   hmcgpu_draw_params / _signals    <- update_μσ! draws (:302-335; with signal statistics :267-314), update_ρ! (:350-356),
+ *                                       update_A! (:358-369)
  *   hmcgpu_forecast                  <- forecast (:658-667)
  *
  * Conventions
@@ -183,6 +184,14 @@ int hmcgpu_draw_params(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B,
                        const double* xi, const double* alpha, const double* nu, const double* beta,
                        uint64_t seed, uint32_t chain0, uint32_t sweep,
                        double* sigma2, double* mu, double* rho, double* A);
+/* Same with the noisy signals of update_μσ! (:267-314): Mi [B][K] signal counts, Sm [B][K] sums, Sm2 [B][K] centred sums of
+ * squares of the signals of each state, kappa their relative imprecision (Ni / S / S2 then cover the observations only).  K <= 4. */
+int hmcgpu_draw_params_signals(hmcgpu_ctx* ctx, int32_t precision, int32_t K, int64_t B,
+                               const int64_t* Ni, const double* S, const double* S2,
+                               const int64_t* Mi, const double* Sm, const double* Sm2, double kappa, const int64_t* trans,
+                               const double* xi, const double* alpha, const double* nu, const double* beta,
+                               uint64_t seed, uint32_t chain0, uint32_t sweep,
+                               double* sigma2, double* mu, double* rho, double* A);
 /* out [B][2*n_h]: forecast and error for each horizon; yreal [n_h]. */
 int hmcgpu_forecast(hmcgpu_ctx* ctx, int32_t K, int64_t B, const double* mu, const double* A, const double* pi,
                     const int32_t* horizons, int32_t n_h, const double* yreal, double* out);

@@ -169,6 +169,28 @@ def test_conjugate_draws_match_oracle_streams(ctx, oracle):
     assert np.isclose(Af, A, rtol=5e-3, atol=1e-5).mean() > 0.99
 
 
+def test_conjugate_draws_with_signal_statistics_match_oracle_streams(ctx, oracle):
+    """update_μσ! with noisy signals (src/Hmc.jl:267-314): Meff = Mi/(1+κ), a = α + ½Ni + ½Mi, b with ½Sm2/(1+κ), posterior mean
+    (S + Sm + νξ)/(Neff + ν) — fp64 draws agree with the oracle's on the same Philox streams."""
+    rng = np.random.default_rng(52)
+    K, B = 3, 150
+    Ni = rng.integers(0, 300, size=(B, K)); Mi = rng.integers(0, 40, size=(B, K))
+    Mi[::7] = 0; Ni[3::11] = 0
+    S = Ni * rng.normal(3, 2, size=(B, K)); Sm = Mi * rng.normal(3, 2, size=(B, K))
+    S2 = Ni * rng.uniform(0.3, 4.0, size=(B, K)); Sm2 = Mi * rng.uniform(0.3, 6.0, size=(B, K))
+    trans = rng.integers(0, 200, size=(B, K, K)) + 1
+    xi, two = np.full(K, 3.3), np.full(K, 2.0)
+    for kappa in (0.0, 0.6, 3.0):
+        s2, mu, rho, A = ctx.draw_params(Ni, S, S2, trans, xi, two, two, two, seed=99, chain0=500, sweep=4, precision=64,
+                                         Mi=Mi, Sm=Sm, Sm2=Sm2, kappa=kappa)
+        for b in range(0, B, 3):
+            o = oracle.draw_params(Ni[b], S[b], S2[b], trans[b], xi, two, two, two, 99, 500 + b, 4, kappa=kappa, Mi=Mi[b], Sm=Sm[b], Sm2=Sm2[b])
+            np.testing.assert_allclose(s2[b], o[0], rtol=1e-9)
+            np.testing.assert_allclose(mu[b], o[1], rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(rho[b], o[2], rtol=1e-9)
+            np.testing.assert_allclose(A[b], o[3], rtol=1e-9)
+
+
 def _run(H, ctx, y, ws, we, **kw):
     spec = H.ProblemSpec(y, ws, we, **kw)
     return H.estimate(ctx, spec)
