@@ -300,12 +300,15 @@ __global__ void __launch_bounds__(kWideThreads) gibbs_wide_kernel(const GibbsArg
                 if (s < kBatch && t >= 0) { prefetch_l1(y0 + (long long)t * yld); prefetch_l1(pi0 + (long long)t * K); }
             }
             if constexpr (kPipe) fetch(i0 + kBatch);
+            if ((i0 & (4 * W - 1)) == 0) w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)((i0 >> 2) + s));   // block of steps i0 + 4s .. + 3
 #pragma unroll
             for (int j = 0; j < kBatch; ++j) {
                 const int i = i0 + j;
                 if (i >= T) break;
-                if ((i & 3) == 0) w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
-                const uint32_t wi = (i & 3) == 0 ? w.x : (i & 3) == 1 ? w.y : (i & 3) == 2 ? w.z : w.w;
+                // uniforms: every lane of the group generated ONE Philox block of the next 4W steps (see above), so a step costs
+                // one shuffle instead of a quarter of a Philox evaluation in every lane
+                const uint32_t wsel = (j & 3) == 0 ? w.x : (j & 3) == 1 ? w.y : (j & 3) == 2 ? w.z : w.w;
+                const uint32_t wi = __shfl_sync(gm, wsel, (i >> 2) & (W - 1), W);
                 const R u = u01<R>(wi);
                 R pt, p;
                 if (i == 0) {
