@@ -53,8 +53,11 @@ template <typename R> __host__ __device__ constexpr size_t wide_group_bytes(int 
     return (sizeof(R) * ((size_t)K * wide_row_stride(K) + 2 * (size_t)W) + sizeof(int) * (size_t)K * K + 15) / 16 * 16;
 }
 
+#ifndef HMC_WIDE_MINBLOCKS32
+#define HMC_WIDE_MINBLOCKS32 5
+#endif
 template <typename R, int W, bool LOGLIK>
-__global__ void __launch_bounds__(kWideThreads) gibbs_wide_kernel(const GibbsArgs a, const int K, const long long* __restrict__ slot_pi_off) {
+__global__ void __launch_bounds__(kWideThreads, sizeof(R) == 8 ? 3 : (W == 32 ? HMC_WIDE_MINBLOCKS32 : 4)) gibbs_wide_kernel(const GibbsArgs a, const int K, const long long* __restrict__ slot_pi_off) {
     using WC = WideChain<R, W>;
     extern __shared__ __align__(16) unsigned char wide_smem[];
     const int lane = threadIdx.x & 31;
