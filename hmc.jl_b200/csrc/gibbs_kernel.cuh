@@ -74,9 +74,9 @@ __device__ __forceinline__ void ld_quad_shared(const double* p, double& a, doubl
 }
 constexpr int kGibbsThreads = 128;
 #ifndef HMC_MINBLOCKS
-#define HMC_MINBLOCKS 5
+#define HMC_MINBLOCKS 4
 #endif
-constexpr int kGibbsMinBlocks = HMC_MINBLOCKS;   // 5 blocks x 128 threads per SM -> register cap 102, 20 resident warps
+constexpr int kGibbsMinBlocks = HMC_MINBLOCKS;   // 4 blocks x 128 threads per SM -> 128 registers, 16 resident warps (5 blocks / 96 registers was the best before the tiled spill layout; measured again after it: 4 is +5 %)
 // K = 5..8 keep K x K matrices per thread: 2 blocks per SM (shared-memory tables and rings allow no more), 255 registers
 #ifndef HMC_MINBLOCKS_F64
 #define HMC_MINBLOCKS_F64 3
