@@ -246,7 +246,7 @@ def main():
     ap.add_argument("--nrun", type=int, default=1000)
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--traffic", type=float, default=2.61e9,
+    ap.add_argument("--traffic", type=float, default=2.51e9,
                     help="dram__bytes_read+write per sweep-kernel launch from the ncu --set full capture "
                          "(profiles/r1_gibbs_sweeps_ncu_full.txt: one task group of 1000 warp tasks x 16 sweeps = 1.79e8 state-steps)")
     args = ap.parse_args()
@@ -385,7 +385,7 @@ def main():
     # instructions per warp-step come from the ncu capture of the same kernel (smsp__inst_executed.sum / warp-steps,
     # profiles/r1_gibbs_sweeps_ncu_full_alltasks.txt); the peak is 4 schedulers x 1 warp-instr/clk x SMs at the SM clock
     # sampled under load during this run.
-    wi = {3: 103.0}.get(getattr(args, "K_run", K)) if args.precision == 32 and args.workload == "c2" and len(ws) * n_chains > 16000 else None   # thread-per-chain kernel only
+    wi = {3: 102.4}.get(getattr(args, "K_run", K)) if args.precision == 32 and args.workload == "c2" and len(ws) * n_chains > 16000 else None   # thread-per-chain kernel only
     issue = None
     if wi is not None and clocks.get("sm_mhz"):
         sms = torch.cuda.get_device_properties(local).multi_processor_count
