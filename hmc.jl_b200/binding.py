@@ -25,7 +25,7 @@ SYMBOLS = [
     "hmcgpu_version", "hmcgpu_device_count", "hmcgpu_ctx_create", "hmcgpu_ctx_destroy", "hmcgpu_last_error",
     "hmcgpu_ctx_sync", "hmcgpu_estimate", "hmcgpu_estimate_multi", "hmcgpu_plan_create", "hmcgpu_plan_run",
     "hmcgpu_plan_fetch", "hmcgpu_plan_destroy", "hmcgpu_filter", "hmcgpu_filter_masked", "hmcgpu_smooth", "hmcgpu_sample_states",
-    "hmcgpu_draw_params", "hmcgpu_draw_params_signals", "hmcgpu_forecast", "hmcgpu_philox",
+    "hmcgpu_draw_params", "hmcgpu_draw_params_signals", "hmcgpu_forecast", "hmcgpu_philox", "hmcgpu_philox_rounds",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -100,6 +100,7 @@ def load(build_if_missing: bool = True):
                                              _i64p, _dp, _dp, _dp, _dp, C.c_uint64, C.c_uint32, C.c_uint32, _dp, _dp, _dp, _dp]
     L.hmcgpu_forecast.argtypes = [C.c_void_p, C.c_int32, C.c_int64, _dp, _dp, _dp, _i32p, C.c_int32, _dp, _dp]
     L.hmcgpu_philox.argtypes = [C.c_void_p, C.c_int64, _u32p, _u32p, _u32p]
+    L.hmcgpu_philox_rounds.argtypes = [C.c_void_p, C.c_int32, C.c_int64, _u32p, _u32p, _u32p]
     _lib = L
     return L
 
@@ -204,11 +205,11 @@ class Context:
         self._check(self.L.hmcgpu_forecast(self.h, K, B, _p(mu), _p(A), _p(pi), _p(h, _i32p), len(h), _p(yreal), _p(out)))
         return out
 
-    def philox(self, ctr, key):
+    def philox(self, ctr, key, rounds=10):
         ctr = np.ascontiguousarray(ctr, dtype=np.uint32)
         key = np.ascontiguousarray(key, dtype=np.uint32)
         out = np.empty_like(ctr)
-        self._check(self.L.hmcgpu_philox(self.h, len(ctr), _p(ctr, _u32p), _p(key, _u32p), _p(out, _u32p)))
+        self._check(self.L.hmcgpu_philox_rounds(self.h, rounds, len(ctr), _p(ctr, _u32p), _p(key, _u32p), _p(out, _u32p)))
         return out
 
 

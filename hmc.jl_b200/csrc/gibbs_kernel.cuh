@@ -568,7 +568,7 @@ struct GibbsWarp {
             return ch.pi0 + (size_t)(jp >> 2) * (4 * K * 32) + (jp & 3);
         };
         R* pap = SMOOTH ? ch.pacc0 + (size_t)(Tw - 1) * K * 32 : nullptr;
-        uint4 w = rng_block(key, sweep, (KIND_STATES << 16), 0u);
+        uint4 w = rng_block_states(key, sweep, 0u);
         if (T > 0) {
             // X[N] ~ Categorical(pif[N,:]); with quirk Q1 the relabelled row is used with chain labels (:512-514)
             R pN[K];
@@ -689,7 +689,7 @@ struct GibbsWarp {
                     y3 = (!ragged || i + 3 < T) ? ld_ro(yp - 4 * ys) : R(0);
                 }
                 const R s0 = load_sw(0), s1 = load_sw(1), s2 = load_sw(2), s3 = load_sw(3);
-                w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
+                w = rng_block_states(key, sweep, (uint32_t)(i >> 2));
                 HMC_BACK(0, w.x, c0, y0, s0) HMC_BACK(1, w.y, c1, y1, s1) HMC_BACK(2, w.z, c2, y2, s2) HMC_BACK(3, w.w, c3, y3, s3)
                 __syncwarp();                                            // all lanes are done with this stage
             }
@@ -700,12 +700,12 @@ struct GibbsWarp {
             if constexpr (Pack::kFlush) { if ((since += 4) > Pack::kMaxT) flush(); }
             R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3, s0, s1, s2, s3;
             load_row(0, c0, y0, s0); load_row(1, c1, y1, s1); load_row(2, c2, y2, s2); load_row(3, c3, y3, s3);
-            w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
+            w = rng_block_states(key, sweep, (uint32_t)(i >> 2));
             HMC_BACK(0, w.x, c0, y0, s0) HMC_BACK(1, w.y, c1, y1, s1) HMC_BACK(2, w.z, c2, y2, s2) HMC_BACK(3, w.w, c3, y3, s3)
         }
 #endif
         if (i < Tw) {
-            w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
+            w = rng_block_states(key, sweep, (uint32_t)(i >> 2));
             R p0[K], p1[K], p2[K], y0 = R(0), y1 = R(0), y2 = R(0), s0 = R(1), s1 = R(1), s2 = R(1);
             load_row(0, p0, y0, s0);
             if (i + 1 < Tw) load_row(1, p1, y1, s1);

@@ -170,8 +170,8 @@ struct GibbsPair {
         }
         const float* yp = ch.y0 + (long long)(Tw - 1) * ys;
         const float2* pip = ch.pi0 + (size_t)(Tw - 1) * K * 32;
-        uint4 w0 = rng_block(key0, sweep, (KIND_STATES << 16), 0u);
-        uint4 w1 = rng_block(key1, sweep, (KIND_STATES << 16), 0u);
+        uint4 w0 = rng_block_states(key0, sweep, 0u);
+        uint4 w1 = rng_block_states(key1, sweep, 0u);
         // one chain's step: draw X_t | X_{t+1}; quirk Q5 only recorded unless GATED (see gibbs_kernel.cuh)
         auto chain_step = [&](Back& b, unsigned tab_off, const float (&pt)[K], float yt, uint32_t word) {
             float p[K];
@@ -277,8 +277,8 @@ struct GibbsPair {
                 const float y1 = (!RAGGED || i + 1 < T) ? ld_ro(yp - 2 * ys) : 0.f;
                 const float y2 = (!RAGGED || i + 2 < T) ? ld_ro(yp - 3 * ys) : 0.f;
                 const float y3 = (!RAGGED || i + 3 < T) ? ld_ro(yp - 4 * ys) : 0.f;
-                w0 = rng_block(key0, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
-                w1 = rng_block(key1, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
+                w0 = rng_block_states(key0, sweep, (uint32_t)(i >> 2));
+                w1 = rng_block_states(key1, sweep, (uint32_t)(i >> 2));
                 HMC_PBACK(0, w0.x, w1.x, c0, y0) HMC_PBACK(1, w0.y, w1.y, c1, y1)
                 HMC_PBACK(2, w0.z, w1.z, c2, y2) HMC_PBACK(3, w0.w, w1.w, c3, y3)
                 __syncwarp();
@@ -286,8 +286,8 @@ struct GibbsPair {
             cp_async_wait<0>();
         }
         if (i < Tw) {
-            w0 = rng_block(key0, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
-            w1 = rng_block(key1, sweep, (KIND_STATES << 16), (uint32_t)(i >> 2));
+            w0 = rng_block_states(key0, sweep, (uint32_t)(i >> 2));
+            w1 = rng_block_states(key1, sweep, (uint32_t)(i >> 2));
             float2 p0[K], p1[K], p2[K];
             float y0 = 0.f, y1 = 0.f, y2 = 0.f;
             load_row(0, p0, y0);

@@ -268,7 +268,7 @@ struct ScanWarp {
             }
             // uniforms of the backward pass: the i-th consumed (i = T-1-t) is word i&3 of Philox block i>>2
             for (int b = lane; 4 * b < T; b += 32) {
-                const uint4 w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)b);
+                const uint4 w = rng_block_states(key, sweep, (uint32_t)b);
                 const int i = 4 * b;
                 us[T - 1 - i] = u01<R>(w.x);
                 if (i + 1 < T) us[T - 2 - i] = u01<R>(w.y);

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kWideThreads, sizeof(R) == 8 ? 3 : (W == 32 ? 
                 if (s < kBatch && t >= 0) { prefetch_l1(y0 + (long long)t * yld); prefetch_l1(pi0 + (long long)t * K); }
             }
             if constexpr (kPipe) fetch(i0 + kBatch);
-            if ((i0 & (4 * W - 1)) == 0) w = rng_block(key, sweep, (KIND_STATES << 16), (uint32_t)((i0 >> 2) + s));   // block of steps i0 + 4s .. + 3
+            if ((i0 & (4 * W - 1)) == 0) w = rng_block_states(key, sweep, (uint32_t)((i0 >> 2) + s));   // block of steps i0 + 4s .. + 3
 #pragma unroll
             for (int j = 0; j < kBatch; ++j) {
                 const int i = i0 + j;

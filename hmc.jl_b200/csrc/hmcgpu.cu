@@ -553,10 +553,11 @@ __global__ void draw_params_kernel_generic(int K, long long B, const long long* 
     for (int i = 0; i < K; ++i) rhoo[b * K + i] = (double)((R)rhoo[b * K + i] / rsum);
 }
 
-__global__ void philox_kernel(long long n, const unsigned* __restrict__ ctr, const unsigned* __restrict__ key, unsigned* __restrict__ out) {
+__global__ void philox_kernel(long long n, int rounds, const unsigned* __restrict__ ctr, const unsigned* __restrict__ key, unsigned* __restrict__ out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint4 r = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1]);
+    const uint4 r = rounds == kStateRounds ? philox4x32<kStateRounds>(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1])
+                                           : philox4x32<10>(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1]);
     out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
 }
 
@@ -756,14 +757,20 @@ extern "C" int hmcgpu_forecast(hmcgpu_ctx* ctx, int32_t K, int64_t B, const doub
     return HMCGPU_OK;
 }
 
+extern "C" int hmcgpu_philox_rounds(hmcgpu_ctx* ctx, int32_t rounds, int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
 extern "C" int hmcgpu_philox(hmcgpu_ctx* ctx, int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    return hmcgpu_philox_rounds(ctx, 10, n, ctr, key, out);
+}
+
+extern "C" int hmcgpu_philox_rounds(hmcgpu_ctx* ctx, int32_t rounds, int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
     if (!ctx || n <= 0 || !ctr || !key || !out) return fail(ctx, HMCGPU_ERR_ARG, "bad arguments");
+    if (rounds != 10 && rounds != kStateRounds) return fail(ctx, HMCGPU_ERR_ARG, "rounds must be 10 (parameter draws) or %d (state uniforms)", kStateRounds);
     CU(ctx, cudaSetDevice(ctx->device));
     tl_pool = ctx->pool;
     Xfer x{ctx};
     unsigned *dc, *dk, *dout;
     TRY(x.up(ctr, (size_t)n * 4, &dc)); TRY(x.up(key, (size_t)n * 2, &dk)); TRY(x.up((unsigned*)nullptr, (size_t)n * 4, &dout));
-    philox_kernel<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, dc, dk, dout);
+    philox_kernel<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, rounds, dc, dk, dout);
     CU(ctx, cudaGetLastError());
     TRY(x.down(out, dout, (size_t)n * 4));
     CU(ctx, cudaStreamSynchronize(ctx->stream));

@@ -2,8 +2,10 @@
 //
 // Replaces the reference's global MersenneTwister + Distributions.jl samplers (src/Hmc.jl:320 InverseGamma,
 // :334 Normal, :355/:367 Dirichlet, :464/:481 Categorical).  Every random number is a pure function of
-// (seed, chain id, sweep, purpose, index): Philox4x32-10 with key = seed and counter = {block, purpose, sweep, chain},
-// so results do not depend on scheduling or on how chains are sharded over GPUs.
+// (seed, chain id, sweep, purpose, index): Philox4x32 with key = seed and counter = {block, purpose, sweep, chain},
+// so results do not depend on scheduling or on how chains are sharded over GPUs.  The parameter draws use the 10-round
+// generator; the STATES stream (one uniform per time step of every sweep: a third of the backward pass's instructions)
+// uses Philox4x32-7, the fewest rounds Random123 reports as passing BigCrush ("crush-resistant").
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -17,9 +19,10 @@ struct RngKey {
     uint32_t chain;    // global chain id = window_id * n_chains + chain
 };
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int round = 0; round < 10; ++round) {
+    for (int round = 0; round < ROUNDS; ++round) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
@@ -29,8 +32,17 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    return philox4x32<10>(c0, c1, c2, c3, k0, k1);
+}
+constexpr int kStateRounds = 7;
+// parameter draws (KIND_MU / SIGMA / RHO / A)
 __device__ __forceinline__ uint4 rng_block(const RngKey& k, uint32_t sweep, uint32_t purpose, uint32_t block) {
-    return philox4x32_10(block, purpose, sweep, k.chain, k.k0, k.k1);
+    return philox4x32<10>(block, purpose, sweep, k.chain, k.k0, k.k1);
+}
+// backward-sampler uniforms (KIND_STATES): block b holds the uniforms consumed 4b .. 4b+3
+__device__ __forceinline__ uint4 rng_block_states(const RngKey& k, uint32_t sweep, uint32_t block) {
+    return philox4x32<kStateRounds>(block, (KIND_STATES << 16), sweep, k.chain, k.k0, k.k1);
 }
 
 // uniform in (0,1): fp64 = (w + 0.5) * 2^-32 exactly

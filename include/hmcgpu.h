@@ -197,6 +197,8 @@ int hmcgpu_forecast(hmcgpu_ctx* ctx, int32_t K, int64_t B, const double* mu, con
                     const int32_t* horizons, int32_t n_h, const double* yreal, double* out);
 /* Raw Philox4x32-10 blocks (known-answer tests): ctr [n][4], key [n][2] -> out [n][4]. */
 int hmcgpu_philox(hmcgpu_ctx* ctx, int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
+/* Same with the round count of the stream: 10 = parameter draws, 7 = the backward sampler's state uniforms. */
+int hmcgpu_philox_rounds(hmcgpu_ctx* ctx, int32_t rounds, int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
 
 #ifdef __cplusplus
 }

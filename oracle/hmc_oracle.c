@@ -17,9 +17,9 @@ static const double TWO_PI = 6.283185307179586;
 static const double EPS64 = 2.220446049250313e-16;   /* Julia eps() */
 
 /* ---------------------------------------------------------------- RNG spec */
-void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+void orc_philox4x32(int rounds, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
-    for (int round = 0; round < 10; ++round) {
+    for (int round = 0; round < rounds; ++round) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -32,10 +32,13 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { orc_philox4x32(10, ctr, key, out); }
+
+/* parameter draws: 10 rounds; the STATES stream (one uniform per time step and sweep): Philox4x32-7 */
 static void orc_block(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t purpose, uint32_t block, uint32_t w[4]) {
     uint32_t ctr[4] = {block, purpose, sweep, chain};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    orc_philox4x32_10(ctr, key, w);
+    orc_philox4x32((purpose >> 16) == ORC_KIND_STATES ? ORC_STATE_ROUNDS : 10, ctr, key, w);
 }
 
 double orc_u01(uint32_t w) { return ((double)w + 0.5) * 2.3283064365386963e-10; /* 2^-32 */ }

@@ -41,6 +41,8 @@ extern "C" {
 #define ORC_KIND_A      4u
 
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void orc_philox4x32(int rounds, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+#define ORC_STATE_ROUNDS 7   /* rounds of the STATES stream (backward-sampler uniforms) */
 double orc_u01(uint32_t w);
 /* one standard normal pair from a block's words 0..3 (Box-Muller: words 0,1 -> cos branch z0; sin branch z1) */
 void orc_normal_pair(const uint32_t w[4], double* z0, double* z1);

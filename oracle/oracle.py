@@ -74,11 +74,11 @@ def _f64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
 
-def philox(ctr, key):
+def philox(ctr, key, rounds=10):
     c = (C.c_uint32 * 4)(*[int(x) & 0xFFFFFFFF for x in ctr])
     k = (C.c_uint32 * 2)(*[int(x) & 0xFFFFFFFF for x in key])
     o = (C.c_uint32 * 4)()
-    lib().orc_philox4x32_10(c, k, o)
+    lib().orc_philox4x32(C.c_int(rounds), c, k, o)
     return [int(x) for x in o]
 
 

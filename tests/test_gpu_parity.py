@@ -43,6 +43,12 @@ def test_philox_known_answers_on_device(ctx, oracle):
     out = ctx.philox(ctr, key)
     for i in range(0, 1000, 37):
         assert out[i].tolist() == oracle.philox(ctr[i], key[i])
+    # the 7-round generator of the STATES stream (Random123 kat_vectors, philox4x32-7)
+    out7 = ctx.philox(ctr[:3], key[:3], rounds=7)
+    for i in range(3):
+        assert out7[i].tolist() == oracle.philox(ctr[i], key[i], rounds=7)
+    kat = ctx.philox(np.array([[0, 0, 0, 0], [0xffffffff] * 4], dtype=np.uint32), np.array([[0, 0], [0xffffffff] * 2], dtype=np.uint32), rounds=7)
+    assert kat.tolist() == [[0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48], [0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662]]
 
 
 @pytest.mark.parametrize("K", [2, 3, 4, 5, 8, 32])

@@ -17,6 +17,11 @@ def test_philox_known_answers(oracle):
     assert oracle.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert oracle.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    # Random123 kat_vectors for philox4x32-7: the round count of the STATES stream (backward-sampler uniforms)
+    assert oracle.philox([0, 0, 0, 0], [0, 0], rounds=7) == [0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]
+    assert oracle.philox([0xffffffff] * 4, [0xffffffff] * 2, rounds=7) == [0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662]
+    assert oracle.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], rounds=7) == \
+        [0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a]
 
 
 def numpy_filter(y, A, mu, sigma2, rho):
