@@ -385,7 +385,7 @@ def main():
     # instructions per warp-step come from the ncu capture of the same kernel (smsp__inst_executed.sum / warp-steps,
     # profiles/r1_gibbs_sweeps_ncu_full_alltasks.txt); the peak is 4 schedulers x 1 warp-instr/clk x SMs at the SM clock
     # sampled under load during this run.
-    wi = {3: 102.4}.get(getattr(args, "K_run", K)) if args.precision == 32 and args.workload == "c2" and len(ws) * n_chains > 16000 else None   # thread-per-chain kernel only
+    wi = {3: 99.4}.get(getattr(args, "K_run", K)) if args.precision == 32 and args.workload == "c2" and len(ws) * n_chains > 16000 else None   # thread-per-chain kernel only
     issue = None
     if wi is not None and clocks.get("sm_mhz"):
         sms = torch.cuda.get_device_properties(local).multi_processor_count
