@@ -35,6 +35,11 @@ constexpr int kRing = HMC_RING_STAGES;
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
+// same with the 32-bit shared-window address computed once by the caller (the generic -> shared conversion reads a special
+// register and is not hoisted out of loops by the compiler)
+__device__ __forceinline__ void cp_async16_s(unsigned saddr, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // The passes are out-of-line functions, where pointers arriving through their by-value arguments would be generic
@@ -649,12 +654,13 @@ struct GibbsWarp {
             const int n_groups = (Tw - i) / 4;                          // full groups (i == 4 here when there are any)
             // group g (0-based) holds rows [jlo, jlo+3], jlo = Tw - 8 - 4g  (the rows of steps i = 4+4g .. 7+4g, highest first)
             const R* gsrc = ch.pi0 - lane * 4 + (long long)(Tw + pad - 8) * K * 32;   // tile of group 0, lane 0
+            const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)lane * 16u;
             auto issue = [&](int g) {
                 if (g < n_groups) {
-                    const char* src = reinterpret_cast<const char*>(gsrc - (long long)g * kGroupElems);
-                    char* dst = reinterpret_cast<char*>(ring + (g % kRing) * kGroupElems);
+                    const char* src = reinterpret_cast<const char*>(gsrc - (long long)g * kGroupElems) + lane * 16;
+                    const unsigned dst = ring_s + (unsigned)((g % kRing) * kGroupElems * (int)sizeof(R));
 #pragma unroll
-                    for (int m = 0; m < kChunksPerLane; ++m) cp_async16(dst + (lane + 32 * m) * 16, src + (lane + 32 * m) * 16);
+                    for (int m = 0; m < kChunksPerLane; ++m) cp_async16_s(dst + 512u * m, src + 512 * m);
                 }
                 cp_async_commit();                                       // (possibly empty) keeps the group count uniform
             };
