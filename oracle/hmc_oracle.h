@@ -18,7 +18,7 @@
  * exactly as the reference stores them.  A[r*K+s] = P(X_t=s | X_{t-1}=r); sigma2 holds variances.
  * pif[t*K+s], Pf[(t*K+r)*K+s].
  *
- * Random numbers: a counter-based Philox4x32-10 stream specification shared with the CUDA
+ * Random numbers: a counter-based Philox4x32 stream specification (10 rounds; 7 for the STATES stream) shared with the CUDA
  * product (documented in DESIGN.md §RNG).  The oracle has its own independent implementation.
  */
 #ifndef HMC_ORACLE_H
