@@ -99,6 +99,9 @@ function estimate(ctx::Context, rawdata::VecOrMat{Float64}, win_start::Vector{In
     return (μ = mu, σ = sig, A = A, πbend = pie, forecasts = fc, status = status, events = rc, gpu_ms = res.gpu_ms)
 end
 
+# 0/1 flags over rawdata: 1 = the index belongs to opt.signalRange (hmcgpu_problem.is_signal)
+signalmask(opt) = (m = zeros(UInt8, length(opt.rawdata)); m[collect(opt.signalRange)] .= 0x01; m)
+
 """
     estimatemodel(opt; ctx = Context(0), n_chains = 1, precision = 64)
 
@@ -106,8 +109,6 @@ GPU drop-in for `Hmc.estimatemodel(opt)` (src/Hmc.jl:850-865).  `opt` is an `Hmc
 Nrun×1×D array holding the end-of-window row: `saveresults` reads `samples.πb[:, end, :]` (src/Hmc.jl:744), which works
 unchanged; the Nrun×N×D tensor of the reference (3.5 GB per end date in production) is never materialised.
 """
-signalmask(opt) = (m = zeros(UInt8, length(opt.rawdata)); m[collect(opt.signalRange)] .= 0x01; m)
-
 function estimatemodel(opt; ctx::Context = Context(0), n_chains::Int = 1, precision::Int = 64)
     sr = opt.sampleRange
     # a non-empty signalRange still goes through the signal branches with hp = HyperParams(Y, D), i.e. κ = 1.0 (src/Hmc.jl:853)

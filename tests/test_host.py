@@ -19,13 +19,71 @@ def test_library_exports_every_declared_symbol(H):
     assert L.hmcgpu_version() >= 100
 
 
-def test_struct_layout_matches_header(H):
-    # field order/size of the ctypes mirrors = the C structs (8-byte pointers, natural alignment)
+def _header_struct_fields(name):
+    """(type, field) pairs of `typedef struct <name> {...}` in include/hmcgpu.h, in declaration order."""
+    header = open(os.path.join(ROOT, "include", "hmcgpu.h")).read()
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        m = re.match(r"(const )?(\w+)\s*(\*?)\s*(.+)$", decl)
+        ctype = m.group(2) + m.group(3)
+        for f in m.group(4).split(","):
+            out.append((ctype, f.strip()))
+    return out
+
+
+def _c_offsets(tmp_path, name, fields):
+    """offsetof of every field and sizeof the struct as gcc lays out include/hmcgpu.h."""
+    import subprocess
+    src = tmp_path / f"layout_{name}.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hmcgpu.h"', "int main(void) {"]
+    lines += [f'  printf("{f} %zu\\n", offsetof({name}, {f}));' for _, f in fields]
+    lines += [f'  printf("sizeof %zu\\n", sizeof({name}));', "  return 0; }"]
+    src.write_text("\n".join(lines))
+    exe = tmp_path / f"layout_{name}"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    return {k: int(v) for k, v in (ln.split() for ln in subprocess.check_output([str(exe)], text=True).splitlines())}
+
+
+_C2CTYPES = {"double*": "LP_c_double", "int32_t*": "LP_c_int", "int64_t*": "LP_c_long", "uint8_t*": "LP_c_ubyte",
+             "double": "c_double", "int32_t": "c_int", "uint32_t": "c_uint", "int64_t": "c_long", "uint64_t": "c_ulong"}
+_C2JULIA = {"double*": "Ptr{Float64}", "int32_t*": "Ptr{Int32}", "int64_t*": "Ptr{Int64}", "uint8_t*": "Ptr{UInt8}",
+            "double": "Float64", "int32_t": "Int32", "uint32_t": "UInt32", "int64_t": "Int64", "uint64_t": "UInt64"}
+
+
+@pytest.mark.parametrize("cname,pyname", [("hmcgpu_problem", "Problem"), ("hmcgpu_result", "Result")])
+def test_struct_layout_matches_header(H, tmp_path, cname, pyname):
+    """Both bindings mirror include/hmcgpu.h field by field: the ctypes Structure is compared with gcc's offsetof/sizeof
+    of the header itself, the Julia struct (never executed here) by field name, order and type."""
     from hmc_jl_b200 import binding as B
-    assert ctypes.sizeof(B.Problem) == 192
-    assert ctypes.sizeof(B.Result) == 11 * 8 + 2 * 8 + 5 * 8
-    assert B.Problem.flags.offset == 172 and B.Problem.K.offset == 56
-    assert B.Problem.win_init_series.offset == 176 and B.Problem.pi_row_back.offset == 184 and B.Problem.is_signal_per_series.offset == 188
+    fields = _header_struct_fields(cname)
+    off = _c_offsets(tmp_path, cname, fields)
+    S = getattr(B, pyname)
+    assert [f for f, _ in S._fields_] == [f for _, f in fields]
+    assert ctypes.sizeof(S) == off["sizeof"]
+    for (ctype, f), (_, pytype) in zip(fields, S._fields_):
+        assert getattr(S, f).offset == off[f], f
+        assert pytype.__name__ == _C2CTYPES[ctype], (f, pytype.__name__, ctype)
+    jl = open(os.path.join(ROOT, "hmc.jl_b200", "julia", "HmcGPU.jl")).read()
+    body = re.search(r"struct %s\n(.*?)\nend" % pyname, jl, re.S).group(1)
+    jfields = [tuple(x.strip().split("::")) for ln in body.splitlines() for x in ln.split(";") if x.strip()]
+    assert jfields == [(f, _C2JULIA[ctype]) for ctype, f in fields]
+
+
+def test_flag_and_error_constants_match_header(H):
+    from hmc_jl_b200 import binding as B
+    header = open(os.path.join(ROOT, "include", "hmcgpu.h")).read()
+    jl = open(os.path.join(ROOT, "hmc.jl_b200", "julia", "HmcGPU.jl")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define HMCGPU_((?:FLAG|ERR)_\w+) \(?(-?\d+)u?\)?", header)}
+    assert len(defs) == 10
+    for k, v in defs.items():
+        assert getattr(B, k) == v, k
+        if k.startswith("FLAG_"):
+            assert re.search(r"const %s = UInt32\(%d\)" % (k, v), jl), k
 
 
 def test_no_device_fails_loudly(H):
