@@ -11,9 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -50,6 +52,16 @@ static int fail(hmcgpu_ctx* ctx, int code, const char* fmt, ...) {
             return fail(ctx, e__ == cudaErrorMemoryAllocation ? HMCGPU_ERR_ALLOC : HMCGPU_ERR_CUDA,     \
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);   \
     } while (0)
+
+// No C++ exception may cross the C ABI (include/hmcgpu.h): host-side allocation failures become HMCGPU_ERR_ALLOC.
+#define GUARD(ctx, expr)                                                                                \
+    try {                                                                                               \
+        return (expr);                                                                                  \
+    } catch (const std::bad_alloc&) {                                                                   \
+        return fail(ctx, HMCGPU_ERR_ALLOC, "%s: host allocation failed", __func__);                     \
+    } catch (const std::exception& e__) {                                                               \
+        return fail(ctx, HMCGPU_ERR_ALLOC, "%s: %s", __func__, e__.what());                             \
+    }
 
 // Device memory is recycled per context: repeated estimations of the same shape (the rolling-window driver calls
 // hmcgpu_estimate once per batch) reuse their multi-GB buffers instead of paying cudaMalloc/cudaFree every call.
@@ -1093,6 +1105,9 @@ static int validate_problem(hmcgpu_ctx* ctx, const hmcgpu_problem* p) {
     if (!k_thread(p->K) && (p->flags & HMCGPU_FLAG_SMOOTHED_MEAN))
         return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "smoothed means are only implemented for K <= 4");
     if (p->n_chains < 1) return fail(ctx, HMCGPU_ERR_ARG, "n_chains < 1");
+    // chain slots are indexed with 32-bit ints (padded to a multiple of 64); the Philox chain id is 32 bits as well
+    if ((long long)p->n_windows * p->n_chains > 0x7fffffffLL - 64)
+        return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "n_windows * n_chains = %lld exceeds 2^31 - 65 chains per call", (long long)p->n_windows * p->n_chains);
     if (p->burnin < 0 || p->nrun < 1) return fail(ctx, HMCGPU_ERR_ARG, "burnin < 0 or nrun < 1");
     if (p->burnin + p->nrun > 0xffffffffLL) return fail(ctx, HMCGPU_ERR_ARG, "more than 2^32 sweeps");
     if (p->precision != 32 && p->precision != 64) return fail(ctx, HMCGPU_ERR_ARG, "precision must be 32 or 64");
@@ -1445,8 +1460,6 @@ static int plan_run_t(hmcgpu_plan* pl) {
                 CU(ctx, cudaGetLastError());
                 ++pl->n_launches;
             }
-            CU(ctx, cudaGetLastError());
-            ++pl->n_launches;
         }
         CU(ctx, new_event(&post_done[k]));
         CU(ctx, cudaEventRecord(post_done[k], st));
@@ -1526,22 +1539,25 @@ static int plan_run_t(hmcgpu_plan* pl) {
     return HMCGPU_OK;
 }
 
-extern "C" int hmcgpu_plan_create(hmcgpu_ctx* ctx, const hmcgpu_problem* p, hmcgpu_plan** out) {
-    if (!out) return fail(ctx, HMCGPU_ERR_ARG, "out is NULL");
-    *out = nullptr;
+static int plan_create_impl(hmcgpu_ctx* ctx, const hmcgpu_problem* p, hmcgpu_plan** out) {
     TRY(validate_problem(ctx, p));
     CU(ctx, cudaSetDevice(ctx->device));
     tl_pool = ctx->pool;
-    hmcgpu_plan* pl = new hmcgpu_plan();
+    std::unique_ptr<hmcgpu_plan> pl(new hmcgpu_plan());
     pl->ctx = ctx;
-    int rc = (p->precision == 32) ? plan_build<float>(pl, p) : plan_build<double>(pl, p);
-    if (rc != 0) { delete pl; return rc; }
-    *out = pl;
+    int rc = (p->precision == 32) ? plan_build<float>(pl.get(), p) : plan_build<double>(pl.get(), p);
+    if (rc != 0) return rc;
+    *out = pl.release();
     return HMCGPU_OK;
 }
 
-extern "C" int hmcgpu_plan_run(hmcgpu_plan* pl) {
-    if (!pl) return HMCGPU_ERR_ARG;
+extern "C" int hmcgpu_plan_create(hmcgpu_ctx* ctx, const hmcgpu_problem* p, hmcgpu_plan** out) {
+    if (!out) return fail(ctx, HMCGPU_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    GUARD(ctx, plan_create_impl(ctx, p, out));
+}
+
+static int plan_run_impl(hmcgpu_plan* pl) {
     hmcgpu_ctx* ctx = pl->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     int rc = HMCGPU_ERR_UNSUPPORTED;
@@ -1549,8 +1565,18 @@ extern "C" int hmcgpu_plan_run(hmcgpu_plan* pl) {
     return rc;
 }
 
+extern "C" int hmcgpu_plan_run(hmcgpu_plan* pl) {
+    if (!pl) return HMCGPU_ERR_ARG;
+    GUARD(pl->ctx, plan_run_impl(pl));
+}
+
+static int plan_fetch_impl(hmcgpu_plan* pl, hmcgpu_result* r);
 extern "C" int hmcgpu_plan_fetch(hmcgpu_plan* pl, hmcgpu_result* r) {
     if (!pl || !r) return HMCGPU_ERR_ARG;
+    GUARD(pl->ctx, plan_fetch_impl(pl, r));
+}
+
+static int plan_fetch_impl(hmcgpu_plan* pl, hmcgpu_result* r) {
     hmcgpu_ctx* ctx = pl->ctx;
     if (!pl->ran) return fail(ctx, HMCGPU_ERR_ARG, "plan_fetch before plan_run");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1638,8 +1664,13 @@ extern "C" int hmcgpu_estimate(hmcgpu_ctx* ctx, const hmcgpu_problem* p, hmcgpu_
 }
 
 // Windows sharded over devices by longest-processing-time-first on T_w; one host thread per device, no collectives.
+static int estimate_multi_impl(const int* devices, int n_dev, const hmcgpu_problem* p, hmcgpu_result* r);
 extern "C" int hmcgpu_estimate_multi(const int* devices, int n_dev, const hmcgpu_problem* p, hmcgpu_result* r) {
     if (!devices || n_dev < 1 || !p || !r) return fail(nullptr, HMCGPU_ERR_ARG, "bad arguments");
+    GUARD(nullptr, estimate_multi_impl(devices, n_dev, p, r));
+}
+
+static int estimate_multi_impl(const int* devices, int n_dev, const hmcgpu_problem* p, hmcgpu_result* r) {
     if (p->n_windows < 1 || !p->win_start || !p->win_end) return fail(nullptr, HMCGPU_ERR_ARG, "no windows");
     const int nw = p->n_windows, K = p->K, nh = p->n_h;
     std::vector<int> ord(nw);
@@ -1664,11 +1695,12 @@ extern "C" int hmcgpu_estimate_multi(const int* devices, int n_dev, const hmcgpu
     std::vector<std::thread> th;
     for (int d = 0; d < n_dev; ++d) {
         th.emplace_back([&, d]() {
+          hmcgpu_ctx* ctx = nullptr;
+          try {
             const std::vector<int>& ws = shard[d];
             const int n = (int)ws.size();
             memset(&parts[d], 0, sizeof(hmcgpu_result));
             if (n == 0) return;
-            hmcgpu_ctx* ctx = nullptr;
             int rc = hmcgpu_ctx_create(devices[d], &ctx);
             if (rc != 0) { rcs[d] = rc; errs[d] = hmcgpu_last_error(nullptr); return; }
             std::vector<int32_t> ser(n), iser(n), st(n), en(n);
@@ -1722,6 +1754,10 @@ extern "C" int hmcgpu_estimate_multi(const int* devices, int n_dev, const hmcgpu
                 }
             }
             hmcgpu_ctx_destroy(ctx);
+          } catch (const std::exception& e) {     // an exception escaping a std::thread would terminate the host process
+            rcs[d] = HMCGPU_ERR_ALLOC; errs[d] = std::string("host allocation failed: ") + e.what();
+            if (ctx) hmcgpu_ctx_destroy(ctx);
+          }
         });
     }
     for (auto& t : th) t.join();

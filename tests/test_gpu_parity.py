@@ -461,6 +461,9 @@ def test_error_paths(H, ctx):
     assert e.value.code == -4
     with pytest.raises(H.HmcGpuError):
         _run(H, ctx, y, [10], [10], K=3)
+    with pytest.raises(H.HmcGpuError) as e:          # 32-bit chain slots: refused before anything is allocated
+        H.Plan(ctx, H.ProblemSpec(y, [1] * 40000, [40] * 40000, K=3, n_chains=60000))
+    assert e.value.code == -4
     with pytest.raises(H.HmcGpuError):
         H.Context(99)
 
