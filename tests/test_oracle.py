@@ -55,6 +55,68 @@ def test_forward_matches_numpy(oracle, K):
     assert abs(np.log(f.totals).sum() - f.loglik) < 1e-9
 
 
+@pytest.mark.parametrize("kappa", [0.0, 0.6, 3.0])
+def test_forward_signal_rows_match_numpy(oracle, kappa):
+    """Signal rows are emitted with sd*(1+kappa) (src/Hmc.jl:382, :396, :424), observation rows with sd."""
+    rng = np.random.default_rng(21)
+    K = 3
+    A, mu, s2, rho = (v[0] for v in random_params(rng, 1, K))
+    y = rng.normal(0, 3, size=120)
+    mask = np.zeros(len(y), dtype=np.uint8)
+    mask[[0, 5, 6, 50]] = 1
+    mask[-12:] = 1                                           # the reference's layout: signals after the end date (+ row 1)
+    f = oracle.forward(y, A, mu, s2, rho, is_signal=mask, kappa=kappa)
+    sd = np.sqrt(s2)[None, :] * np.where(mask[:, None] != 0, 1.0 + kappa, 1.0)
+    logp = norm.logpdf(y[:, None], mu[None, :], sd)
+    prev, ll, pif = np.log(rho), 0.0, np.zeros((len(y), K))
+    for t in range(len(y)):
+        joint = prev[:, None] + np.log(A) + logp[t][None, :]
+        tot = logsumexp(joint)
+        ll += tot
+        prev = logsumexp(joint, axis=0) - tot
+        pif[t] = np.exp(prev)
+    np.testing.assert_allclose(f.pif, pif, rtol=1e-9, atol=1e-300)
+    assert abs(f.loglik - ll) < 1e-8 * abs(ll)
+    if kappa == 0.0:                                         # kappa = 0: a signal is an observation
+        np.testing.assert_array_equal(f.pif, oracle.forward(y, A, mu, s2, rho).pif)
+
+
+def test_shortest_window_and_single_step_filter(oracle):
+    """Edge sizes: T = 1 for the deterministic pieces, T = 2 for a whole chain (the shortest window the library accepts)."""
+    rng = np.random.default_rng(2)
+    A, mu, s2, rho = (v[0] for v in random_params(rng, 1, 3))
+    f = oracle.forward(np.array([0.7]), A, mu, s2, rho)
+    joint = rho[:, None] * A * norm.pdf(0.7, mu, np.sqrt(s2))[None, :]
+    np.testing.assert_allclose(f.Pf[0], joint / joint.sum(), rtol=1e-12)
+    np.testing.assert_allclose(f.totals[0], joint.sum(), rtol=1e-12)
+    X = oracle.sample_states(f.pif, A, np.array([0.999999]), form=1)
+    assert X.tolist() == [3]
+    o = oracle.gibbs(np.array([1.0, 4.0]), 2, 5, 20, seed=3, horizons=(0, 1), y_future=[4.0, np.nan])
+    assert o.mu.shape == (20, 2) and np.isfinite(o.mu).all() and np.isfinite(o.sigma2).all() and (o.sigma2 > 0).all()
+    np.testing.assert_allclose(o.A.sum(2), 1.0, atol=1e-12)
+    np.testing.assert_allclose(o.pi_end.sum(1), 1.0, atol=1e-12)
+    np.testing.assert_allclose(o.forecasts[:, 0], (o.pi_end * o.mu).sum(1), rtol=1e-12)      # horizon 0 = pi_end' mu
+    assert np.isnan(o.forecasts[:, 3]).all()                                                   # no realised value: NaN error
+
+
+def test_categorical_convention_and_zero_normaliser_fallback(oracle):
+    """rand(Categorical(p)) = first i with cumsum_i >= u; rows whose normaliser is <= eps() fall back to 1/D (:472-480)."""
+    K = 3
+    A = np.array([[0.0, 0.5, 0.5], [0.0, 0.5, 0.5], [0.0, 0.5, 0.5]])      # no path INTO state 1
+    pif = np.array([[0.2, 0.3, 0.5], [1.0, 0.0, 0.0]])                     # ... but X[2] = 1 is forced by piN
+    for u0, want in ((0.0, 1), (0.3, 1), (0.34, 2), (0.66, 2), (0.67, 3), (0.999, 3)):
+        X = oracle.sample_states(pif, A, np.array([u0, 0.5]), form=1)
+        assert X.tolist() == [want, 1], (u0, X)
+    # regular rows: boundaries of the cumulative sums of pif[0] * A[:, x] normalised
+    A2 = np.array([[0.5, 0.25, 0.25], [0.1, 0.8, 0.1], [0.3, 0.3, 0.4]])
+    pif2 = np.array([[0.2, 0.3, 0.5], [0.0, 1.0, 0.0]])
+    w = pif2[0] * A2[:, 1]
+    c = np.cumsum(w / w.sum())
+    for u0 in (0.0, c[0] - 1e-9, c[0] + 1e-9, c[1] - 1e-9, c[1] + 1e-9, 0.999999):
+        X = oracle.sample_states(pif2, A2, np.array([u0, 0.5]), form=1)
+        assert X[1] == 2 and X[0] == 1 + int(np.searchsorted(c, u0, side="left")), (u0, X)
+
+
 def test_backward_forms_agree_and_match_numpy(oracle):
     rng = np.random.default_rng(3)
     K = 3
