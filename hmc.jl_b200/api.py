@@ -56,6 +56,46 @@ class EstOpt:
         if not set(self.signalSave) <= set(self.signalRange):
             raise ValueError("signalSave is not a subset of signalRange")
 
+    # ---- accessors of the reference (src/Hmc.jl:75-107), same names and 1-based index meaning
+    @property
+    def obsRange(self):
+        """setdiff(sampleRange, signalRange) (:63, :76), in sampleRange order."""
+        sig = set(self.signalRange)
+        return [i for i in self.sampleRange if i not in sig]
+
+    def update_itators(self):
+        """`update_itators!` (:75-83).  The reference caches six index vectors that must be rebuilt by hand after the
+        ranges are edited (`code/run_hmm.jl` does so per end date); here every range-derived quantity (obsRange, the signal
+        mask) is computed on access, so this only re-validates the ranges."""
+        self.__post_init__()
+        return self
+
+    def makey(self):
+        """rawdata[sampleRange] (:85-87)."""
+        return np.asarray(self.rawdata, dtype=np.float64)[self.sampleRange[0] - 1:self.sampleRange[-1]]
+
+    def makeysignals(self):
+        """rawdata[signalRange] (:89-91)."""
+        return np.asarray(self.rawdata, dtype=np.float64)[[i - 1 for i in self.signalRange]]
+
+    def enddate(self, extra: int = 0):
+        """dates[endIndex + extra] (:93-95)."""
+        return self.dates[self.endIndex + extra - 1]
+
+    def startdate(self):
+        """dates[first(sampleRange)] (:97-99)."""
+        return self.dates[self.sampleRange[0] - 1]
+
+    def yobs(self, index: int):
+        """rawdata[index], 1-based (:101-103)."""
+        if index < 1:
+            raise IndexError(index)                   # Julia's BoundsError; a negative numpy index would wrap silently
+        return float(self.rawdata[index - 1])
+
+    def yend(self, extra: int = 0):
+        """rawdata[endIndex + extra] (:105-107)."""
+        return self.yobs(self.endIndex + extra)
+
     def signal_mask(self):
         """uint8 flag per index of rawdata: 1 on opt.signalRange (obsRange = setdiff(sampleRange, signalRange), :63)."""
         m = np.zeros(len(self.rawdata), dtype=np.uint8)

@@ -130,6 +130,23 @@ def test_estopt_mirror_defaults_and_validation(H):
         H.EstOpt(y, None, sampleRange=range(1, 124), signalRange=range(122, 124), signalSave=range(120, 123))
     with pytest.raises(ValueError):
         H.EstOpt(y, None, sampleRange=range(1, 300))
+    # accessors (src/Hmc.jl:75-107): 1-based like the reference
+    dates = [f"d{i}" for i in range(1, 201)]
+    o = H.EstOpt(y, dates, sampleRange=range(3, 124), signalRange=range(122, 124), endIndex=121)
+    assert o.obsRange == list(range(3, 122))
+    np.testing.assert_array_equal(o.makey(), y[2:123])
+    np.testing.assert_array_equal(o.makeysignals(), y[121:123])
+    assert (o.enddate(), o.enddate(12), o.startdate()) == ("d121", "d133", "d3")
+    assert (o.yobs(1), o.yend(), o.yend(12)) == (0.0, 120.0, 132.0)
+    with pytest.raises(IndexError):
+        o.yobs(201)
+    with pytest.raises(IndexError):
+        o.yobs(0)
+    o.signalRange = range(130, 132)                                                      # edited by hand, then re-derived
+    with pytest.raises(ValueError):
+        o.update_itators()
+    o.signalRange = range(123, 124)
+    assert o.update_itators().obsRange == list(range(3, 123))
 
 
 def test_problem_spec_layouts(H):
