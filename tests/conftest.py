@@ -64,3 +64,28 @@ def ctx(H):
     c = H.Context(0)
     yield c
     c.close()
+
+
+# ---- the reference's noisy-signal goldens (tests/golden/signals_allsignal_subset.json, made by tests/golden/make_golden.py)
+
+def signals_golden_case(end_index, noise):
+    """(y, dates, case, sigma_signal) of one end date x noise level of data/output/signals_official_noise_<noise>_allsignal.
+    sigma_signal = the realised spread of the reference's perturbed values at its two saved dates."""
+    import json
+    y, dates = load_inflation()
+    g = json.load(open(os.path.join(GOLDEN, "signals_allsignal_subset.json")))
+    case = next(c for c in g["cases"] if c["end_index"] == end_index and c["noise"] == noise)
+    assert dates[end_index - 1] == case["date"]
+    return y, dates, case, float(np.sqrt(np.mean(np.square(case["signal_std"]))))
+
+
+def dispersion_close(per_copy, gold, name, nse=5.0, atol=0.01):
+    """per_copy: (copies, n) per-copy posterior means; gold: {"mean": [...], "std": [...]} over the reference's 100 copies."""
+    gm, gs = np.array(gold["mean"]), np.array(gold["std"])
+    m, sd = per_copy.mean(0), per_copy.std(0, ddof=1)
+    se = np.sqrt(sd ** 2 / len(per_copy) + gs ** 2 / 100)
+    assert np.all(np.abs(m - gm) <= nse * se + atol), (name, m, gm, se)
+    # spread across copies: same scale.  The std of a std over 100 copies is ~7 %; ours also carries the Monte-Carlo error of
+    # each copy's posterior mean (a few thousand draws here, 250 000 in the reference), which only widens it
+    big = gs > 0.02
+    assert np.all((sd[big] > 0.55 * gs[big]) & (sd[big] < 2.5 * gs[big])), (name, sd, gs)

@@ -49,3 +49,33 @@ for idx in range(120, 580):
             full[n].append([round(v, 6) for v in tabs[n][1][d]])
 json.dump(full, open(f"{HERE}/official_summary_all.json", "w"), separators=(",", ":"))
 print(len(full["end_index"]), "end dates in the full table")
+
+# ---- noisy-signal Monte Carlo goldens (estimatesignals!, src/Hmc.jl:868-914): data/output/signals_official_noise_<κ>_allsignal/
+# produced by the "make everything a signal" block of code/run_hmm.jl (:160-176): sampleRange = signalRange = start:end,
+# signalSave = end-1:end, noise = κ, 100 perturbed copies x (100 000 + 250 000) sweeps, then aggregate.jl's dispersion
+# tables = mean and std over the 100 copies of each copy's posterior means.  signal_<j>_std is the sample std of the
+# perturbed values at the two saved dates, i.e. an estimate of the σsignal the run used (mean(σ²-draws)·κ of a base run
+# whose σ² posterior is heavy-tailed, so it cannot be recomputed to better than ±20 %: tests inject it instead).
+sig_names = ["filtered_means", "filtered_variances", "filtered_state_probs", "filtered_trans_probs", "forecasts"]
+sig = {"source": "data/output/signals_official_noise_<noise>_allsignal/<name>_dispersion.csv", "K": 3, "noise_samples": 100,
+       "signalburnin": 100000, "signalNrun": 250000,
+       "note": "trans_a_b column holds A[b,a]; <col>_mean / <col>_std = mean / std over the 100 perturbed copies of the per-copy posterior mean",
+       "cases": []}
+for noise in ("0.1", "0.3", "0.6"):
+    tabs = {}
+    for n in sig_names:
+        r = list(csv.reader(open(f"{REF}/data/output/signals_official_noise_{noise}_allsignal/{n}_dispersion.csv")))
+        tabs[n] = (r[0], {x[0]: x for x in r[1:]})
+    for idx in (121, 200, 300, 450, 570):
+        d = dates[idx - 1]
+        case = {"noise": float(noise), "end_index": idx, "date": d}
+        for n in sig_names:
+            head, rows_ = tabs[n]
+            row = dict(zip(head, rows_[d]))
+            cols = [c[:-5] for c in head if c.endswith("_mean") and not c.startswith("signal")]
+            case[n] = {"columns": cols, "mean": [float(row[c + "_mean"]) for c in cols], "std": [float(row[c + "_std"]) for c in cols]}
+        row = dict(zip(*[tabs["filtered_means"][0], tabs["filtered_means"][1][d]]))
+        case["signal_std"] = [float(row["signal_1_std"]), float(row["signal_2_std"])]
+        sig["cases"].append(case)
+json.dump(sig, open(f"{HERE}/signals_allsignal_subset.json", "w"), indent=1)
+print(len(sig["cases"]), "signal cases")

@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, K3_TRUTH, load_inflation, random_params, synth_hmm
+from conftest import dispersion_close, signals_golden_case, GOLDEN, K3_TRUTH, load_inflation, random_params, synth_hmm
 
 pytestmark = pytest.mark.gpu
 
@@ -823,6 +823,30 @@ def test_estimatesignals_mirror(H, ctx, tmp_path):
     assert head == ["date", "signalid", "state_1", "state_2", "state_3"] + [f"signal_{i}" for i in range(1, 13)]
     row = open(paths["forecasts"]).readlines()[1].strip().split(",")
     assert row[1] == "1" and len(row) == 2 + 4 + 12
+
+
+@pytest.mark.parametrize("end_index,noise", [(121, 0.3), (300, 0.1), (570, 0.6)])
+def test_estimatesignals_matches_reference_golden_dispersion(H, ctx, end_index, noise):
+    """The whole noisy-signal Monte Carlo through the host mirror (EstOpt -> estimatesignals -> calcdispersion) against
+    the reference's OWN outputs, data/output/signals_official_noise_<noise>_allsignal/*_dispersion.csv (the "make
+    everything a signal" block of code/run_hmm.jl:160-176: 100 perturbed copies per end date).  Same tolerances as the
+    oracle's check of the same goldens (tests/test_oracle.py::test_golden_signal_dispersion); fp32 kernels."""
+    y, dates, case, ssig = signals_golden_case(end_index, noise)
+    rng_all = range(1, end_index + 1)
+    opt = H.EstOpt(y, dates, sampleRange=rng_all, signalRange=rng_all, signalSave=range(end_index - 1, end_index + 1),
+                   endIndex=end_index, horizons=[12], D=3, signalburnin=1500, signalNrun=500, noise=noise, noiseSamples=100,
+                   σsignal=ssig, n_chains=8, precision=32)
+    s = H.estimatesignals(opt, ctx, rng=np.random.default_rng(1234))
+    assert s.events == 0 and s.μ.shape == (100 * 8 * 500, 3)
+    assert abs(s.signalvals[::4000].std(0, ddof=1).mean() / ssig - 1) < 0.25          # the copies carry the injected noise level
+    _, per_copy = H.signal_summaries(s)
+    dispersion_close(per_copy["filtered_means"], case["filtered_means"], "mu", atol=0.02)
+    dispersion_close(per_copy["filtered_variances"], case["filtered_variances"], "sigma2", atol=0.15 * ssig ** 2 / (1 + noise))
+    dispersion_close(per_copy["filtered_state_probs"], case["filtered_state_probs"], "pi_end")
+    dispersion_close(per_copy["filtered_trans_probs"], case["filtered_trans_probs"], "A")
+    dispersion_close(per_copy["forecasts"], case["forecasts"], "forecasts", atol=0.02)
+    disp = H.calcdispersion(s)                                                          # the table aggregate.jl writes
+    np.testing.assert_allclose(disp["filtered_means"][0], per_copy["filtered_means"].mean(0))
 
 
 def test_differential_fuzz_of_the_two_sweep_kernels():

@@ -8,7 +8,7 @@ import pytest
 from scipy.special import logsumexp
 from scipy.stats import norm
 
-from conftest import GOLDEN, K3_TRUTH, load_inflation, random_params, synth_hmm
+from conftest import GOLDEN, K3_TRUTH, dispersion_close, load_inflation, random_params, signals_golden_case, synth_hmm
 
 
 def test_philox_known_answers(oracle):
@@ -262,3 +262,29 @@ def test_golden_posterior_summaries(oracle, which):
     np.testing.assert_allclose(pe, g["filtered_state_probs"], atol=0.01)
     if np.isfinite(fc[1]):
         np.testing.assert_allclose(fc, g["forecasts"], atol=0.06)
+
+
+@pytest.mark.parametrize("end_index,noise", [(121, 0.3), (300, 0.1), (570, 0.6)])
+def test_golden_signal_dispersion(oracle, end_index, noise):
+    """The signal tier (mask, sd*(1+kappa) emissions, kappa-weighted statistics incl. quirk Q3, HyperParams(opt) priors,
+    estimatesignals! :868-914) against the reference's OWN outputs: data/output/signals_official_noise_<kappa>_allsignal
+    (every observation a signal, 100 perturbed copies per end date).  sigma_signal is taken from the golden's realised
+    signal spread (the reference derives it from a heavy-tailed mean of sigma^2 draws that no finite run pins down)."""
+    y, dates, case, ssig = signals_golden_case(end_index, noise)
+    Y = y[:end_index]
+    mask, two, xi = np.ones(end_index, dtype=np.uint8), np.full(3, 2.0), np.full(3, Y.mean())
+    X0, _, _ = oracle.make_params(Y, 3)                         # :888: initial states from the real data
+    rng = np.random.default_rng(1234)
+    S = 100
+    outs, _ = oracle.gibbs_batch([dict(y=Y + rng.standard_normal(end_index) * ssig, K=3, burnin=1500, nrun=2500, seed=1234,
+                                       chain=100 + s, horizons=(12,), y_future=[y[end_index - 1 + 12]], is_signal=mask, kappa=noise,
+                                       alpha=two, nu=two, xi=xi, X0=X0) for s in range(S)])
+    assert sum(o.n_events for o in outs) == 0
+    pm = lambda k: np.array([getattr(o, k).mean(0) for o in outs])
+    dispersion_close(pm("mu"), case["filtered_means"], "mu", atol=0.02)
+    # the injected sigma_signal is itself an estimate from 2 x 100 values (+-5 %, so +-10 % on sigma_signal^2, which enters the
+    # variance draws as Sm2 / (1 + kappa), :315): allow 1.5 sigma of that on top of the sampling error
+    dispersion_close(pm("sigma2"), case["filtered_variances"], "sigma2", atol=0.15 * ssig ** 2 / (1 + noise))
+    dispersion_close(pm("pi_end"), case["filtered_state_probs"], "pi_end")
+    dispersion_close(np.transpose(pm("A"), (0, 2, 1)).reshape(S, 9), case["filtered_trans_probs"], "A")     # trans_a_b = A[b,a]
+    dispersion_close(pm("forecasts"), case["forecasts"], "forecasts", atol=0.02)
