@@ -825,7 +825,8 @@ def test_estimatesignals_mirror(H, ctx, tmp_path):
     assert row[1] == "1" and len(row) == 2 + 4 + 12
 
 
-@pytest.mark.parametrize("end_index,noise", [(121, 0.3), (300, 0.1), (570, 0.6)])
+@pytest.mark.parametrize("noise", [0.1, 0.3, 0.6])
+@pytest.mark.parametrize("end_index", [121, 200, 300, 450, 570])
 def test_estimatesignals_matches_reference_golden_dispersion(H, ctx, end_index, noise):
     """The whole noisy-signal Monte Carlo through the host mirror (EstOpt -> estimatesignals -> calcdispersion) against
     the reference's OWN outputs, data/output/signals_official_noise_<noise>_allsignal/*_dispersion.csv (the "make
@@ -841,7 +842,7 @@ def test_estimatesignals_matches_reference_golden_dispersion(H, ctx, end_index, 
     assert abs(s.signalvals[::4000].std(0, ddof=1).mean() / ssig - 1) < 0.25          # the copies carry the injected noise level
     _, per_copy = H.signal_summaries(s)
     dispersion_close(per_copy["filtered_means"], case["filtered_means"], "mu", atol=0.02)
-    dispersion_close(per_copy["filtered_variances"], case["filtered_variances"], "sigma2", atol=0.15 * ssig ** 2 / (1 + noise))
+    dispersion_close(per_copy["filtered_variances"], case["filtered_variances"], "sigma2", atol=0.25 * ssig ** 2 / (1 + noise))
     dispersion_close(per_copy["filtered_state_probs"], case["filtered_state_probs"], "pi_end")
     dispersion_close(per_copy["filtered_trans_probs"], case["filtered_trans_probs"], "A")
     dispersion_close(per_copy["forecasts"], case["forecasts"], "forecasts", atol=0.02)

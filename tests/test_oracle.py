@@ -264,7 +264,7 @@ def test_golden_posterior_summaries(oracle, which):
         np.testing.assert_allclose(fc, g["forecasts"], atol=0.06)
 
 
-@pytest.mark.parametrize("end_index,noise", [(121, 0.3), (300, 0.1), (570, 0.6)])
+@pytest.mark.parametrize("end_index,noise", [(121, 0.3), (200, 0.6), (300, 0.1), (450, 0.3), (570, 0.6)])
 def test_golden_signal_dispersion(oracle, end_index, noise):
     """The signal tier (mask, sd*(1+kappa) emissions, kappa-weighted statistics incl. quirk Q3, HyperParams(opt) priors,
     estimatesignals! :868-914) against the reference's OWN outputs: data/output/signals_official_noise_<kappa>_allsignal
@@ -283,8 +283,8 @@ def test_golden_signal_dispersion(oracle, end_index, noise):
     pm = lambda k: np.array([getattr(o, k).mean(0) for o in outs])
     dispersion_close(pm("mu"), case["filtered_means"], "mu", atol=0.02)
     # the injected sigma_signal is itself an estimate from 2 x 100 values (+-5 %, so +-10 % on sigma_signal^2, which enters the
-    # variance draws as Sm2 / (1 + kappa), :315): allow 1.5 sigma of that on top of the sampling error
-    dispersion_close(pm("sigma2"), case["filtered_variances"], "sigma2", atol=0.15 * ssig ** 2 / (1 + noise))
+    # variance draws as Sm2 / (1 + kappa), :315): allow 2.5 sigma of that on top of the sampling error
+    dispersion_close(pm("sigma2"), case["filtered_variances"], "sigma2", atol=0.25 * ssig ** 2 / (1 + noise))
     dispersion_close(pm("pi_end"), case["filtered_state_probs"], "pi_end")
     dispersion_close(np.transpose(pm("A"), (0, 2, 1)).reshape(S, 9), case["filtered_trans_probs"], "A")     # trans_a_b = A[b,a]
     dispersion_close(pm("forecasts"), case["forecasts"], "forecasts", atol=0.02)
