@@ -79,3 +79,25 @@ for noise in ("0.1", "0.3", "0.6"):
         sig["cases"].append(case)
 json.dump(sig, open(f"{HERE}/signals_allsignal_subset.json", "w"), indent=1)
 print(len(sig["cases"]), "signal cases")
+
+# the complete allsignal tables (every end date of the three noise levels), compact: used by scripts/signals_run_report.py
+sig_all = {"source": sig["source"], "note": sig["note"], "noise": {}}
+for noise in ("0.1", "0.3", "0.6"):
+    tabs = {}
+    for n in sig_names:
+        r = list(csv.reader(open(f"{REF}/data/output/signals_official_noise_{noise}_allsignal/{n}_dispersion.csv")))
+        tabs[n] = (r[0], r[1:])
+    date_idx = {d: i + 1 for i, d in enumerate(dates)}
+    block = {"end_index": [date_idx[x[0]] for x in tabs["filtered_means"][1]], "signal_std": []}
+    for n in sig_names:
+        head, body = tabs[n]
+        assert [date_idx[x[0]] for x in body] == block["end_index"]
+        cols = [c[:-5] for c in head if c.endswith("_mean") and not c.startswith("signal")]
+        block[n] = {"columns": cols,
+                    "mean": [[float(f"{float(x[head.index(c + '_mean')]):.6g}") for c in cols] for x in body],
+                    "std": [[float(f"{float(x[head.index(c + '_std')]):.4g}") for c in cols] for x in body]}
+    head, body = tabs["filtered_means"]
+    block["signal_std"] = [[float(f"{float(x[head.index('signal_1_std')]):.5g}"), float(f"{float(x[head.index('signal_2_std')]):.5g}")] for x in body]
+    sig_all["noise"][noise] = block
+json.dump(sig_all, open(f"{HERE}/signals_allsignal_all.json", "w"), separators=(",", ":"))
+print({k: len(v["end_index"]) for k, v in sig_all["noise"].items()}, "end dates in the full signal tables")
