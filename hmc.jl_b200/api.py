@@ -400,6 +400,65 @@ def calcdispersion(samples):
     return {k: (v.mean(0), v.std(0, ddof=1) if len(v) > 1 else np.full(v.shape[1], np.nan)) for k, v in per_signal.items()}
 
 
+def _signal_tables(samples, horizons: Sequence[int]):
+    """name -> (column names without suffix, [S, columns]) per perturbed copy, incl. the saved signal values (constant within a
+    copy, so their mean is the value itself), in the column order of the reference's signal CSVs (:707-721, :733-741)."""
+    ids, per_signal = signal_summaries(samples)
+    D = samples.μ.shape[1]
+    vals = np.stack([samples.signalvals[samples.signalids == i].mean(0) for i in ids])
+    sig_cols = [f"signal_{j}" for j in range(1, vals.shape[1] + 1)]
+    state = [f"state_{i}" for i in range(1, D + 1)]
+    heads = {"filtered_means": state, "filtered_variances": state, "filtered_state_probs": state,
+             "filtered_trans_probs": [f"trans_{i}_{j}" for j in range(1, D + 1) for i in range(1, D + 1)],
+             "forecasts": sum([[f"forecast_{h}", f"forecast_error_{h}"] for h in horizons], [])}
+    return ids, {k: (heads[k] + sig_cols, np.concatenate([per_signal[k], vals], axis=1)) for k in heads}
+
+
+def write_signal_summaries(samples_by_date, horizons: Sequence[int], directory: str):
+    """`<var>_summary.csv` of a signals directory: Hmc.runaggregate with groups [:date, :signalid] (src/Hmc.jl:1053-1076),
+    one row per (end date, perturbed copy) = that copy's posterior means, columns `<col>_mean`.
+    samples_by_date: iterable of estimatesignals results (one per end date)."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    paths, files = {}, {}
+    for smp in samples_by_date:
+        ids, tabs = _signal_tables(smp, horizons)
+        for name, (hdr, data) in tabs.items():
+            if name not in files:
+                paths[name] = os.path.join(directory, f"{name}_summary.csv")
+                files[name] = open(paths[name], "w")
+                files[name].write(",".join(["date", "signalid"] + [h + "_mean" for h in hdr]) + "\n")
+            for i, row in zip(ids, data):
+                files[name].write(",".join([str(smp.obsdates[0]), str(int(i))] + [repr(float(v)) for v in row]) + "\n")
+    for f in files.values():
+        f.close()
+    return paths
+
+
+def write_dispersion(samples_by_date, horizons: Sequence[int], directory: str):
+    """`<var>_dispersion.csv`: Hmc.calcdispersion (src/Hmc.jl:1078-1090) = per end date the mean and the standard deviation
+    (n−1) over the perturbed copies of every column of `<var>_summary.csv` (signalid included, as DataFrames.aggregate does):
+    `date, signalid_mean, <col>_mean…, signal_j_mean…, signalid_std, <col>_std…, signal_j_std…` — the layout of
+    data/output/signals_official_noise_*_allsignal/*_dispersion.csv."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    paths, files = {}, {}
+    for smp in samples_by_date:
+        ids, tabs = _signal_tables(smp, horizons)
+        for name, (hdr, data) in tabs.items():
+            full = np.concatenate([ids[:, None].astype(np.float64), data], axis=1)
+            cols = ["signalid"] + hdr
+            if name not in files:
+                paths[name] = os.path.join(directory, f"{name}_dispersion.csv")
+                files[name] = open(paths[name], "w")
+                files[name].write(",".join(["date"] + [c + "_mean" for c in cols] + [c + "_std" for c in cols]) + "\n")
+            sd = full.std(0, ddof=1) if len(full) > 1 else np.full(full.shape[1], np.nan)
+            files[name].write(",".join([str(smp.obsdates[0])] + [repr(float(v)) for v in full.mean(0)] + [repr(float(v)) for v in sd]) + "\n")
+    for f in files.values():
+        f.close()
+    return paths
+
+
 def calccorr(samples, D: int):
     """Mirror of the per-date block of Hmc.calccorr (src/Hmc.jl:1092-1129): correlation matrix across draws of
     [μ_1..D, σ_1..D, π_1..D, trans_i_j (column-major), first forecast].  Returns (names, matrix)."""

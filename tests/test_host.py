@@ -236,6 +236,46 @@ def test_dispersion_and_correlation_analytics(H):
     np.testing.assert_allclose(C[10, 0], np.corrcoef(s.A[:, 1, 0], mu[:, 0])[0, 1])     # trans_2_1 = A[2,1]
 
 
+def test_signal_summary_and_dispersion_csv_layout(H, tmp_path):
+    """write_signal_summaries / write_dispersion produce the files of a signals directory (runaggregate with groups
+    [:date, :signalid] + calcdispersion, src/Hmc.jl:1053-1090); headers as in data/output/signals_official_noise_*_allsignal."""
+    from types import SimpleNamespace
+    rng = np.random.default_rng(1)
+    S, R, D = 4, 30, 3
+
+    def fake(date, shift):
+        n = S * R
+        ids = np.repeat(np.arange(1, S + 1), R)
+        return SimpleNamespace(μ=np.sort(rng.normal(size=(n, D)), axis=1) + shift + ids[:, None], σ=rng.uniform(0.5, 2, size=(n, D)),
+                               πb=rng.dirichlet(np.ones(D), size=n), A=rng.dirichlet(np.ones(D), size=(n, D)),
+                               forecasts=rng.normal(size=(n, 2)), signalids=ids, obsdates=np.array([date] * n, dtype=object),
+                               signalvals=np.repeat(rng.normal(size=(S, 2)), R, axis=0))
+    runs = [fake("1980-01-01", 0.0), fake("1980-02-01", 5.0)]
+    sp = H.write_signal_summaries(runs, [12], str(tmp_path))
+    dp = H.write_dispersion(runs, [12], str(tmp_path))
+    # the reference's own headers (signals_official_noise_0.3_allsignal/forecasts_summary.csv, filtered_means_dispersion.csv)
+    assert open(sp["forecasts"]).readline().strip() == "date,signalid,forecast_12_mean,forecast_error_12_mean,signal_1_mean,signal_2_mean"
+    assert open(dp["filtered_means"]).readline().strip() == (
+        "date,signalid_mean,state_1_mean,state_2_mean,state_3_mean,signal_1_mean,signal_2_mean,"
+        "signalid_std,state_1_std,state_2_std,state_3_std,signal_1_std,signal_2_std")
+    assert open(dp["forecasts"]).readline().strip() == (
+        "date,signalid_mean,forecast_12_mean,forecast_error_12_mean,signal_1_mean,signal_2_mean,"
+        "signalid_std,forecast_12_std,forecast_error_12_std,signal_1_std,signal_2_std")
+    hdr = open(dp["filtered_trans_probs"]).readline().strip().split(",")
+    assert len(hdr) == 1 + 2 * (1 + 9 + 2) and sorted(hdr[2:11]) == sorted(f"trans_{i}_{j}_mean" for i in (1, 2, 3) for j in (1, 2, 3))
+    rows = [ln.split(",") for ln in open(sp["filtered_means"]).read().splitlines()[1:]]
+    assert len(rows) == 2 * S and rows[S][0] == "1980-02-01" and rows[S][1] == "1"
+    _, per = H.signal_summaries(runs[1])
+    np.testing.assert_allclose([float(v) for v in rows[S][2:5]], per["filtered_means"][0])
+    np.testing.assert_allclose(float(rows[S][5]), runs[1].signalvals[0, 0])
+    d = [ln.split(",") for ln in open(dp["filtered_means"]).read().splitlines()[1:]]
+    assert len(d) == 2 and d[1][0] == "1980-02-01" and float(d[1][1]) == 2.5                        # mean of signalid 1..4
+    disp = H.calcdispersion(runs[1])
+    np.testing.assert_allclose([float(v) for v in d[1][2:5]], disp["filtered_means"][0])
+    np.testing.assert_allclose([float(v) for v in d[1][8:11]], disp["filtered_means"][1])
+    np.testing.assert_allclose(float(d[1][7]), np.std([1, 2, 3, 4], ddof=1))
+
+
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU port on the host cores; no GPU involved): exactly one JSON line on stdout with
     the contract's keys, whatever the libraries print."""
