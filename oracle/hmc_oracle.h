@@ -11,8 +11,11 @@
  * numpy/scipy log-space check (tests/test_oracle.py).  Random draws are "parity unpinned" at the
  * bit level (Julia's MersenneTwister + Distributions.jl 0.21.8 samplers are not vendored and Julia
  * is absent); the full sampler is pinned distributionally against the reference's own golden
- * posterior summaries (data/output/official/<var>_summary.csv, copied to tests/golden/) and against
- * the reference's only test (test/runtests.jl:56-57).
+ * posterior summaries (data/output/official/<var>_summary.csv, copied to tests/golden/), the signal
+ * tier (mask, kappa-weighted statistics, quirk Q3, HyperParams(opt) priors) against the reference's
+ * noisy-signal outputs (data/output/signals_official_noise_<kappa>_allsignal/<var>_dispersion.csv,
+ * tests/golden/signals_allsignal_subset.json), and against the reference's only test
+ * (test/runtests.jl:56-57).
  *
  * Array conventions: row-major C arrays, 0-based in storage, states reported 1-based in X
  * exactly as the reference stores them.  A[r*K+s] = P(X_t=s | X_{t-1}=r); sigma2 holds variances.
