@@ -101,3 +101,15 @@ for noise in ("0.1", "0.3", "0.6"):
     sig_all["noise"][noise] = block
 json.dump(sig_all, open(f"{HERE}/signals_allsignal_all.json", "w"), separators=(",", ":"))
 print({k: len(v["end_index"]) for k, v in sig_all["noise"].items()}, "end dates in the full signal tables")
+
+# ---- the published in-sample table (code/run_insamplefcasts.jl -> data/output/official_insample/forecats_insample.csv):
+# one full-sample estimation (idx 1..576, burnin 20 000, Nrun 10 000), per date the 12-month forecast from that date's state
+# probabilities and the probabilities themselves.  Its s1..s3 are FILTERED probabilities.
+ins = list(csv.DictReader(open(f"{REF}/data/output/official_insample/forecats_insample.csv")))
+assert [r["date"] for r in ins] == dates[:len(ins)]
+r6 = lambda v: float(f"{float(v):.6g}")
+json.dump({"source": "data/output/official_insample/forecats_insample.csv", "first_index": 1, "last_index": len(ins), "horizon": 12,
+           "burnin": 20000, "nrun": 10000, "forecast": [r6(r["forecast"]) for r in ins],
+           "probs": [[r6(r["s1"]), r6(r["s2"]), r6(r["s3"])] for r in ins]},
+          open(f"{HERE}/official_insample.json", "w"), separators=(",", ":"))
+print(len(ins), "in-sample rows")

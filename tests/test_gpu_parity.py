@@ -625,6 +625,27 @@ def test_insample_forecast_means(H, ctx, oracle):
     np.testing.assert_allclose(a.insample_forecast_mean[0][-1], a.summary_mean[0][18:22:2], rtol=1e-4)
 
 
+def test_insample_filtered_table_matches_reference_publication(H, ctx):
+    """forecastinsample(probabilities="filtered") on the GPU (one estimation with draws + batched hmcgpu_filter over the thinned
+    draws) against the reference's published in-sample table, data/output/official_insample/forecats_insample.csv: its
+    s1..s3 are posterior means of the filtered probabilities (tests/test_oracle.py::test_golden_insample_table_is_filtered)."""
+    y, dates = load_inflation()
+    g = json.load(open(os.path.join(GOLDEN, "official_insample.json")))
+    N = g["last_index"]
+    opt = H.EstOpt(y, dates, sampleRange=range(1, N + 1), endIndex=N, horizons=[12], D=3, burnin=2000, Nrun=1500, n_chains=8,
+                   precision=32)
+    t = H.forecastinsample(opt, ctx=ctx, probabilities="filtered", max_draws=2000)
+    p = np.stack([t["s1"], t["s2"], t["s3"]], axis=1)
+    np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-5)
+    d = np.abs(p - np.array(g["probs"])).max(1)
+    assert np.median(d) < 2e-3 and (d < 0.03).mean() > 0.85 and d.max() < 0.25, (np.median(d), (d < 0.03).mean(), d.max())
+    df = np.abs(t["forecast"] - np.array(g["forecast"]))
+    assert np.median(df) < 0.03 and np.quantile(df, 0.99) < 0.5, (np.median(df), np.quantile(df, 0.99))
+    ts = H.forecastinsample(opt, ctx=ctx, probabilities="smoothed")              # the smoothed table is a different object
+    ds = np.abs(np.stack([ts["s1"], ts["s2"], ts["s3"]], axis=1) - np.array(g["probs"])).max(1)
+    assert ds.mean() > 2 * d.mean() and ds[-1] < 5e-3
+
+
 def test_complete_official_run_against_reference_summaries(H, ctx):
     """All 460 end dates of the reference's published run (data/output/official/*_summary.csv, real series) in one call.
     Typical agreement is ~1e-3; a few end dates have a bimodal posterior (e.g. idx 479: mu_3 near 8.25 or 10.45 — the

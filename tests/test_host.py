@@ -276,6 +276,50 @@ def test_signal_summary_and_dispersion_csv_layout(H, tmp_path):
     np.testing.assert_allclose(float(d[1][7]), np.std([1, 2, 3, 4], ddof=1))
 
 
+def test_forecastinsample_filtered_host_logic(H, oracle, monkeypatch):
+    """Host side of forecastinsample(probabilities="filtered") — draw thinning, layouts, A^h mu weights, chunked filter calls,
+    table columns — with the two C-ABI calls it makes replaced by oracle-backed stand-ins (no GPU here); the result is
+    checked against the reference's published in-sample table.  The GPU run of the same function is a -m gpu test."""
+    import json
+    from types import SimpleNamespace
+    from conftest import load_inflation
+    from hmc_jl_b200 import binding as B
+    y, dates = load_inflation()
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "official_insample.json")))
+    N = g["last_index"]
+
+    def fake_estimate(ctx, spec):
+        assert spec.flags & B.FLAG_DRAWS and list(spec.horizons) == [12] and spec.win_end[0] == N
+        outs, _ = oracle.gibbs_batch([dict(y=spec.y[0, :N], K=spec.K, burnin=spec.burnin, nrun=spec.nrun, seed=spec.seed, chain=c,
+                                           horizons=(12,), y_future=[spec.y[0, N - 1 + 12]]) for c in range(spec.n_chains)])
+        cat = lambda k: np.concatenate([getattr(o, k) for o in outs])
+        return SimpleNamespace(mu=[cat("mu").T], sigma2=[cat("sigma2").T], A=[np.transpose(cat("A"), (2, 1, 0))], events=0)
+
+    calls = []
+
+    class FakeCtx:
+        def filter(self, yw, A, mu, s2, rho, precision=64, want_totals=True):
+            calls.append(len(mu))
+            return SimpleNamespace(pif=np.stack([oracle.forward(yw, A[b], mu[b], s2[b], rho[b], want_Pf=False).pif for b in range(len(mu))]))
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(B, "estimate", fake_estimate)
+    opt = H.EstOpt(y, dates, sampleRange=range(1, N + 1), endIndex=N, horizons=[12], D=3, burnin=1500, Nrun=1500, n_chains=2)
+    t = H.forecastinsample(opt, ctx=FakeCtx(), probabilities="filtered", max_draws=300)
+    assert calls == [256, 44] and t["date"][0] == dates[0] and len(t["forecast"]) == N
+    p = np.stack([t["s1"], t["s2"], t["s3"]], axis=1)
+    np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-9)
+    d = np.abs(p - np.array(g["probs"])).max(1)
+    assert np.median(d) < 5e-3 and (d < 0.05).mean() > 0.85
+    assert np.median(np.abs(t["forecast"] - np.array(g["forecast"]))) < 0.05
+    np.testing.assert_allclose(t["forecasterror"][:N - 12], t["forecast"][:N - 12] - y[12:N], atol=1e-12)
+    np.testing.assert_array_equal(t["current"], y[:N])
+    with pytest.raises(ValueError):
+        H.forecastinsample(opt, ctx=FakeCtx(), probabilities="both")
+
+
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU port on the host cores; no GPU involved): exactly one JSON line on stdout with
     the contract's keys, whatever the libraries print."""

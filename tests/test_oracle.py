@@ -288,3 +288,33 @@ def test_golden_signal_dispersion(oracle, end_index, noise):
     dispersion_close(pm("pi_end"), case["filtered_state_probs"], "pi_end")
     dispersion_close(np.transpose(pm("A"), (0, 2, 1)).reshape(S, 9), case["filtered_trans_probs"], "A")     # trans_a_b = A[b,a]
     dispersion_close(pm("forecasts"), case["forecasts"], "forecasts", atol=0.02)
+
+
+def test_golden_insample_table_is_filtered(oracle):
+    """The reference's published in-sample table (data/output/official_insample/forecats_insample.csv, 576 dates, one
+    full-sample estimation) against the oracle: its state probabilities are the posterior mean of the FILTERED
+    probabilities pif (median deviation < 2e-3) and not of the smoothed pib, which is far sharper in mid-sample; its
+    12-month forecasts are pif[t,:]' A^12 mu.  This pins the forward filter (:371-440) to reference output on every date."""
+    y, dates = load_inflation()
+    g = json.load(open(os.path.join(GOLDEN, "official_insample.json")))
+    N = g["last_index"]
+    gp, gf = np.array(g["probs"]), np.array(g["forecast"])
+    outs, _ = oracle.gibbs_batch([dict(y=y[:N], K=3, burnin=3000, nrun=3000, seed=1234, chain=c, horizons=(12,),
+                                       y_future=[y[N - 1 + 12]], want_pib_mean=True) for c in range(8)])
+    rng = np.random.default_rng(0)
+    pf, fc, n = np.zeros((N, 3)), np.zeros(N), 0
+    for o in outs:
+        for j in range(0, 3000, 12):
+            A, mu = o.A[j], o.mu[j]
+            f = oracle.forward(y[:N], A, mu, o.sigma2[j], rng.dirichlet(np.ones(3)), want_Pf=False)     # rho ~ flat prior (:350-356)
+            pf += f.pif
+            fc += f.pif @ np.linalg.matrix_power(A, 12) @ mu
+            n += 1
+    pf /= n
+    fc /= n
+    pb = np.mean([o.pib_mean for o in outs], axis=0)
+    d_f, d_b = np.abs(pf - gp).max(1), np.abs(pb - gp).max(1)
+    assert np.median(d_f) < 2e-3 and (d_f < 0.03).mean() > 0.85 and d_f.max() < 0.25
+    assert (d_b < 0.03).mean() < 0.8 and d_b.max() > 0.5 and d_b.mean() > 2 * d_f.mean()     # the smoothed rows are NOT what was published
+    assert d_f[-1] < 5e-3 and d_b[-1] < 5e-3                                                  # last date: filtered = smoothed
+    assert np.median(np.abs(fc - gf)) < 0.03 and np.quantile(np.abs(fc - gf), 0.99) < 0.5
