@@ -8,7 +8,9 @@
  *
  * Parity status: deterministic pieces (filter, smoother, forecast) have NO known-answer vectors
  * in the reference — they are pinned by this restatement plus an independent
- * numpy/scipy log-space check (tests/test_oracle.py).  Random draws are "parity unpinned" at the
+ * numpy/scipy log-space check (tests/test_oracle.py), and the filter + forecast also by the
+ * reference's published in-sample table (data/output/official_insample/forecats_insample.csv =
+ * posterior means of the filtered probabilities on 576 dates, tests/golden/official_insample.json).  Random draws are "parity unpinned" at the
  * bit level (Julia's MersenneTwister + Distributions.jl 0.21.8 samplers are not vendored and Julia
  * is absent); the full sampler is pinned distributionally against the reference's own golden
  * posterior summaries (data/output/official/<var>_summary.csv, copied to tests/golden/), the signal
