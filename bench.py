@@ -94,6 +94,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def issue_roofline(warp_inst_per_warp_step, state_steps, sweep_seconds, sms, sm_mhz):
+    """Warp-instruction issue roofline of the sweep kernel: nominal peak = SMs x 4 schedulers x the SM clock sampled under
+    load; next to it the MEASURED rate of a pure-arithmetic kernel with the sweep's instruction blend
+    (scripts/issue_peak.cu -> profiles/r1_issue_peak.json: FFMA / MUFU.EX2 / IMAD.WIDE / integer folds), scaled to that clock."""
+    ach = warp_inst_per_warp_step * (state_steps / 32.0) / sweep_seconds
+    pk = sms * 4 * sm_mhz * 1e6
+    out = {"bound": "issue", "achieved": ach / 1e9, "peak": pk / 1e9, "unit": "Gwarp-inst/s", "frac": ach / pk,
+           "warp_inst_per_warp_step": warp_inst_per_warp_step, "mufu_per_state_step": 4, "peak_source": "SMs x 4 x sampled SM clock"}
+    try:
+        m = json.load(open(os.path.join(ROOT, "profiles", "r1_issue_peak.json")))
+        mixed = float(m["mix_gwarp_inst_s"]) * 1e9 * (sm_mhz * 1e6 * 4 * int(m["sms"])) / (float(m["nominal_issue_gwarp_inst_s_at_max_clock"]) * 1e9)
+        out["measured_mixed_peak"] = mixed / 1e9
+        out["frac_of_measured_mixed_peak"] = ach / mixed
+    except Exception:
+        pass
+    return out
+
+
 # Rank 0 prints ONE JSON line on stdout.  Libraries (NCCL's version banner, ...) write to file descriptor 1 directly, so
 # the descriptor is pointed at stderr for the whole run and the line goes to a private duplicate of the real stdout.
 _REAL_STDOUT = None
@@ -389,10 +407,7 @@ def main():
     issue = None
     if wi is not None and clocks.get("sm_mhz"):
         sms = torch.cuda.get_device_properties(local).multi_processor_count
-        ach = wi * (float(steps_per_run) * args.steps / 32.0) / (sweep_ms / 1e3)
-        pk = sms * 4 * clocks["sm_mhz"] * 1e6
-        issue = {"bound": "issue", "achieved": ach / 1e9, "peak": pk / 1e9, "unit": "Gwarp-inst/s", "frac": ach / pk,
-                 "warp_inst_per_warp_step": wi, "mufu_per_state_step": 4, "peak_source": "SMs x 4 x sampled SM clock"}
+        issue = issue_roofline(wi, float(steps_per_run) * args.steps, sweep_ms / 1e3, sms, clocks["sm_mhz"])
     # ---- the reference's own shape of the same job (BASELINE configs[1] read literally): ONE chain per end date.  Such a
     # narrow batch runs on the time-parallel warp-per-chain kernel; reported next to the headline, not instead of it.
     literal = None

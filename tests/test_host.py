@@ -320,6 +320,21 @@ def test_forecastinsample_filtered_host_logic(H, oracle, monkeypatch):
         H.forecastinsample(opt, ctx=FakeCtx(), probabilities="both")
 
 
+def test_bench_issue_roofline_arithmetic():
+    """bench.issue_roofline on the numbers of the committed bench line: nominal fraction as recorded, and the measured
+    mixed-blend peak (profiles/r1_issue_peak.json) scaled to the sampled clock."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    r = b.issue_roofline(100.0, 3.2e11, 1.0, 148, 1500.0)
+    assert abs(r["achieved"] - 1000.0) < 1e-9 and abs(r["peak"] - 888.0) < 1e-9 and abs(r["frac"] - 1000.0 / 888.0) < 1e-12
+    m = json.load(open(os.path.join(ROOT, "profiles", "r1_issue_peak.json")))
+    want = m["mix_gwarp_inst_s"] * 1500.0 / (m["nominal_issue_gwarp_inst_s_at_max_clock"] / (148 * 4) * 1e3)
+    assert abs(r["measured_mixed_peak"] - want) < 1e-6 * want and r["frac_of_measured_mixed_peak"] > r["frac"]
+
+
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU port on the host cores; no GPU involved): exactly one JSON line on stdout with
     the contract's keys, whatever the libraries print."""
