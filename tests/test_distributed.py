@@ -64,3 +64,24 @@ def test_single_process_gather_is_a_permutation():
     local = np.arange(8.0).reshape(4, 2)
     out = H.gather_window_summaries(local, shard, 4)
     np.testing.assert_array_equal(out[shard], local)
+
+
+def test_bench_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """The driver launches `bench.py --impl reference --gpus N` under torchrun like the GPU arm: rank 0 alone runs the CPU port
+    and prints the contract line, the other ranks exit 0 without work (no process group, no GPU needed)."""
+    import json
+    import socket
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0", "--burnin", "2", "--nrun", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
