@@ -414,6 +414,84 @@ def forecastinsample(opt: EstOpt, horizon_index: int = -1, ctx: Optional[B.Conte
     return table
 
 
+def makeparams_states(Y, D: int):
+    """The initial state path of `makeParams` (src/Hmc.jl:161-195, :185-187): X_i = argmax_s pdf(Normal(μ0_s, std(Y)), y_i) on the
+    grid μ0 = range(median − 0.25R, median + 0.25R, length = D), first maximum on ties (`findmax`).  1-based states.
+    (The library applies the same rule on the device when no X0 is passed; this host copy exists for window chaining.)"""
+    Y = np.asarray(Y, dtype=np.float64)
+    R = Y.max() - Y.min()
+    med = float(np.median(Y))
+    lo, hi = med - 0.25 * R, med + 0.25 * R
+    mu0 = np.array([lo + (hi - lo) * (k / (D - 1)) for k in range(D)]) if D > 1 else np.array([med])
+    sd = Y.std(ddof=1)
+    z = (Y[:, None] - mu0[None, :]) / sd
+    pdf = np.exp(-(z * z) / 2.0) * 0.3989422804014327 / sd
+    return np.argmax(pdf, axis=1).astype(np.int64) + 1
+
+
+def sample_and_forecast_all(rawdata, dates, dataRange, horizons, filterRange, *, D: int = 2, burnin: int = 1000, Nrun: int = 1000,
+                            initialburn: int = 1000, initialNrun: int = 1000, seed: int = 1234, precision: int = 64,
+                            ctx: Optional[B.Context] = None, rng: Optional[np.random.Generator] = None):
+    """Warm-started rolling estimation: the intent of the reference's `sampleAndForecastAll` (src/Hmc.jl:584-638, stale — it calls
+    helpers with signatures that no longer exist): one long burn-in on the first sample, then for every end date j of
+    filterRange a SHORT burn-in started from the previous window's state path (new dates initialised by the makeParams rule,
+    :613-617), posterior means per end date (`calcPostior`, :564-571) and forecasts from those means (:631-635).
+
+    The device never materialises X, so the carried path is re-drawn: after each window the last parameter draw θ goes through
+    the batched filter and the backward sampler (hmcgpu_filter + hmcgpu_sample_states with fresh uniforms), which is exactly the
+    conditional X | θ, y the next sweep of that chain would have sampled — the chain continues with the same law, not the same
+    realisation.  β stays at its post-first-sweep value 2 in the chained windows (:347).  End dates are serial by construction
+    (the opposite of hmcgpu_estimate's all-end-dates-at-once batch); each call is a narrow batch on the time-parallel kernel.
+
+    Returns a dict of tables with one row per end date: dates, μ [n, D], σ [n, D] (variances), A [n, D, D], πb [n, D] (last
+    row), forecasts [n, 2|H|] (forecast, error vs rawdata[j + h]; NaN past the end of the data) and events."""
+    y = np.asarray(rawdata, dtype=np.float64)
+    start = int(dataRange[0])
+    ends = [int(j) for j in filterRange]
+    if not ends or start < 1 or ends[0] - start + 1 < 2 or ends[-1] > len(y):
+        raise ValueError("filterRange must lie inside rawdata and leave at least 2 observations in the first sample")
+    rng = rng or np.random.default_rng(seed)
+    own = ctx is None
+    ctx = ctx or B.Context(0)
+    two = np.full(D, 2.0)
+    hs = [int(h) for h in horizons] or [1]     # per-draw device forecasts are not used here (forecasts come from the posterior means)
+
+    def run(end, X0, burn, nrun, beta0, wid):
+        spec = B.ProblemSpec(y, [start], [end], K=D, n_chains=1, burnin=burn, nrun=nrun, seed=seed, horizons=hs, precision=precision,
+                             flags=B.FLAG_REF_Q1 | B.FLAG_DRAWS, X0=None if X0 is None else [X0], beta0=beta0, win_id=[wid])
+        o = B.estimate(ctx, spec)
+        mu, s2 = o.mu[0][:, -1], o.sigma2[0][:, -1]
+        A = np.ascontiguousarray(o.A[0][:, :, -1].T)                              # stored [s][r][draw] -> A[r, s] of the last draw
+        Yw = y[start - 1:end]
+        pif = ctx.filter(Yw, A[None], mu[None], s2[None], rng.dirichlet(np.ones(D))[None], precision=64, want_totals=False).pif
+        X = ctx.sample_states(A[None], pif, rng.random((1, len(Yw))))[0]
+        return o, X
+
+    try:
+        _, X = run(ends[0], None, initialburn, initialNrun, None, 0)             # :596-603 long burn-in on the first sample
+        n, nh = len(ends), len(horizons)
+        out = {"dates": [dates[j - 1] if dates is not None else j for j in ends], "μ": np.empty((n, D)), "σ": np.empty((n, D)),
+               "A": np.empty((n, D, D)), "πb": np.empty((n, D)), "forecasts": np.full((n, 2 * nh), np.nan), "events": 0}
+        for i, j in enumerate(ends):
+            X0 = makeparams_states(y[start - 1:j], D)                             # :612 makeParams(Y, D) ...
+            m = min(len(X0), len(X))
+            X0[:m] = X[:m]                                                        # ... :613-615 copy over the previous states
+            o, X = run(j, X0, burnin, Nrun, two, i + 1)
+            mu, A = o.mu[0].mean(1), np.transpose(o.A[0], (2, 1, 0)).mean(0)      # calcPostior: means over the draws
+            pe = o.pi_end[0].mean(1)
+            out["μ"][i], out["σ"][i], out["A"][i], out["πb"][i] = mu, o.sigma2[0].mean(1), A, pe
+            out["events"] += int(o.events)
+            for k, h in enumerate(horizons):
+                f = float(pe @ np.linalg.matrix_power(A, int(h)) @ mu)            # forecast (:658-667) at the posterior means
+                out["forecasts"][i, 2 * k] = f
+                if j + h <= len(y):
+                    out["forecasts"][i, 2 * k + 1] = f - y[j + h - 1]
+    finally:
+        if own:
+            ctx.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Offline analytics of the reference (SURVEY section 8f-4), on the arrays the GPU path returns instead of on CSV files
 

@@ -320,6 +320,60 @@ def test_forecastinsample_filtered_host_logic(H, oracle, monkeypatch):
         H.forecastinsample(opt, ctx=FakeCtx(), probabilities="both")
 
 
+def test_warm_started_window_chaining_host_logic(H, oracle, monkeypatch):
+    """sample_and_forecast_all (the intent of the stale sampleAndForecastAll, src/Hmc.jl:584-638): the carried state path, the
+    makeParams rule for new dates, beta0 = 2 in chained windows, posterior-mean tables and forecasts — with the three C-ABI
+    calls it makes replaced by oracle-backed stand-ins that check the argument shapes the real binding requires."""
+    from types import SimpleNamespace
+    from conftest import K3_TRUTH, synth_hmm
+    from hmc_jl_b200 import binding as B
+    y, _ = synth_hmm(260, **K3_TRUTH)
+    for n in (150, 201):
+        np.testing.assert_array_equal(H.makeparams_states(y[:n], 3), oracle.make_params(y[:n], 3)[0])
+    seen = []
+
+    def fake_estimate(ctx, spec):
+        end = int(spec.win_end[0])
+        X0 = None if spec.X0 is None else spec.X0.copy()
+        seen.append(SimpleNamespace(end=end, X0=X0, beta0=spec.hp[3], burnin=spec.burnin, nrun=spec.nrun, wid=int(spec.win_id[0])))
+        assert spec.n_chains == 1 and spec.flags & B.FLAG_DRAWS and (X0 is None or X0.shape == (end,))
+        r = oracle.gibbs(spec.y[0, :end], spec.K, spec.burnin, spec.nrun, seed=spec.seed, chain=int(spec.win_id[0]), horizons=(12,),
+                         y_future=[np.nan], X0=X0, beta0=spec.hp[3])
+        return SimpleNamespace(mu=[r.mu.T], sigma2=[r.sigma2.T], A=[np.transpose(r.A, (2, 1, 0))], pi_end=[r.pi_end.T], events=0)
+
+    class FakeCtx:
+        def filter(self, yw, A, mu, s2, rho, precision=64, want_totals=True):
+            assert A.shape == (1, 3, 3) and mu.shape == s2.shape == rho.shape == (1, 3) and yw.ndim == 1 and precision == 64
+            return SimpleNamespace(pif=oracle.forward(yw, A[0], mu[0], s2[0], rho[0], want_Pf=False).pif[None])
+
+        def sample_states(self, A, pif, u, piN=None):
+            assert A.shape == (1, 3, 3) and pif.ndim == 3 and u.shape == pif.shape[:2] and (u >= 0).all() and (u < 1).all()
+            return oracle.sample_states(pif[0], A[0], u[0], form=1)[None]
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(B, "estimate", fake_estimate)
+    dates = [f"d{i}" for i in range(1, 261)]
+    out = H.sample_and_forecast_all(y, dates, range(1, 261), [1, 12], range(200, 204), D=3, burnin=60, Nrun=300, initialburn=800,
+                                    initialNrun=50, ctx=FakeCtx())
+    assert [s.end for s in seen] == [200, 200, 201, 202, 203] and [s.wid for s in seen] == [0, 1, 2, 3, 4]
+    assert seen[0].X0 is None and seen[0].beta0 is None and (seen[0].burnin, seen[0].nrun) == (800, 50)
+    for a, b in zip(seen[1:], seen[2:]):                               # chained windows: short burn-in, beta0 = 2, carried path
+        assert (b.burnin, b.nrun) == (60, 300) and b.beta0.tolist() == [2.0, 2.0, 2.0] and len(b.X0) == len(a.X0) + 1
+        assert b.X0[-1] == H.makeparams_states(y[:b.end], 3)[-1]       # the new date starts from the makeParams rule (:612-617)
+    # the carried path is a draw of X | theta, y: overwhelmingly equal to the true regime on this well-separated series
+    assert out["dates"] == ["d200", "d201", "d202", "d203"] and out["μ"].shape == (4, 3) and out["A"].shape == (4, 3, 3)
+    np.testing.assert_allclose(out["A"].sum(2), 1.0, atol=1e-9)
+    np.testing.assert_allclose(out["πb"].sum(1), 1.0, atol=1e-9)
+    assert np.all(np.abs(out["μ"] - np.array(K3_TRUTH["mu"])) < 0.6)                         # warm start: 60 sweeps of burn-in suffice
+    f12 = np.array([out["πb"][i] @ np.linalg.matrix_power(out["A"][i], 12) @ out["μ"][i] for i in range(4)])
+    np.testing.assert_allclose(out["forecasts"][:, 2], f12, rtol=1e-12)
+    np.testing.assert_allclose(out["forecasts"][:, 1], out["forecasts"][:, 0] - y[200:204], rtol=1e-12)
+    with pytest.raises(ValueError):
+        H.sample_and_forecast_all(y, dates, range(1, 261), [12], range(259, 263), D=3, ctx=FakeCtx())
+
+
 def test_bench_issue_roofline_arithmetic():
     """bench.issue_roofline on the numbers of the committed bench line: nominal fraction as recorded, and the measured
     mixed-blend peak (profiles/r1_issue_peak.json) scaled to the sampled clock."""
