@@ -374,6 +374,24 @@ def test_warm_started_window_chaining_host_logic(H, oracle, monkeypatch):
         H.sample_and_forecast_all(y, dates, range(1, 261), [12], range(259, 263), D=3, ctx=FakeCtx())
 
 
+def test_committed_bench_lines_carry_the_contract_keys():
+    """profiles/r1_bench_n*.json are bench.py's own output lines: each parses and carries the measurement contract's keys."""
+    import glob
+    import json
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_bench_n*.json")))
+    assert files
+    for f in files:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert k in d, (f, k)
+        assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+        assert d["roofline"]["bound"] == "hbm" and abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if d["n_gpus"] == 1:
+            assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
 def test_bench_issue_roofline_arithmetic():
     """bench.issue_roofline on the numbers of the committed bench line: nominal fraction as recorded, and the measured
     mixed-blend peak (profiles/r1_issue_peak.json) scaled to the sampled clock."""
