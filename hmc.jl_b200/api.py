@@ -41,8 +41,6 @@ class EstOpt:
     n_chains: int = 1
     precision: int = 64
     device: int = 0
-    full_pib: bool = False
-    extra: dict = field(default_factory=dict)
 
     def __post_init__(self):
         sr = self.sampleRange
@@ -259,7 +257,11 @@ def gather_window_summaries(local: np.ndarray, shard: np.ndarray, n_windows: int
         return out
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
-    max_rows = (n_windows + world - 1) // world + 1
+    # shards are balanced by sum of T_w (LPT), not by window count: a shard of short windows can hold many more rows than
+    # n_windows / world, so the padded payload is sized by the real maximum over the ranks
+    rows = torch.tensor([len(shard)], dtype=torch.int64, device=device if device is not None else "cpu")
+    dist.all_reduce(rows, op=dist.ReduceOp.MAX)
+    max_rows = max(1, int(rows.item()))
     # payload rows: [global index, F values]; padded with index -1
     pad = torch.full((max_rows, local.shape[1] + 1), -1.0, dtype=torch.float64)
     pad[: len(shard), 0] = torch.as_tensor(np.asarray(shard), dtype=torch.float64)
@@ -414,6 +416,55 @@ def forecastinsample(opt: EstOpt, horizon_index: int = -1, ctx: Optional[B.Conte
     return table
 
 
+def saveinsampleforecasts(table, fname: str):
+    """Mirror of Hmc.saveinsampleforecasts (src/Hmc.jl:701-705): the table of `forecastinsample` as CSV with the reference's
+    header `date,forecast,forecasterror,current,future,s1..sD` (layout of data/output/official_insample/forecats_insample.csv;
+    CSV.jl writes full-precision floats, `repr` does the same here)."""
+    import os
+    os.makedirs(os.path.dirname(os.path.abspath(fname)), exist_ok=True)
+    D = sum(1 for k in table if k.startswith("s") and k[1:].isdigit())
+    cols = ["date", "forecast", "forecasterror", "current", "future"] + [f"s{i}" for i in range(1, D + 1)]
+    with open(fname, "w") as f:
+        f.write(",".join(cols) + "\n")
+        for i in range(len(table["forecast"])):
+            f.write(",".join([str(table["date"][i])] + [repr(float(table[c][i])) for c in cols[1:]]) + "\n")
+    return fname
+
+
+def smoothStates(rawdata, dates, dataRange, *, D: int = 2, burnin: int = 1000, Nrun: int = 1000, n_chains: int = 1, seed: int = 1234,
+                 precision: int = 64, ctx: Optional[B.Context] = None):
+    """GPU version of Hmc.smoothStates (src/Hmc.jl:640-656): one estimation on rawdata[dataRange] and, per date of the sample, the
+    posterior mean of the smoothed state probabilities πb[t, :] (`calcPostior`, :564-571), accumulated on the device
+    (HMCGPU_FLAG_SMOOTHED_MEAN).  Returns the reference's table: a list of rows [date, p_1, ..., p_D]."""
+    y = np.asarray(rawdata, dtype=np.float64)
+    s, e = int(dataRange[0]), int(dataRange[-1])
+    own = ctx is None
+    ctx = ctx or B.Context(0)
+    try:
+        spec = B.ProblemSpec(y, [s], [e], K=D, n_chains=n_chains, burnin=burnin, nrun=Nrun, seed=seed, horizons=[], precision=precision,
+                             flags=B.FLAG_REF_Q1 | B.FLAG_SMOOTHED_MEAN)
+        o = B.estimate(ctx, spec)
+    finally:
+        if own:
+            ctx.close()
+    pm = o.pib_mean[0]
+    return [[dates[j - 1] if dates is not None else j] + pm[i].tolist() for i, j in enumerate(range(s, e + 1))]
+
+
+def savesmoothresults(πbresults, directory: str):
+    """Mirror of Hmc.savesmoothresults (src/Hmc.jl:750-758): `smoothed_state_probs.csv` with the reference's header
+    `Date,state_1,...,state_D` (its Dname vector is state_0..state_D with the first entry replaced by Date)."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    path = os.path.join(directory, "smoothed_state_probs.csv")
+    D = len(πbresults[0]) - 1
+    with open(path, "w") as f:
+        f.write(",".join(["Date"] + [f"state_{j}" for j in range(1, D + 1)]) + "\n")
+        for row in πbresults:
+            f.write(",".join([str(row[0])] + [repr(float(v)) for v in row[1:]]) + "\n")
+    return path
+
+
 def makeparams_states(Y, D: int):
     """The initial state path of `makeParams` (src/Hmc.jl:161-195, :185-187): X_i = argmax_s pdf(Normal(μ0_s, std(Y)), y_i) on the
     grid μ0 = range(median − 0.25R, median + 0.25R, length = D), first maximum on ties (`findmax`).  1-based states.
@@ -423,10 +474,8 @@ def makeparams_states(Y, D: int):
     med = float(np.median(Y))
     lo, hi = med - 0.25 * R, med + 0.25 * R
     mu0 = np.array([lo + (hi - lo) * (k / (D - 1)) for k in range(D)]) if D > 1 else np.array([med])
-    sd = Y.std(ddof=1)
-    z = (Y[:, None] - mu0[None, :]) / sd
-    pdf = np.exp(-(z * z) / 2.0) * 0.3989422804014327 / sd
-    return np.argmax(pdf, axis=1).astype(np.int64) + 1
+    # the pdfs share sd: first maximum of the pdf = first minimum of |y - mu0_k| (exact; the library and the oracle use the same form)
+    return np.argmin(np.abs(Y[:, None] - mu0[None, :]), axis=1).astype(np.int64) + 1
 
 
 def sample_and_forecast_all(rawdata, dates, dataRange, horizons, filterRange, *, D: int = 2, burnin: int = 1000, Nrun: int = 1000,

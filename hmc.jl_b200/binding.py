@@ -26,7 +26,11 @@ SYMBOLS = [
     "hmcgpu_ctx_sync", "hmcgpu_estimate", "hmcgpu_estimate_multi", "hmcgpu_plan_create", "hmcgpu_plan_run",
     "hmcgpu_plan_fetch", "hmcgpu_plan_destroy", "hmcgpu_filter", "hmcgpu_filter_masked", "hmcgpu_smooth", "hmcgpu_sample_states",
     "hmcgpu_draw_params", "hmcgpu_draw_params_signals", "hmcgpu_forecast", "hmcgpu_philox", "hmcgpu_philox_rounds",
+    "hmcgpu_build_info", "hmcgpu_ctx_trim",
 ]
+KERNEL_NAMES = {0: "gibbs_sweeps_kernel (thread per chain)", 1: "gibbs_scan_kernel (warp per chain, time-parallel)",
+                2: "gibbs_wide_kernel (lane per state)", 3: "gibbs_pair_kernel (two chains per thread)",
+                4: "gibbs_seg_kernel (L lanes per chain, one time segment per lane)"}
 
 _dp = C.POINTER(C.c_double)
 _i32p = C.POINTER(C.c_int32)
@@ -50,7 +54,7 @@ class Result(C.Structure):
                 ("summary_mean", _dp), ("summary_var", _dp), ("pib_mean", _dp), ("insample_forecast_mean", _dp), ("status", _i32p),
                 ("gpu_ms", C.c_double), ("sweep_kernel_ms", C.c_double), ("n_launches", C.c_int64),
                 ("n_sweep_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("state_steps", C.c_int64)]
+                ("state_steps", C.c_int64), ("sweep_launch_ms_sum", C.c_double), ("sweep_kernel", C.c_int32), ("n_tasks", C.c_int32)]
 
 
 class HmcGpuError(RuntimeError):
@@ -81,6 +85,14 @@ def load(build_if_missing: bool = True):
     L.hmcgpu_ctx_destroy.argtypes = [C.c_void_p]
     L.hmcgpu_ctx_destroy.restype = None
     L.hmcgpu_ctx_sync.argtypes = [C.c_void_p]
+    L.hmcgpu_ctx_trim.argtypes = [C.c_void_p]
+    L.hmcgpu_build_info.restype = C.c_char_p
+    L.hmcgpu_build_info.argtypes = []
+    # a library built from other sources than the ones next to it must never be measured or tested by mistake
+    info = L.hmcgpu_build_info().decode()
+    want = _build.source_hash()
+    if want is not None and info.split(";")[1] != want:
+        raise HmcGpuError(ERR_UNSUPPORTED, f"{path} was built from other sources (library {info}, sources {want}): rebuild with hmc.jl_b200/build.py --force")
     L.hmcgpu_estimate.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Result)]
     L.hmcgpu_estimate_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(Problem), C.POINTER(Result)]
     L.hmcgpu_plan_create.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(C.c_void_p)]
@@ -129,6 +141,10 @@ class Context:
         if getattr(self, "h", None):
             self.L.hmcgpu_ctx_destroy(self.h)
             self.h = None
+
+    def trim(self):
+        """Release the idle device buffers kept for reuse between calls (hmcgpu_ctx_trim)."""
+        self._check(self.L.hmcgpu_ctx_trim(self.h))
 
     def __del__(self):
         try:
@@ -273,7 +289,7 @@ class ProblemSpec:
             o.pib_mean = np.empty(int(self.T.sum()) * K)
             o.insample_forecast_mean = np.empty(int(self.T.sum()) * nh) if nh else None
         res = Result(_p(o.mu), _p(o.sigma2), _p(o.A), _p(o.pi_end), _p(o.forecasts), _p(o.loglik), _p(o.summary_mean),
-                     _p(o.summary_var), _p(o.pib_mean), _p(o.insample_forecast_mean), _p(o.status, _i32p), 0, 0, 0, 0, 0, 0, 0)
+                     _p(o.summary_var), _p(o.pib_mean), _p(o.insample_forecast_mean), _p(o.status, _i32p), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
         return o, res
 
     def finish(self, o, res, rc):
@@ -281,6 +297,7 @@ class ProblemSpec:
         o.gpu_ms, o.sweep_kernel_ms = res.gpu_ms, res.sweep_kernel_ms
         o.n_launches, o.n_sweep_launches = res.n_launches, res.n_sweep_launches
         o.h2d_bytes, o.d2h_bytes, o.state_steps = res.h2d_bytes, res.d2h_bytes, res.state_steps
+        o.sweep_launch_ms_sum, o.sweep_kernel, o.n_tasks = res.sweep_launch_ms_sum, res.sweep_kernel, res.n_tasks
         if o.pib_mean is not None:   # split into per-window [N_w, K] (stored column-major N_w x K)
             K, off, parts = self.K, 0, []
             for n in self.T:

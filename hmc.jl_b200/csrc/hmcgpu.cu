@@ -69,7 +69,14 @@ struct DevPool {
     std::mutex mu;
     std::multimap<size_t, void*> free_blocks;
     size_t pooled = 0;
-    static constexpr size_t kMaxPooled = 64ull << 30;
+    // Upper bound of idle memory kept for reuse (HMCGPU_POOL_MAX_GB overrides; 0 disables pooling).  Idle blocks are also
+    // released by hmcgpu_ctx_trim, when another allocation on this context fails, and when the context is destroyed, so
+    // other allocators on the same GPU (torch, NCCL, a second context) are never starved by memory nobody is using.
+    size_t max_pooled = 16ull << 30;
+    static constexpr size_t kMaxBlocks = 64;
+    DevPool() {
+        if (const char* e = getenv("HMCGPU_POOL_MAX_GB")) max_pooled = (size_t)(atof(e) * (double)(1ull << 30));
+    }
     cudaError_t get(size_t n, void** out) {
         {
             std::lock_guard<std::mutex> g(mu);
@@ -86,7 +93,14 @@ struct DevPool {
     }
     void put(size_t n, void* p) {
         std::lock_guard<std::mutex> g(mu);
-        if (pooled + n > kMaxPooled || free_blocks.size() >= 256) { cudaFree(p); return; }
+        if (n > max_pooled) { cudaFree(p); return; }
+        // make room by dropping the smallest idle blocks first (big buffers are the expensive ones to re-allocate)
+        while (!free_blocks.empty() && (pooled + n > max_pooled || free_blocks.size() >= kMaxBlocks)) {
+            auto it = free_blocks.begin();
+            cudaFree(it->second);
+            pooled -= it->first;
+            free_blocks.erase(it);
+        }
         free_blocks.emplace(n, p);
         pooled += n;
     }
@@ -124,8 +138,6 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-extern "C" int hmcgpu_version(void) { return 100; }
-
 extern "C" int hmcgpu_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -138,20 +150,28 @@ extern "C" int hmcgpu_ctx_create(int device, hmcgpu_ctx** out) {
     int n = hmcgpu_device_count();
     if (n <= 0) return fail(nullptr, HMCGPU_ERR_NODEVICE, "no CUDA device visible (this library has no CPU fallback)");
     if (device < 0 || device >= n) return fail(nullptr, HMCGPU_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
-    hmcgpu_ctx* ctx = new hmcgpu_ctx();
+    std::unique_ptr<hmcgpu_ctx> ctx(new hmcgpu_ctx());     // released into *out only when everything below succeeded
     ctx->device = device;
     CU(nullptr, cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(nullptr, cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
-        delete ctx;
         return fail(nullptr, HMCGPU_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
                     device, prop.major, prop.minor);
     }
     ctx->sm_count = prop.multiProcessorCount;
     CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->pool = std::make_shared<DevPool>();
-    *out = ctx;
+    *out = ctx.release();
+    return HMCGPU_OK;
+}
+
+// releases the idle device buffers this context keeps for reuse (they are also released on allocation failure and at destroy)
+extern "C" int hmcgpu_ctx_trim(hmcgpu_ctx* ctx) {
+    if (!ctx) return HMCGPU_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->pool) ctx->pool->release_all();
     return HMCGPU_OK;
 }
 
@@ -420,6 +440,7 @@ __global__ void forecast_kernel(long long B, const double* __restrict__ mu, cons
 // ---- runtime-K (5..32) versions of the deterministic entry points: same arithmetic, small local arrays, A read from
 //      global memory.  These are checking utilities, not hot paths.
 constexpr int kMaxK = 32;
+constexpr int kMaxHorizon = 100000;   // forecast horizons run an in-kernel loop of that length per saved draw
 
 template <typename R>
 __global__ void filter_kernel_generic(int K, long long B, long long T, const double* __restrict__ y, long long ystride,
@@ -577,7 +598,8 @@ __global__ void philox_kernel(long long n, int rounds, const unsigned* __restric
 struct Xfer {
     hmcgpu_ctx* ctx;
     std::vector<DevBuf*> owned;
-    ~Xfer() { for (auto* b : owned) delete b; }
+    // error paths return with copies / kernels still queued on the stream: nothing may go back to the pool before they finish
+    ~Xfer() { cudaStreamSynchronize(ctx->stream); for (auto* b : owned) delete b; }
     template <typename T> int up(const T* host, size_t n, T** dev) {
         DevBuf* b = new DevBuf();
         owned.push_back(b);
@@ -879,12 +901,14 @@ __global__ void __launch_bounds__(256) window_init_kernel(int K, const double* _
     for (int i = threadIdx.x; i < N; i += blockDim.x) {                               // :185-187 findmax of the pdfs
         if (X0u) { x0[i] = (unsigned char)(X0u[x0_off[w] + i] - 1); continue; }
         const double v = yi[i * ld];
+        // first maximum of pdf(Normal(mu0_k, sd), v) = first minimum of |v - mu0_k| (all states share sd): exact, independent of
+        // the exp implementation and of the last bits of sd, so near-ties (the median observation between two grid points)
+        // resolve exactly as in the oracle; exact ties go to the lower state like findmax
         int best = 0;
-        double z = (v - mu0[0]) / sd, bv = exp(-(z * z) / 2.0) * 0.3989422804014327 / sd;
+        double bv = fabs(__dsub_rn(v, mu0[0]));
         for (int k = 1; k < K; ++k) {
-            z = (v - mu0[k]) / sd;
-            const double pv = exp(-(z * z) / 2.0) * 0.3989422804014327 / sd;
-            if (pv > bv) { bv = pv; best = k; }
+            const double pv = fabs(__dsub_rn(v, mu0[k]));
+            if (pv < bv) { bv = pv; best = k; }
         }
         x0[i] = (unsigned char)best;
     }
@@ -1078,9 +1102,12 @@ struct hmcgpu_plan {
     bool scan = false;   // narrow batch: one warp per chain, time-parallel (gibbs_scan_kernel.cuh)
     bool wide = false;
     bool pair = false;   // fp32 paired kernel: a task is 64 chain slots (two chains per thread)
+    bool seg = false;    // mid-width batch: L lanes per chain, each lane one contiguous time segment (gibbs_seg_kernel.cuh)
     int n_groups = 1, n_bufs = 1;
     std::vector<cudaStream_t> gstreams;
     std::vector<cudaEvent_t> pool_events;
+    std::vector<cudaEvent_t> timing_events;   // pairs around every sweep launch + one end-of-sweeps event per group (timing enabled)
+    double launch_ms_sum = 0.0;
     DevBuf d_mu, d_sig2, d_A, d_pie, d_fc, d_ll, d_sum, d_sumsq, d_pibsum, d_fcsum;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     double gpu_ms = 0.0, sweep_ms = 0.0;
@@ -1089,6 +1116,7 @@ struct hmcgpu_plan {
     ~hmcgpu_plan() {
         for (auto s2 : gstreams) cudaStreamDestroy(s2);
         for (auto e : pool_events) cudaEventDestroy(e);
+        for (auto e : timing_events) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (evk0) cudaEventDestroy(evk0);
@@ -1118,8 +1146,20 @@ static int validate_problem(hmcgpu_ctx* ctx, const hmcgpu_problem* p) {
         if (p->is_signal && !(p->kappa >= 0.0)) return fail(ctx, HMCGPU_ERR_ARG, "kappa must be >= 0 with is_signal");
         if (p->pi_row_back < 0) return fail(ctx, HMCGPU_ERR_ARG, "pi_row_back < 0");
     }
-    for (int j = 0; j < p->n_h; ++j) if (p->horizons[j] < 0) return fail(ctx, HMCGPU_ERR_ARG, "horizons must be >= 0");
+    for (int j = 0; j < p->n_h; ++j)
+        if (p->horizons[j] < 0 || p->horizons[j] > kMaxHorizon) return fail(ctx, HMCGPU_ERR_ARG, "horizons must be in 0..%d", kMaxHorizon);
+    // The InverseGamma draw needs a > 0 and b > 0 (the reference catches the exception and keeps the old value, :319-329);
+    // with positive priors both always hold for finite statistics, so a skipped draw can only follow a NaN.
+    for (int i = 0; i < p->K; ++i) {
+        if ((p->alpha && !(p->alpha[i] > 0.0)) || (p->nu && !(p->nu[i] > 0.0)) || (p->beta0 && !(p->beta0[i] > 0.0)) || (p->beta && !(p->beta[i] > 0.0)))
+            return fail(ctx, HMCGPU_ERR_ARG, "alpha, nu, beta0 and beta must be > 0 (state %d)", i + 1);
+        if (p->xi && !std::isfinite(p->xi[i])) return fail(ctx, HMCGPU_ERR_ARG, "xi[%d] is not finite", i);
+    }
     for (int w = 0; w < p->n_windows; ++w) {
+        // the Philox chain id win_id * n_chains + chain is a 32-bit counter word: ids must not wrap (distinct windows would share streams)
+        const long long wid = p->win_id ? (long long)p->win_id[w] : (long long)w;
+        if (wid < 0 || (wid + 1) * (long long)p->n_chains > 0x100000000LL)
+            return fail(ctx, HMCGPU_ERR_ARG, "window %d: win_id %lld with %d chains per window leaves the 32-bit chain-id range", w, wid, p->n_chains);
         const long long s = p->win_start[w], e = p->win_end[w];
         if (s < 1 || e > p->y_len || e - s + 1 < 2) return fail(ctx, HMCGPU_ERR_ARG, "window %d: [%lld,%lld] outside 1..%lld or shorter than 2", w, s, e, (long long)p->y_len);
         if (p->win_series && (p->win_series[w] < 0 || p->win_series[w] >= p->n_series)) return fail(ctx, HMCGPU_ERR_ARG, "window %d: bad series index", w);
@@ -1417,7 +1457,24 @@ static int plan_run_t(hmcgpu_plan* pl) {
     cudaEvent_t ev_init;
     CU(ctx, new_event(&ev_init));
     CU(ctx, cudaEventRecord(ev_init, st));
+    CU(ctx, cudaEventRecord(pl->evk0, st));                  // start of the sweeps (sweep_kernel_ms)
     for (int g = 0; g < G; ++g) CU(ctx, cudaStreamWaitEvent(pl->gstreams[g], ev_init, 0));
+    // an event pair around every sweep launch (its own duration, on its own stream) and one event per group after its last launch
+    static const bool launch_timing = !(getenv("HMCGPU_LAUNCH_TIMING") && atoi(getenv("HMCGPU_LAUNCH_TIMING")) == 0);
+    size_t tev_used = 0;
+    auto timing_event = [&](cudaEvent_t* e) -> cudaError_t {
+        if (tev_used == pl->timing_events.size()) {
+            cudaEvent_t x;
+            cudaError_t rc = cudaEventCreate(&x);
+            if (rc != cudaSuccess) return rc;
+            pl->timing_events.push_back(x);
+        }
+        *e = pl->timing_events[tev_used++];
+        return cudaSuccess;
+    };
+    std::vector<cudaEvent_t> gend(G, nullptr);
+    for (int g = 0; g < G; ++g) CU(ctx, timing_event(&gend[g]));
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> launch_pairs;
 
     const GibbsLaunch cfg{pl->flags, pl->max_T, ctx->sm_count, pl->n_h, pl->sig};
     const long long S = pl->burnin + pl->nrun;
@@ -1501,6 +1558,8 @@ static int plan_run_t(hmcgpu_plan* pl) {
             }
             a.sweep0 = s0; a.n_sweeps = (int)n;
             a.task0 = g; a.task_stride = G; a.n_tasks = (pl->n_warps - g + G - 1) / G;
+            cudaEvent_t lt0 = nullptr, lt1 = nullptr;
+            if (launch_timing) { CU(ctx, timing_event(&lt0)); CU(ctx, timing_event(&lt1)); CU(ctx, cudaEventRecord(lt0, gs)); }
             if constexpr (K == 0) {
                 CU(ctx, (launch_gibbs_wide<R>(cfg, a, pl->K, pl->slot_pi_off.as<long long>(), gs)));
             } else if constexpr (K <= 4) {
@@ -1512,8 +1571,10 @@ static int plan_run_t(hmcgpu_plan* pl) {
             } else {
                 CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
             }
+            if (launch_timing) { CU(ctx, cudaEventRecord(lt1, gs)); launch_pairs.emplace_back(lt0, lt1); }
             ++pl->n_launches; ++pl->n_sweep_launches;
             next[g] = s0 + n;
+            if (next[g] >= S) CU(ctx, cudaEventRecord(gend[g], gs));
             if (k >= 0 && next[g] == pl->burnin + std::min<long long>(pl->nrun, (k + 1) * pl->chunk)) {
                 CU(ctx, new_event(&chunk_done[k][g]));
                 CU(ctx, cudaEventRecord(chunk_done[k][g], gs));
@@ -1534,7 +1595,20 @@ static int plan_run_t(hmcgpu_plan* pl) {
     float ms = 0.f;
     CU(ctx, cudaEventElapsedTime(&ms, pl->ev0, pl->ev1));
     pl->gpu_ms = ms;
-    pl->sweep_ms = ms;                                       // launches of different groups overlap: report the enclosing time
+    // the launches of different groups overlap: sweep_ms is the interval from the start of the first sweep launch to the end of
+    // the last one (it leaves out the init kernel and the post-processing tail); launch_ms_sum adds up each launch's own duration
+    pl->sweep_ms = 0.0;
+    for (int g = 0; g < G; ++g) {
+        float t = 0.f;
+        CU(ctx, cudaEventElapsedTime(&t, pl->evk0, gend[g]));
+        pl->sweep_ms = std::max(pl->sweep_ms, (double)t);
+    }
+    pl->launch_ms_sum = 0.0;
+    for (auto& pr : launch_pairs) {
+        float t = 0.f;
+        CU(ctx, cudaEventElapsedTime(&t, pr.first, pr.second));
+        pl->launch_ms_sum += t;
+    }
     pl->ran = true;
     return HMCGPU_OK;
 }
@@ -1546,7 +1620,11 @@ static int plan_create_impl(hmcgpu_ctx* ctx, const hmcgpu_problem* p, hmcgpu_pla
     std::unique_ptr<hmcgpu_plan> pl(new hmcgpu_plan());
     pl->ctx = ctx;
     int rc = (p->precision == 32) ? plan_build<float>(pl.get(), p) : plan_build<double>(pl.get(), p);
-    if (rc != 0) return rc;
+    if (rc != 0) {
+        cudaStreamSynchronize(ctx->stream);    // uploads / init kernels may still be queued on buffers the plan is about to release
+        cudaGetLastError();
+        return rc;
+    }
     *out = pl.release();
     return HMCGPU_OK;
 }
@@ -1642,6 +1720,9 @@ static int plan_fetch_impl(hmcgpu_plan* pl, hmcgpu_result* r) {
     }
     r->gpu_ms = pl->gpu_ms; r->sweep_kernel_ms = pl->sweep_ms; r->n_launches = pl->n_launches;
     r->n_sweep_launches = pl->n_sweep_launches; r->h2d_bytes = pl->h2d; r->d2h_bytes = d2h; r->state_steps = pl->state_steps;
+    r->sweep_launch_ms_sum = pl->launch_ms_sum;
+    r->sweep_kernel = pl->wide ? HMCGPU_KERNEL_LANE : pl->scan ? HMCGPU_KERNEL_SCAN : pl->pair ? HMCGPU_KERNEL_PAIR : pl->seg ? HMCGPU_KERNEL_SEG : HMCGPU_KERNEL_THREAD;
+    r->n_tasks = pl->n_warps;
     return bad;
 }
 
@@ -1763,6 +1844,7 @@ static int estimate_multi_impl(const int* devices, int n_dev, const hmcgpu_probl
     for (auto& t : th) t.join();
     int bad = 0;
     r->gpu_ms = 0; r->sweep_kernel_ms = 0; r->n_launches = 0; r->n_sweep_launches = 0; r->h2d_bytes = 0; r->d2h_bytes = 0; r->state_steps = 0;
+    r->sweep_launch_ms_sum = 0; r->sweep_kernel = 0; r->n_tasks = 0;
     for (int d = 0; d < n_dev; ++d) {
         if (rcs[d] < 0) return fail(nullptr, rcs[d], "device %d: %s", devices[d], errs[d].c_str());
         bad += rcs[d];
@@ -1770,6 +1852,8 @@ static int estimate_multi_impl(const int* devices, int n_dev, const hmcgpu_probl
         r->sweep_kernel_ms = std::max(r->sweep_kernel_ms, parts[d].sweep_kernel_ms);
         r->n_launches += parts[d].n_launches; r->n_sweep_launches += parts[d].n_sweep_launches;
         r->h2d_bytes += parts[d].h2d_bytes; r->d2h_bytes += parts[d].d2h_bytes; r->state_steps += parts[d].state_steps;
+        r->sweep_launch_ms_sum += parts[d].sweep_launch_ms_sum; r->n_tasks += parts[d].n_tasks;
+        if (shard[d].size()) r->sweep_kernel = parts[d].sweep_kernel;
     }
     return bad;
 }

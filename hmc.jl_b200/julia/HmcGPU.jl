@@ -43,6 +43,7 @@ mutable struct Result
     summary_mean::Ptr{Float64}; summary_var::Ptr{Float64}; pib_mean::Ptr{Float64}; insample_forecast_mean::Ptr{Float64}; status::Ptr{Int32}
     gpu_ms::Float64; sweep_kernel_ms::Float64; n_launches::Int64; n_sweep_launches::Int64
     h2d_bytes::Int64; d2h_bytes::Int64; state_steps::Int64
+    sweep_launch_ms_sum::Float64; sweep_kernel::Int32; n_tasks::Int32
 end
 
 struct HmcGpuError <: Exception
@@ -63,6 +64,24 @@ mutable struct Context
 end
 
 lasterror(ctx::Context) = unsafe_string(ccall((:hmcgpu_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.h))
+
+# Releases the context (stream, device buffers) now instead of whenever the GC runs the finalizer.
+function Base.close(ctx::Context)
+    ctx.h != C_NULL && ccall((:hmcgpu_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx.h)
+    ctx.h = C_NULL
+    return nothing
+end
+# Hands the idle device buffers the context keeps for reuse back to the driver (hmcgpu_ctx_trim).
+trim(ctx::Context) = ccall((:hmcgpu_ctx_trim, LIB), Cint, (Ptr{Cvoid},), ctx.h)
+
+# One context per device for the whole session: a loop over end dates that calls estimatemodel(opt) must not create a
+# context (stream + buffer pool) per call and wait for the GC to release them.
+const _contexts = Dict{Int,Context}()
+function default_context(device::Integer = 0)
+    c = get(_contexts, Int(device), nothing)
+    (c === nothing || c.h == C_NULL) && (c = _contexts[Int(device)] = Context(device))
+    return c
+end
 
 """
     estimate(ctx, rawdata, win_start, win_end; D, n_chains, burnin, Nrun, seed, horizons, precision)
@@ -87,7 +106,7 @@ function estimate(ctx::Context, rawdata::VecOrMat{Float64}, win_start::Vector{In
     fc = Array{Float64}(undef, R, 2nh, nw)
     status = zeros(Int32, n_chains, nw)
     res = Result(pointer(mu), pointer(sig), pointer(A), pointer(pie), nh > 0 ? pointer(fc) : C_NULL, C_NULL,
-                 C_NULL, C_NULL, C_NULL, C_NULL, pointer(status), 0.0, 0.0, 0, 0, 0, 0, 0)
+                 C_NULL, C_NULL, C_NULL, C_NULL, pointer(status), 0.0, 0.0, 0, 0, 0, 0, 0, 0.0, 0, 0)
     rc = GC.@preserve rawdata win_start win_end horizons mu sig A pie fc status win_series win_init_series is_signal xi alpha nu begin
         prob = Problem(pointer(rawdata), y_len, n_series, nw, ptr_or_null(win_series), pointer(win_start), pointer(win_end), C_NULL,
                        D, n_chains, burnin, Nrun, UInt64(seed), ptr_or_null(xi), ptr_or_null(alpha), ptr_or_null(nu), C_NULL, C_NULL,
@@ -103,13 +122,13 @@ end
 signalmask(opt) = (m = zeros(UInt8, length(opt.rawdata)); m[collect(opt.signalRange)] .= 0x01; m)
 
 """
-    estimatemodel(opt; ctx = Context(0), n_chains = 1, precision = 64)
+    estimatemodel(opt; ctx = default_context(0), n_chains = 1, precision = 64)
 
 GPU drop-in for `Hmc.estimatemodel(opt)` (src/Hmc.jl:850-865).  `opt` is an `Hmc.estopt`.  `πb` is returned as an
 Nrun×1×D array holding the end-of-window row: `saveresults` reads `samples.πb[:, end, :]` (src/Hmc.jl:744), which works
 unchanged; the Nrun×N×D tensor of the reference (3.5 GB per end date in production) is never materialised.
 """
-function estimatemodel(opt; ctx::Context = Context(0), n_chains::Int = 1, precision::Int = 64)
+function estimatemodel(opt; ctx::Context = default_context(0), n_chains::Int = 1, precision::Int = 64)
     sr = opt.sampleRange
     # a non-empty signalRange still goes through the signal branches with hp = HyperParams(Y, D), i.e. κ = 1.0 (src/Hmc.jl:853)
     mask = isempty(opt.signalRange) ? UInt8[] : signalmask(opt)
@@ -129,7 +148,7 @@ function estimatemodel(opt; ctx::Context = Context(0), n_chains::Int = 1, precis
 end
 
 """
-    estimatesignals!(opt; ctx = Context(0), n_chains = 1, precision = 64)
+    estimatesignals!(opt; ctx = default_context(0), n_chains = 1, precision = 64)
 
 GPU drop-in for `Hmc.estimatesignals!(opt)` (src/Hmc.jl:868-914).  The `opt.noiseSamples` perturbed copies of the sample
 are estimated side by side as independent chains (the reference chains them serially on one state, each with its own
@@ -137,7 +156,7 @@ are estimated side by side as independent chains (the reference chains them seri
 `makeParams` on the real data, `πb` is the smoothed row at `opt.endIndex` (:893), forecasts follow :900-906.
 Same logic as `estimatesignals` in hmc.jl_b200/api.py, which is the version the GPU tests exercise.
 """
-function estimatesignals!(opt; ctx::Context = Context(0), n_chains::Int = 1, precision::Int = 64)
+function estimatesignals!(opt; ctx::Context = default_context(0), n_chains::Int = 1, precision::Int = 64)
     if isapprox(opt.σsignal, 0)
         base = estimatemodel(opt; ctx = ctx, n_chains = n_chains, precision = precision)
         opt.σsignal = sum(base.σ) / length(base.σ) * opt.noise

@@ -127,15 +127,32 @@ typedef struct hmcgpu_result {
     double* insample_forecast_mean;
     int32_t* status;
     /* filled by the library */
-    double gpu_ms;        /* device time of the sweeps (CUDA events on the library's stream) */
-    double sweep_kernel_ms; /* device time inside the dominant Gibbs sweep kernel only */
+    double gpu_ms;        /* device time of the whole run: chain init, every sweep launch, per-chunk post-processing (CUDA
+                             events on the library's stream) */
+    double sweep_kernel_ms; /* device time from the start of the first Gibbs sweep launch to the end of the last one (CUDA events
+                             on the task-group streams; the launches of different groups overlap, so this is their enclosing
+                             interval — it leaves out the init kernel and the post-processing after the last sweep) */
     int64_t n_launches;   /* kernels launched for this job */
     int64_t n_sweep_launches; /* launches of the Gibbs sweep kernel among them */
     int64_t h2d_bytes, d2h_bytes;
     int64_t state_steps;  /* sum_w T_w * n_chains * (burnin + nrun) */
+    /* ---- appended in ABI version 200 (older callers that zero-initialise the struct keep working) */
+    double sweep_launch_ms_sum; /* sum over the sweep-kernel launches of each launch's own duration (an event pair around every
+                             launch on its stream); divided by n_sweep_launches = the average launch duration */
+    int32_t sweep_kernel; /* which sweep kernel the plan chose: HMCGPU_KERNEL_* */
+    int32_t n_tasks;      /* warp tasks of that kernel (32 lanes each) */
 } hmcgpu_result;
 
+#define HMCGPU_KERNEL_THREAD 0  /* one thread per chain (gibbs_sweeps_kernel), wide batches, K <= 8 */
+#define HMCGPU_KERNEL_SCAN 1    /* one warp per chain, time-parallel scans (gibbs_scan_kernel), narrow batches */
+#define HMCGPU_KERNEL_LANE 2    /* one lane per state (gibbs_wide_kernel), K = 9..32 */
+#define HMCGPU_KERNEL_PAIR 3    /* two chains per thread (gibbs_pair_kernel), opt-in */
+#define HMCGPU_KERNEL_SEG 4     /* L lanes per chain, each lane a contiguous time segment (gibbs_seg_kernel), mid-width batches */
+
 int hmcgpu_version(void);
+/* "<abi version>;<hash of the CUDA/C sources the library was built from>" — hosts compare the hash with the sources next to
+ * them and refuse (or rebuild) a stale library */
+const char* hmcgpu_build_info(void);
 /* number of CUDA devices visible (0 if none / no driver) */
 int hmcgpu_device_count(void);
 int hmcgpu_ctx_create(int device, hmcgpu_ctx** out);
@@ -144,6 +161,9 @@ void hmcgpu_ctx_destroy(hmcgpu_ctx* ctx);
 const char* hmcgpu_last_error(const hmcgpu_ctx* ctx);
 /* blocks until all work queued by this ctx has finished */
 int hmcgpu_ctx_sync(hmcgpu_ctx* ctx);
+/* Releases the idle device buffers the context keeps for reuse between calls (bounded by HMCGPU_POOL_MAX_GB, default 16 GiB;
+ * they are also released when an allocation on this context fails and at hmcgpu_ctx_destroy). */
+int hmcgpu_ctx_trim(hmcgpu_ctx* ctx);
 
 /* Whole estimation, host buffers in and out (H2D, all sweeps, D2H inside the call). */
 int hmcgpu_estimate(hmcgpu_ctx* ctx, const hmcgpu_problem* p, hmcgpu_result* r);

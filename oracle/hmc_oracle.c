@@ -101,11 +101,17 @@ void orc_make_params(const double* y, int N, int K, int64_t* X, double* mu0, dou
     double mu[MAXK];
     double lo = med - 0.25 * R, hi = med + 0.25 * R;   /* :176 */
     for (int k = 0; k < K; ++k) mu[k] = (K > 1) ? lo + (hi - lo) * ((double)k / (double)(K - 1)) : med;
-    for (int i = 0; i < N; ++i) {                      /* :185-187 findmax -> first maximum */
-        int best = 0; double bv = normpdf(mu[0], sd, y[i]);
+    /* :185-187 findmax of pdf(Normal(mu_k, sd), y_i) -> FIRST maximum.  All states share sd, so the pdf is a decreasing
+     * function of |y - mu_k| and the first maximum of the pdf is the first minimum of that distance.  Comparing distances
+     * instead of exp(-z^2/2) makes the rule independent of the exp implementation and of the last bits of sd: with an odd
+     * window length and an even K the median observation lies exactly between two grid points (a tie in exact arithmetic,
+     * decided by the last bit of the grid arithmetic above), and libm / CUDA / Julia exponentials round such near-ties
+     * differently.  Exact ties go to the lower state, as findmax does. */
+    for (int i = 0; i < N; ++i) {
+        int best = 0; double bv = fabs(y[i] - mu[0]);
         for (int k = 1; k < K; ++k) {
-            double v = normpdf(mu[k], sd, y[i]);
-            if (v > bv) { bv = v; best = k; }
+            double v = fabs(y[i] - mu[k]);
+            if (v < bv) { bv = v; best = k; }
         }
         X[i] = best + 1;
     }

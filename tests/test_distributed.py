@@ -58,6 +58,45 @@ def test_two_rank_sharding_and_gather():
     assert abs(load0 - load1) <= T.max()                          # balanced by sum of window lengths
 
 
+def _worker_skewed(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    import hmc_jl_b200 as H
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T = np.array([1000, 2, 2, 2, 2, 2, 2])          # LPT by sum of T: one shard holds 1 window, the other 6
+        shard = H.shard_windows(T, world)[rank]
+        local = np.stack([np.array([w, T[w]], dtype=np.float64) for w in shard])
+        full = H.gather_window_summaries(local, shard, len(T), dist)
+        dist.barrier()
+        q.put((rank, None if full is None else full.tolist(), len(shard)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_with_skewed_shards():
+    """A shard of short windows holds more rows than ceil(n_windows / world) + 1 (round-1 advisor finding): the padded
+    payload must be sized by the real maximum over the ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_skewed, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, full, n0), (_, _, n1) = res
+    assert sorted((n0, n1)) == [1, 6]
+    full = np.array(full)
+    np.testing.assert_array_equal(full[:, 0], np.arange(7))
+    np.testing.assert_array_equal(full[:, 1], [1000, 2, 2, 2, 2, 2, 2])
+
+
 def test_single_process_gather_is_a_permutation():
     import hmc_jl_b200 as H
     shard = np.array([3, 0, 2, 1])

@@ -227,15 +227,14 @@ def test_gibbs_first_sweeps_follow_the_oracle_chain(H, ctx, oracle):
 def test_chunk_shapes_follow_the_oracle_chain(H, ctx, oracle, K, T):
     """Window lengths that stress the time-parallel kernel's chunking (idle lanes, one step per lane, chunks longer than
     the 32-step path record) and K = 2, 4; the same cases run on the thread-per-chain kernel through the module fixture.
-    (K = 4 uses even window lengths: with an odd length the median observation lies exactly on the boundary between the
-    initial states 2 and 3 of makeParams, src/Hmc.jl:175-187, and its initial label is decided by rounding.)"""
+    Even K with an odd window length is included: the median observation then lies exactly between the initial states K/2
+    and K/2 + 1 of makeParams (src/Hmc.jl:175-187); device and oracle decide it with the same exact distance comparison
+    (ties to the lower state, as findmax)."""
     tr = K3_TRUTH if K == 3 else _truth(K)
     y, _ = synth_hmm(T + 3, seed=9 + K, **tr)
     o = _run(H, ctx, y, [1, 2], [T, T + 1], K=K, n_chains=2, burnin=1, nrun=4, seed=5, horizons=(1, 2), precision=64,
              flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_LOGLIK)
     for w, (s, e) in enumerate(((1, T), (2, T + 1))):
-        if K % 2 == 0 and (e - s + 1) % 2 == 1:
-            continue
         for c in range(2):
             r = oracle.gibbs(y[s - 1:e], K, 1, 4, seed=5, chain=w * 2 + c, horizons=(1, 2), y_future=[y[e], y[e + 1]],
                              flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM)
@@ -399,6 +398,41 @@ def test_plan_run_is_repeatable_and_device_resident(H, ctx):
     np.testing.assert_array_equal(a.summary_mean, b.summary_mean)
     assert a.n_sweep_launches >= 2 and a.gpu_ms > 0 and a.sweep_kernel_ms > 0
     assert a.state_steps == (200 + 150) * 40 * 50
+
+
+def test_warm_started_window_chaining(H, ctx, oracle):
+    """api.sample_and_forecast_all (the intent of sampleAndForecastAll, src/Hmc.jl:584-638) on the device against the oracle run
+    the same way: long burn-in on the first sample, then per end date a short burn-in from the carried state path (new dates
+    by the makeParams rule, :610-620), beta0 = 2 (:347), posterior means per end date and forecasts from those means.  The two
+    chains share the law, not the realisation (Julia's stream is unpinnable; the device re-draws the carried path from
+    X | theta, y): agreement within the Monte-Carlo error of one chain."""
+    y, _ = synth_hmm(262, **K3_TRUTH)
+    dates = list(range(1, len(y) + 1))
+    ends = list(range(240, 246))
+    out = H.sample_and_forecast_all(y, dates, range(1, len(y) + 1), [1, 12], ends, D=3, burnin=150, Nrun=3000, initialburn=1500,
+                                    initialNrun=50, seed=11, ctx=ctx)
+    assert out["events"] == 0 and out["dates"] == ends
+    # the oracle chained the same way (its own final state path is carried: X_final)
+    r = oracle.gibbs(y[:ends[0]], 3, 1500, 50, seed=12, chain=0, horizons=(1,))
+    X = r.X_final
+    two = np.full(3, 2.0)
+    for i, j in enumerate(ends):
+        X0 = oracle.make_params(y[:j], 3)[0]
+        m = min(len(X0), len(X))
+        X0[:m] = X[:m]
+        np.testing.assert_array_equal(X0[m:], H.makeparams_states(y[:j], 3)[m:])       # host copy of the makeParams rule
+        r = oracle.gibbs(y[:j], 3, 150, 3000, seed=12, chain=i + 1, horizons=(1,), X0=X0, beta0=two)
+        X = r.X_final
+        mu, A, pe = r.mu.mean(0), r.A.mean(0), r.pi_end.mean(0)
+        np.testing.assert_allclose(out["μ"][i], mu, atol=0.12)
+        np.testing.assert_allclose(out["σ"][i], r.sigma2.mean(0), rtol=0.12)
+        np.testing.assert_allclose(out["A"][i], A, atol=0.02)
+        np.testing.assert_allclose(out["πb"][i], pe, atol=0.03)
+        for k, h in enumerate((1, 12)):
+            f = float(pe @ np.linalg.matrix_power(A, h) @ mu)
+            assert abs(out["forecasts"][i, 2 * k] - f) < 0.12
+            assert abs(out["forecasts"][i, 2 * k + 1] - (out["forecasts"][i, 2 * k] - y[j + h - 1])) < 1e-12
+    assert np.all(np.diff(out["μ"], axis=1) > 0)
 
 
 def test_full_size_properties_fp32(H, ctx):

@@ -276,6 +276,23 @@ def test_signal_summary_and_dispersion_csv_layout(H, tmp_path):
     np.testing.assert_allclose(float(d[1][7]), np.std([1, 2, 3, 4], ddof=1))
 
 
+def test_insample_and_smoothed_writers_use_the_reference_headers(H, tmp_path):
+    """saveinsampleforecasts (src/Hmc.jl:701-705, header of data/output/official_insample/forecats_insample.csv) and
+    savesmoothresults (:750-758: Date,state_1..state_D)."""
+    table = {"date": ["1970-01-01", "1970-02-01"], "forecast": np.array([6.4768, 6.1]), "forecasterror": np.array([1.18, -0.2]),
+             "current": np.array([6.18, 6.0]), "future": np.array([5.29, 6.3]),
+             "s1": np.array([1e-4, 0.2]), "s2": np.array([0.0489, 0.3]), "s3": np.array([0.951, 0.5])}
+    f = H.saveinsampleforecasts(table, str(tmp_path / "insample" / "forecats_insample.csv"))
+    lines = open(f).read().splitlines()
+    assert lines[0] == "date,forecast,forecasterror,current,future,s1,s2,s3"
+    assert lines[1].split(",")[0] == "1970-01-01" and float(lines[1].split(",")[1]) == 6.4768 and len(lines) == 3
+    rows = [["1970-01-01", 0.25, 0.75], ["1970-02-01", 0.5, 0.5]]
+    g = H.savesmoothresults(rows, str(tmp_path / "smooth"))
+    lines = open(g).read().splitlines()
+    assert os.path.basename(g) == "smoothed_state_probs.csv" and lines[0] == "Date,state_1,state_2"
+    assert lines[2] == "1970-02-01,0.5,0.5"
+
+
 def test_forecastinsample_filtered_host_logic(H, oracle, monkeypatch):
     """Host side of forecastinsample(probabilities="filtered") — draw thinning, layouts, A^h mu weights, chunked filter calls,
     table columns — with the two C-ABI calls it makes replaced by oracle-backed stand-ins (no GPU here); the result is
