@@ -27,7 +27,8 @@ def _sweep_kernel_choice(request, monkeypatch):
 
 
 def test_native_library_is_loaded(H, ctx):
-    assert os.path.samefile(H.lib_path(), os.path.join(os.path.dirname(H.__file__), "lib", "libhmcgpu.so"))
+    tag = os.environ.get("HMC_TAG")            # A/B runs of a side library (scripts/ab_lib.sh) load lib/libhmcgpu_<tag>.so
+    assert os.path.samefile(H.lib_path(), os.path.join(os.path.dirname(H.__file__), "lib", f"libhmcgpu_{tag}.so" if tag else "libhmcgpu.so"))
     assert H.load().hmcgpu_device_count() >= 1
 
 
