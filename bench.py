@@ -200,9 +200,92 @@ def cpu_baseline(y, ws, we, target_seconds=15.0, threads=0, burnin=1000, nrun=10
     _, used = O.gibbs_batch(jobs(burnin, nrun, chains), n_threads=cores)
     dt = time.perf_counter() - t0
     steps = int(T.sum()) * sweeps * chains
-    return {"value": steps / dt, "unit": UNIT, "cores": used, "kind": "port",
+    return {"value": steps / dt, "unit": UNIT, "cores": used, "kind": "port", "chains_per_window": chains, "sweeps": sweeps,
             "sample": f"all {len(T)} windows (T=101..600) x {chains} chain(s), {burnin}+{nrun} sweeps, h=1..12 forecasts; "
                       f"{steps:.3e} state-steps in {dt:.1f}s; fp64 C port of src/Hmc.jl on {used} threads (Julia absent)"}, dt, steps
+
+
+ALG_SLOTS_PER_STATE_STEP = 65.0     # SURVEY section 8d at K = 3: ~60 FP32/INT issue slots + 5 MUFU per state-step
+
+
+def headline_profile():
+    """profiles/r2_headline_profile.json (written by scripts/profile_headline.sh from an ncu --set full capture of the headline
+    kernel): warp-instructions per warp-step and DRAM bytes per state-step of the kernel sources identified by `hot_source_hash`.
+    None when the file is missing or was taken from other kernel sources than the ones being run."""
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r2_headline_profile.json")))
+        from hmc_jl_b200 import build as _b
+        prof["matches_sources"] = prof.get("hot_source_hash") == _b.hot_source_hash()
+        return prof
+    except Exception:
+        return None
+
+
+def timed_plan(H, ctx, spec, steps, warmup, dist, local):
+    """Device-resident timing of one problem: warm-up runs, then `steps` runs of hmcgpu_plan_run between barriers; device
+    time from the library's CUDA events (max over ranks), state-steps summed over ranks."""
+    plan = H.Plan(ctx, spec)
+    for _ in range(warmup):
+        plan.run()
+    barrier_sync(dist, local)
+    t0 = time.perf_counter()
+    acc = dict(dev_ms=0.0, sweep_ms=0.0, launch_ms_sum=0.0, launches=0, sweep_launches=0)
+    r = None
+    for _ in range(steps):
+        plan.run()
+        r = H.binding.Result()                      # timing fields only (no output pointers -> no D2H)
+        ctx._check(ctx.L.hmcgpu_plan_fetch(plan.h, ctypes.byref(r)))
+        acc["dev_ms"] += r.gpu_ms; acc["sweep_ms"] += r.sweep_kernel_ms; acc["launch_ms_sum"] += r.sweep_launch_ms_sum
+        acc["launches"] += r.n_launches; acc["sweep_launches"] += r.n_sweep_launches
+    barrier_sync(dist, local)
+    acc["wall_s"] = time.perf_counter() - t0
+    acc["steps_per_run"] = int(r.state_steps)
+    acc["kernel"] = int(r.sweep_kernel); acc["n_tasks"] = int(r.n_tasks)
+    acc["dev_s"] = all_max(dist, local, acc["dev_ms"] / 1e3)
+    acc["total_steps"] = all_sum(dist, local, float(r.state_steps) * steps)
+    acc["value"] = acc["total_steps"] / acc["dev_s"]
+    acc["plan"] = plan
+    return acc
+
+
+def timed_e2e(H, ctx, spec, steps, shard, n_windows, dist, local, total_steps):
+    """The same through the public call with HOST buffers (hmcgpu_estimate: upload, all sweeps, download) plus the final gather
+    of the per-window summaries on rank 0; wall clock between barriers, max over ranks."""
+    dev = f"cuda:{local}" if dist is not None else None
+    o = H.estimate(ctx, spec)                        # warm the allocator path and the gather's lazy NCCL connections once
+    H.gather_window_summaries(np.concatenate([o.summary_mean, o.summary_var], axis=1), shard, n_windows, dist, device=dev)
+    barrier_sync(dist, local)
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    t_est = t_gat = 0.0
+    for _ in range(steps):
+        ta = time.perf_counter()
+        o = H.estimate(ctx, spec)
+        tb = time.perf_counter()
+        h2d += o.h2d_bytes; d2h += o.d2h_bytes
+        H.gather_window_summaries(np.concatenate([o.summary_mean, o.summary_var], axis=1), shard, n_windows, dist, device=dev)
+        t_est += tb - ta; t_gat += time.perf_counter() - tb
+    barrier_sync(dist, local)
+    e2e_s = all_max(dist, local, time.perf_counter() - t0)
+    return {"value": total_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps,
+            "ms_per_step": 1e3 * e2e_s / steps, "estimate_ms": 1e3 * t_est / steps, "gather_ms": 1e3 * t_gat / steps, "device_ms": o.gpu_ms}
+
+
+def wide_series(n_ser, length, Kw=3, n_gen=2048):
+    """C4 / C5 inputs: independent series from the truth parameters, numpy default_rng(1234); n_gen distinct
+    series tiled to n_ser (device work does not depend on the values being distinct)."""
+    truth = TRUTH if Kw == 3 else dict(A=np.full((Kw, Kw), 0.1 / (Kw - 1)) + np.eye(Kw) * (0.9 - 0.1 / (Kw - 1)),
+                                       mu=2.0 * np.arange(Kw), sigma2=np.full(Kw, 0.5))
+    n_gen = min(n_ser, n_gen)
+    L = length + 12
+    rng = np.random.default_rng(1234)
+    X = np.zeros((n_gen, L), dtype=np.int64)
+    u = rng.random((n_gen, L))
+    cum = np.cumsum(truth["A"], axis=1)
+    for t in range(1, L):
+        X[:, t] = np.minimum((u[:, t, None] > cum[X[:, t - 1]]).sum(1), Kw - 1)
+    y = truth["mu"][X] + np.sqrt(truth["sigma2"][X]) * rng.standard_normal((n_gen, L))
+    return np.tile(y, ((n_ser + n_gen - 1) // n_gen, 1))[:n_ser]
 
 
 def run_reference(args):
@@ -225,8 +308,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / len(per), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, args.gpus) | {"note": "reference arm = CPU port of the reference on host cores; "
-                                                                   "Julia is not installed so the reference itself cannot run"},
+            "config": workload_config(args, 1) | {"chains_per_window": base["chains_per_window"], "sharding": "none (host threads over windows x chains)",
+                                                  "note": "reference arm = CPU port of the reference on host cores (Julia is not installed, so "
+                                                          "the reference itself cannot run); a bounded sample of the workload: every window, "
+                                                          "the workload's sweeps, as many chains per window as fit the time budget — the "
+                                                          "metric is a rate, so it does not depend on the number of chains"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit_line(line)
@@ -264,9 +350,7 @@ def main():
     ap.add_argument("--nrun", type=int, default=1000)
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--traffic", type=float, default=2.51e9,
-                    help="dram__bytes_read+write per sweep-kernel launch from the ncu --set full capture "
-                         "(profiles/r1_gibbs_sweeps_ncu_full.txt: one task group of 1000 warp tasks x 16 sweeps = 1.79e8 state-steps)")
+    ap.add_argument("--no-side-records", action="store_true", help="skip the mid-width / fp64 / C4 sub-records of the N=1 line")
     args = ap.parse_args()
     capture_stdout()
     if args.impl == "reference":
@@ -307,111 +391,111 @@ def main():
         sig_kw = dict(is_signal=mask, kappa=1.0, alpha=np.full(K, 2.0), nu=np.full(K, 2.0), pi_row_back=sig_len)
     else:                                           # c4 / c5: wide batch of independent series
         Kw = args.states if args.workload == "c5" else 3
-        truth = TRUTH if Kw == 3 else dict(A=np.full((Kw, Kw), 0.1 / (Kw - 1)) + np.eye(Kw) * (0.9 - 0.1 / (Kw - 1)),
-                                           mu=2.0 * np.arange(Kw), sigma2=np.full(Kw, 0.5))
         n_ser = (args.chains if args.chains != 256 else 65536) * world
-        n_gen = min(n_ser, 2048)                    # distinct series generated; tiled to n_ser (device work is unaffected)
-        L = args.length + 12
-        rng = np.random.default_rng(1234)
-        X = np.zeros((n_gen, L), dtype=np.int64)
-        u = rng.random((n_gen, L))
-        cum = np.cumsum(truth["A"], axis=1)
-        for t in range(1, L):
-            X[:, t] = np.minimum((u[:, t, None] > cum[X[:, t - 1]]).sum(1), Kw - 1)
-        y = truth["mu"][X] + np.sqrt(truth["sigma2"][X]) * rng.standard_normal((n_gen, L))
-        y = np.tile(y, ((n_ser + n_gen - 1) // n_gen, 1))[:n_ser]
+        y = wide_series(n_ser, args.length, Kw)
         ws_all, we_all = np.ones(n_ser, dtype=np.int32), np.full(n_ser, args.length, dtype=np.int32)
         win_series = np.arange(n_ser, dtype=np.int32)
         n_chains = 1
         args.K_run = Kw
     args.chains_run = int(len(ws_all) * n_chains)      # chains in the whole job
+    Krun = getattr(args, "K_run", K)
     shard = H.shard_windows(we_all - ws_all + 1, world)[rank]
     ws, we = ws_all[shard], we_all[shard]
-    spec = H.ProblemSpec(y, ws, we, K=getattr(args, "K_run", K), n_chains=n_chains, burnin=args.burnin, nrun=args.nrun, seed=1234, horizons=HORIZONS,
-                         precision=args.precision, flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY, win_id=shard,
-                         win_series=None if win_series is None else win_series[shard],
-                         win_init_series=np.zeros(len(shard), dtype=np.int32) if sig_kw else None, **sig_kw)
+
+    def make_spec(chains, precision=args.precision, flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY):
+        return H.ProblemSpec(y, ws, we, K=Krun, n_chains=chains, burnin=args.burnin, nrun=args.nrun, seed=1234, horizons=HORIZONS,
+                             precision=precision, flags=flags, win_id=shard,
+                             win_series=None if win_series is None else win_series[shard],
+                             win_init_series=np.zeros(len(shard), dtype=np.int32) if sig_kw else None, **sig_kw)
+
+    spec = make_spec(n_chains)
     ctx = H.Context(local)
-    plan = H.Plan(ctx, spec)
-    for _ in range(args.warmup):
-        plan.run()
     sampler = ClockSampler(local)
-    barrier_sync(dist, local)
     sampler.start()
-    t0 = time.perf_counter()
-    dev_ms = sweep_ms = 0.0
-    launches = sweep_launches = 0
-    for _ in range(args.steps):
-        plan.run()
-        r = H.binding.Result()                      # timing fields only (no output pointers -> no D2H)
-        ctx._check(ctx.L.hmcgpu_plan_fetch(plan.h, ctypes.byref(r)))
-        dev_ms += r.gpu_ms; sweep_ms += r.sweep_kernel_ms
-        launches += r.n_launches; sweep_launches += r.n_sweep_launches
-        steps_per_run = r.state_steps
-    barrier_sync(dist, local)
-    wall = time.perf_counter() - t0
+    m = timed_plan(H, ctx, spec, args.steps, args.warmup, dist, local)
     clocks = sampler.stop()
+    plan = m.pop("plan")
     res = plan.fetch()
     plan.close()
-    dev_s = all_max(dist, local, dev_ms / 1e3)
-    total_steps = all_sum(dist, local, float(steps_per_run) * args.steps)
-    value = total_steps / dev_s
+    value, dev_s, total_steps, steps_per_run = m["value"], m["dev_s"], m["total_steps"], m["steps_per_run"]
+    sweep_ms, dev_ms, sweep_launches = m["sweep_ms"], m["dev_ms"], m["sweep_launches"]
+    kernel_name = H.binding.KERNEL_NAMES.get(m["kernel"], str(m["kernel"]))
 
     # ---- end to end through the public call with host buffers
-    o = H.estimate(ctx, spec)                        # warm the allocator path and the gather's lazy NCCL connections once
-    H.gather_window_summaries(np.concatenate([o.summary_mean, o.summary_var], axis=1), shard, len(we_all), dist,
-                              device=f"cuda:{local}" if dist is not None else None)
-    barrier_sync(dist, local)
-    t0 = time.perf_counter()
-    h2d = d2h = 0
-    t_est = t_gat = 0.0
-    for _ in range(args.steps):
-        ta = time.perf_counter()
-        o = H.estimate(ctx, spec)
-        tb = time.perf_counter()
-        h2d += o.h2d_bytes; d2h += o.d2h_bytes
-        # final gather of per-window summaries on rank 0 (the only cross-rank step)
-        H.gather_window_summaries(np.concatenate([o.summary_mean, o.summary_var], axis=1), shard, len(we_all), dist,
-                                  device=f"cuda:{local}" if dist is not None else None)
-        t_est += tb - ta; t_gat += time.perf_counter() - tb
-    print(f"[bench rank {rank}] e2e per step: estimate {1e3 * t_est / args.steps:.1f} ms (device {o.gpu_ms:.1f} ms), "
-          f"gather {1e3 * t_gat / args.steps:.1f} ms", file=sys.stderr, flush=True)
-    barrier_sync(dist, local)
-    e2e_s = all_max(dist, local, time.perf_counter() - t0)
-    e2e_value = total_steps / e2e_s
+    e2e = timed_e2e(H, ctx, spec, args.steps, shard, len(we_all), dist, local, total_steps)
+    print(f"[bench rank {rank}] e2e per step: estimate {e2e['estimate_ms']:.1f} ms (device {e2e['device_ms']:.1f} ms), "
+          f"gather {e2e['gather_ms']:.1f} ms", file=sys.stderr, flush=True)
 
-    # ---- roofline of the dominant kernel (gibbs_sweeps_kernel): algorithmic bytes = (2K+2)*b per state-step
+    # ---- rooflines of the dominant kernel.  north_star: "the slower of HBM traffic and FP32/MUFU issue".  The sweep kernel is
+    # bound by instruction issue, so `roofline` is the issue roofline; the HBM fractions (algorithmic bytes, and the DRAM bytes ncu
+    # counted) stand beside it.  Instructions per warp-step and DRAM bytes per state-step come from the ncu capture recorded in
+    # profiles/r2_headline_profile.json; they are only used when that capture was taken from the kernel sources being run.
     bpe = 4 if args.precision == 32 else 8
-    alg_bytes_per_step = (2 * getattr(args, "K_run", K) + 2) * bpe
+    alg_bytes_per_step = (2 * Krun + 2) * bpe
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes_per_step * float(steps_per_run) * args.steps / (sweep_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": args.traffic, "kernel": "gibbs_sweeps_kernel", "peak_source": "MEASURED_PEAKS.json (measured copy)" if peaks else "fallback 6650",
-                "algorithmic_bytes_per_state_step": alg_bytes_per_step, "launches_timed": sweep_launches,
-                "avg_launch_ms": sweep_ms / max(1, sweep_launches),
-                "sweep_kernel_share_of_step": sweep_ms / dev_ms,
-                "note": "launches of the 4 task groups overlap on separate streams, so `achieved` uses the enclosing device time "
-                        "of all sweep launches; real DRAM traffic is 14-21 B per state-step (< 32 algorithmic: y and part of pif "
-                        "hit L1/L2) and the kernel is FP32/INT issue-bound (DESIGN.md section 6)"}
-
-    # ---- second roofline (north_star: the slower of HBM traffic and FP32/MUFU issue): warp-instruction issue rate.
-    # instructions per warp-step come from the ncu capture of the same kernel (smsp__inst_executed.sum / warp-steps,
-    # profiles/r1_gibbs_sweeps_ncu_full_alltasks.txt); the peak is 4 schedulers x 1 warp-instr/clk x SMs at the SM clock
-    # sampled under load during this run.
-    wi = {3: 99.4}.get(getattr(args, "K_run", K)) if args.precision == 32 and args.workload == "c2" and len(ws) * n_chains > 16000 else None   # thread-per-chain kernel only
-    issue = None
-    if wi is not None and clocks.get("sm_mhz"):
+    peak_src = "MEASURED_PEAKS.json (measured copy)" if peaks else "fallback 6650 (B200_PROFILING.md)"
+    sweep_s = sweep_ms / 1e3
+    rate = float(steps_per_run) * args.steps / sweep_s          # state-steps/s of this rank inside the sweeps
+    hbm_alg = {"achieved": alg_bytes_per_step * rate / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes_per_step * rate / 1e9 / peak,
+               "bytes_per_state_step": alg_bytes_per_step, "peak_source": peak_src}
+    prof = headline_profile() if (args.workload == "c2" and args.precision == 32 and m["kernel"] == 0) else None
+    usable = bool(prof and prof.get("matches_sources"))
+    hbm_dram = None
+    traffic = None
+    if usable:
+        bps = float(prof["dram_bytes_per_state_step"])
+        hbm_dram = {"achieved": bps * rate / 1e9, "peak": peak, "unit": "GB/s", "frac": bps * rate / 1e9 / peak, "bytes_per_state_step": bps,
+                    "source": prof.get("source")}
+        traffic = bps * float(steps_per_run) * args.steps / max(1, sweep_launches)      # DRAM bytes per sweep-kernel launch
+    common = {"kernel": kernel_name, "launches_timed": sweep_launches, "avg_launch_ms": m["launch_ms_sum"] / max(1, sweep_launches),
+              "sweep_kernel_share_of_step": sweep_ms / dev_ms, "traffic": traffic, "hbm_algorithmic": hbm_alg, "hbm_dram": hbm_dram,
+              "profile": None if prof is None else {k: prof.get(k) for k in ("source", "hot_source_hash", "matches_sources")},
+              "note": "launches of the task groups overlap on separate streams: `achieved` uses the enclosing device time of all sweep "
+                      "launches, avg_launch_ms is each launch's own event pair; traffic = ncu DRAM bytes per state-step x the "
+                      "state-steps of an average launch"}
+    if usable and clocks.get("sm_mhz"):
         sms = torch.cuda.get_device_properties(local).multi_processor_count
-        issue = issue_roofline(wi, float(steps_per_run) * args.steps, sweep_ms / 1e3, sms, clocks["sm_mhz"])
-    # ---- the reference's own shape of the same job (BASELINE configs[1] read literally): ONE chain per end date.  Such a
-    # narrow batch runs on the time-parallel warp-per-chain kernel; reported next to the headline, not instead of it.
+        iss = issue_roofline(float(prof["warp_inst_per_warp_step"]), float(steps_per_run) * args.steps, sweep_s, sms, clocks["sm_mhz"])
+        iss["algorithmic_frac"] = ALG_SLOTS_PER_STATE_STEP * (rate / 32.0) / (iss["peak"] * 1e9)
+        iss["algorithmic_slots_per_state_step"] = ALG_SLOTS_PER_STATE_STEP
+        roofline = iss | common
+    else:
+        # no ncu capture of these kernel sources (or another kernel / workload): only the algorithmic HBM roofline is known
+        roofline = {"bound": "hbm", "achieved": hbm_alg["achieved"], "peak": peak, "unit": "GB/s", "frac": hbm_alg["frac"]} | common
+
+    extra = {}
+    if args.workload == "c2":
+        # ---- strong scaling: the FIXED job (500 end dates x args.chains chains) sharded over the ranks by end date, next to the
+        # weak-scaling headline (per-GPU work fixed).  Efficiency against the whole job on ONE GPU (rank 0) in the same run.
+        if world > 1:
+            sspec = make_spec(args.chains)
+            sm_ = timed_plan(H, ctx, sspec, args.steps, 1, dist, local)
+            sm_.pop("plan").close()
+            se2e = timed_e2e(H, ctx, sspec, args.steps, shard, len(we_all), dist, local, sm_["total_steps"])
+            one = None
+            if rank == 0:
+                full = H.ProblemSpec(y, ws_all, we_all, K=K, n_chains=args.chains, burnin=args.burnin, nrun=args.nrun, seed=1234, horizons=HORIZONS,
+                                     precision=args.precision, flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY)
+                one = timed_plan(H, ctx, full, 2, 1, None, local)
+                one.pop("plan").close()
+            barrier_sync(dist, local)
+            n1 = all_max(dist, local, one["value"] if one else 0.0)
+            extra["strong"] = {"workload": f"the fixed job: 500 end dates x {args.chains} chains, end dates sharded over {world} ranks",
+                               "value": sm_["value"], "unit": UNIT, "ms_per_step": 1e3 * sm_["dev_s"] / args.steps,
+                               "e2e": se2e["value"], "e2e_ms_per_step": se2e["ms_per_step"], "kernel": H.binding.KERNEL_NAMES.get(sm_["kernel"]),
+                               "warp_tasks_per_gpu": sm_["n_tasks"], "one_gpu_same_run": n1, "efficiency": sm_["value"] / (world * n1) if n1 else None}
+        else:
+            extra["strong"] = {"workload": f"the fixed job: 500 end dates x {args.chains} chains on one rank", "value": value, "unit": UNIT,
+                               "e2e": e2e["value"], "efficiency": 1.0}
     literal = None
     if args.workload == "c2" and world == 1:
+        # ---- the reference's own shape of the same job (BASELINE configs[1] read literally): ONE chain per end date (time-parallel
+        # kernel), and the mid-width shapes in between: one GPU's share of the fixed job at 8 / 4 / 2 GPUs
         spec1 = H.ProblemSpec(y, ws, we, K=K, n_chains=1, burnin=args.burnin, nrun=args.nrun, seed=1234, horizons=HORIZONS,
                               precision=args.precision, flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY)
         H.estimate(ctx, spec1)
@@ -421,7 +505,46 @@ def main():
         dt1 = (time.perf_counter() - t0) / 3
         literal = {"workload": "500 end dates x ONE chain (the reference's configuration), same sweeps and outputs",
                    "value": float(o1.state_steps) / dt1, "unit": UNIT, "ms_per_pass_e2e": 1e3 * dt1, "device_ms": o1.gpu_ms,
-                   "kernel": "gibbs_scan_kernel (one warp per chain, time-parallel)"}
+                   "kernel": H.binding.KERNEL_NAMES.get(o1.sweep_kernel)}
+        if not args.no_side_records:
+            widths = []
+            for c in (32, 64, 128):
+                if c >= args.chains:
+                    continue
+                wm = timed_plan(H, ctx, make_spec(c), 2, 1, None, local)
+                wm.pop("plan").close()
+                widths.append({"chains_per_window": c, "chains": 500 * c, "value": wm["value"], "ms_per_step": 1e3 * wm["dev_s"] / 2,
+                               "kernel": H.binding.KERNEL_NAMES.get(wm["kernel"]), "warp_tasks": wm["n_tasks"]})
+            extra["mid_width"] = widths
+            # ---- the reference computes in fp64 throughout (src/Hmc.jl:231 ff.): the same job in fp64
+            if args.precision == 32:
+                s64 = make_spec(n_chains, precision=64)
+                m64 = timed_plan(H, ctx, s64, 2, 1, None, local)
+                m64.pop("plan").close()
+                e64 = timed_e2e(H, ctx, s64, 2, shard, len(we_all), None, local, m64["total_steps"])
+                a64 = (2 * K + 2) * 8 * (m64["steps_per_run"] * 2 / (m64["sweep_ms"] / 1e3)) / 1e9
+                extra["fp64"] = {"workload": "the same C2 job, every array and operation in fp64", "dtype": "f64", "value": m64["value"], "unit": UNIT,
+                                 "ms_per_step": 1e3 * m64["dev_s"] / 2, "e2e": e64["value"],
+                                 "roofline": {"bound": "hbm", "achieved": a64, "peak": peak, "unit": "GB/s", "frac": a64 / peak,
+                                              "bytes_per_state_step": (2 * K + 2) * 8, "traffic": None}}
+            # ---- C4 (BASELINE configs[3]): 65 536 independent series of T = 2000, K = 3, 10 + 100 sweeps, fp32 and fp64
+            yc4 = wide_series(65536, 2000)
+            c4 = {}
+            for prec in (32, 64):
+                sc4 = H.ProblemSpec(yc4, np.ones(65536, dtype=np.int32), np.full(65536, 2000, dtype=np.int32), K=3, n_chains=1, burnin=10, nrun=100,
+                                    seed=1234, horizons=HORIZONS, precision=prec, flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY,
+                                    win_series=np.arange(65536, dtype=np.int32))
+                mc = timed_plan(H, ctx, sc4, 2, 1, None, local)
+                mc.pop("plan").close()
+                ec = timed_e2e(H, ctx, sc4, 2, np.arange(65536), 65536, None, local, mc["total_steps"])
+                ab = 8 * (prec // 8) * (mc["steps_per_run"] * 2 / (mc["sweep_ms"] / 1e3)) / 1e9
+                c4[f"fp{prec}"] = {"value": mc["value"], "unit": UNIT, "ms_per_step": 1e3 * mc["dev_s"] / 2, "e2e": ec["value"],
+                                   "h2d_bytes_per_step": ec["h2d_bytes_per_step"], "kernel": H.binding.KERNEL_NAMES.get(mc["kernel"]),
+                                   "roofline": {"bound": "hbm", "achieved": ab, "peak": peak, "unit": "GB/s", "frac": ab / peak,
+                                                "bytes_per_state_step": 8 * (prec // 8), "traffic": None,
+                                                "note": "every chain streams its own series: DRAM bytes = algorithmic bytes"}}
+            del yc4
+            extra["c4"] = {"workload": "C4: 65 536 independent series of T=2000, K=3, one chain each, 10+100 sweeps, h=1..12, summaries"} | c4
     if rank == 0:
         cb = None
         if not args.no_cpu_baseline and world == 1 and args.workload == "c2":
@@ -429,12 +552,11 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic", "config": workload_config(args, world),
-                "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-                        "ms_per_step": 1e3 * e2e_s / args.steps},
-                "gpu_launches": int(launches), "roofline": roofline, "roofline_issue": issue, "one_chain_per_end_date": literal, "cpu_baseline": cb,
-                "check": {"mu_mean_longest_window": res.summary_mean[int(np.argmax(we - ws))][0:getattr(args, "K_run", K)].tolist(),
-                          "events": int(res.events)}}
+                "wall_ms_per_step": 1e3 * m["wall_s"] / args.steps, "clocks": clocks,
+                "e2e": {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "ms_per_step")},
+                "gpu_launches": int(m["launches"]), "roofline": roofline, "one_chain_per_end_date": literal, "cpu_baseline": cb,
+                "check": {"mu_mean_longest_window": res.summary_mean[int(np.argmax(we - ws))][0:Krun].tolist(),
+                          "events": int(res.events)}} | extra
         emit_line(line)
     if dist is not None:
         dist.barrier()

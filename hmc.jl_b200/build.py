@@ -43,6 +43,20 @@ def source_hash():
     return h.hexdigest()[:16]
 
 
+HOT_SOURCES = ("gibbs_kernel.cuh", "hmm_device.cuh", "rng.cuh")
+
+
+def hot_source_hash():
+    """sha256 (16 hex digits) over the sources of the headline sweep kernel and the compiler flags: what an ncu capture of that
+    kernel is a capture OF (profiles/r2_headline_profile.json carries it; bench.py ignores a capture of other sources)."""
+    h = hashlib.sha256()
+    for f in HOT_SOURCES:
+        h.update(f.encode() + b"\0")
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    h.update(" ".join(FLAGS + DEFS).encode())
+    return h.hexdigest()[:16]
+
+
 def built_hash(lib):
     """The hash a built library carries, read without loading it into this process (the sidecar build() writes)."""
     try:

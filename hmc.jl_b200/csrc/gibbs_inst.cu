@@ -4,6 +4,7 @@
 #include "gibbs_kernel.cuh"
 #if HMC_K <= 4
 #include "gibbs_scan_kernel.cuh"
+#include "gibbs_seg_kernel.cuh"
 #endif
 #ifdef HMC_WITH_PAIR
 #include "gibbs_pair_kernel.cuh"
@@ -108,6 +109,28 @@ template <typename R, int K> cudaError_t launch_gibbs_scan(const GibbsLaunch& cf
     return go(gibbs_scan_kernel<R, K, false>);
 }
 template cudaError_t launch_gibbs_scan<HMC_R, HMC_K>(const GibbsLaunch&, const GibbsArgs&, cudaStream_t);
+
+// mid-width batches: `lanes` lanes per chain, one time segment per lane (gibbs_seg_kernel.cuh); a task is 32 / lanes chains
+template <typename R, int K> cudaError_t launch_gibbs_seg(const GibbsLaunch& cfg, const GibbsArgs& a, int lanes, int threads, cudaStream_t st) {
+    if (threads != 128 && threads != kSegThreads) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)((a.n_tasks + threads / 32 - 1) / (threads / 32));
+    const size_t smem = seg_smem_bytes<R, K>(cfg.n_h, threads);
+    const bool ll = cfg.flags & 16u;
+    auto go = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, threads, smem, st>>>(a);
+        return cudaGetLastError();
+    };
+    switch (lanes) {
+        case 2: return ll ? go(gibbs_seg_kernel<R, K, 2, true>) : go(gibbs_seg_kernel<R, K, 2, false>);
+        case 4: return ll ? go(gibbs_seg_kernel<R, K, 4, true>) : go(gibbs_seg_kernel<R, K, 4, false>);
+        default: return cudaErrorInvalidValue;
+    }
+}
+template cudaError_t launch_gibbs_seg<HMC_R, HMC_K>(const GibbsLaunch&, const GibbsArgs&, int, int, cudaStream_t);
 #endif
 
 }  // namespace hmc

@@ -22,10 +22,6 @@ namespace hmc {
 #define HMC_SEL_LDS 1      // 1: A[:,x] and the counter increment come from a per-thread shared-memory table; 0: register selects
 #endif
 
-#ifndef HMC_LAT
-#define HMC_LAT 0          // 1: latency-optimised fp32 passes (K <= 4, plain sweep): lagged normaliser in the filter, speculative
-#endif                     //    per-entering-state thresholds in the sampler (no shared-memory selection table)
-
 #ifndef HMC_BACK_INLINE
 #define HMC_BACK_INLINE 0  // experiment: backward pass inlined into the sweep loop (no R2UR descriptor moves; shares the kernel's register allocation)
 #endif
@@ -127,7 +123,7 @@ template <typename R, int K, bool SIG> constexpr int gibbs_min_blocks() {
     return K > 6 ? 2 : (K > 4 ? HMC_MINBLOCKS_K56 : (sizeof(R) == 8 ? HMC_MINBLOCKS_F64 : (SIG ? HMC_MINBLOCKS_SIG : kGibbsMinBlocks)));
 }
 // cp.async ring depth: the ring of a warp is stages x 4 rows x K x 32 lanes
-template <typename R, int K> constexpr int gibbs_ring_stages() { return K <= 4 ? kRing : (sizeof(R) == 4 ? 3 : 2); }
+template <typename R, int K> __host__ __device__ constexpr int gibbs_ring_stages() { return K <= 4 ? kRing : (sizeof(R) == 4 ? 3 : 2); }
 
 struct GibbsArgs {
     int n_slots;                 // chains incl. padding, multiple of 32
@@ -180,6 +176,10 @@ struct GibbsArgs {
     const int* totM;             // [n_slots] number of signals in the window
     double kappa;
     int pi_back;                 // the pi_end field of a draw is the smoothed marginal pib[N - pi_back, :] (:893); 0 = last row
+    // ---- segment kernel (gibbs_seg_kernel.cuh)
+    int seg_warm;                // warm-up time steps in front of a segment
+    int seg_barriers;            // block-wide phase barriers per sweep (0, 1: before the filter, 2: also before the sampler)
+    unsigned long long* diag;    // [2] chain-sweeps whose warm-up failed the verification (exact products used instead); groups of 4 steps walked speculatively, summed over chain-sweeps; may be NULL
 };
 
 // Transition counts n_ij of the sampled path, packed: one word per origin state, one bit-field per destination.
@@ -240,7 +240,7 @@ struct GibbsWarp {
         R c;                      // shift of the sufficient statistics
         int rank[K];              // position of each chain label in increasing-mu order
         int T, Tw, off;           // window length, warp length, right-alignment offset (row j <-> t = j - off)
-        bool ragged;              // some lane of the warp has a shorter window (or is padding): steps are guarded
+        int rag_rows;             // rows [0, rag_rows) of the warp's frame lie before the window of some lane (shorter window or padding lane): steps there are guarded per lane; 0 = all windows equal
         long long yld;
         const R* y0;              // row j -> y0[j*yld]
         R* pi0;                   // row j, state k -> pi0[((j + pad) >> 2)*4*K*32 + k*128 + ((j + pad) & 3)]  (lane*4 folded in)
@@ -303,6 +303,11 @@ struct GibbsWarp {
 #pragma unroll
         for (int i = 0; i < K - 1; ++i)
             if (obs && is_state(lt, i)) { b.Sd[i] += d; b.Qd[i] += dd; }
+        select_later(b, ch, lt, pt);
+    }
+    // what the next (earlier) step needs once this step's state (one-hot in lt) is known: column x of A, the packed-counter
+    // increment of destination x, and pif[t, x] (the quirk-Q5 gate)
+    static __device__ __forceinline__ void select_later(Back& b, const Chain& ch, const bool (&lt)[K - 1], const R (&pt)[K]) {
 #if HMC_SEL_LDS
         // the entry's 32-bit shared-window address is selected among K per-thread constants (K-1 selects) and read with
         // ld.shared: stepping a generic pointer cost 5 integer instructions per step (offset chain + window base add)
@@ -423,8 +428,9 @@ struct GibbsWarp {
         }
         R buf[4][K];                                                 // the 4 rows of the current tile (stored together)
         // one step at row j = position u of its tile; yo / so: offsets (in rows) of y and of the z-scale from yp / sp
-        auto step = [&](int j, int u, int yo, R ypre, bool preloaded) {
-            if (!ragged || j >= ch.off) {
+        // (guard: a std::integral_constant — the per-lane window test is compiled out for the rows where every lane is inside its window)
+        auto step = [&](auto guard, int j, int u, int yo, R ypre, bool preloaded) {
+            if (!decltype(guard)::value || j >= ch.off) {
                 const R yt = preloaded ? ypre : ld_ro(yp + yo * yld);   // STREAM: loaded one iteration ahead by the caller
                 R sw = R(1);                                         // signals: sd x (1+kappa) (:382) <=> z scaled by 1/(1+kappa)
                 if constexpr (SIG) sw = ld_ro(sp + yo * ch.sld);
@@ -505,13 +511,15 @@ struct GibbsWarp {
         };
         const int pad = (4 - (ch.Tw & 3)) & 3;
         int j = 0;
-        {   // tile 0: its first `pad` positions are padding (rows are right-aligned to a multiple of 4)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int s = 0; s < K; ++s) buf[u][s] = R(0);
+        if (pad != 0) {   // tile 0: its first `pad` positions are padding (rows are right-aligned to a multiple of 4); a frame of whole tiles starts in the loops below
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                for (int s = 0; s < K; ++s) buf[u][s] = R(0);
                 const int jj = u - pad;
-                if (jj >= 0 && jj < ch.Tw) step(jj, u, jj, R(0), false);
+                if (jj >= 0 && jj < ch.Tw) step(std::integral_constant<bool, RAGGED>{}, jj, u, jj, R(0), false);
             }
             store_tile();
             j = (4 - pad < ch.Tw) ? 4 - pad : ch.Tw;
@@ -526,21 +534,26 @@ struct GibbsWarp {
             for (int u = 0; u < 4; ++u) yn[u] = (jj + u < ch.Tw && (!ragged || jj + u >= ch.off)) ? ld_ro(p + u * yld) : R(0);
         };
         if constexpr (STREAM) load4(j, yp);
-        for (; j + 3 < ch.Tw; j += 4, yp += 4 * yld, pip += 4 * K * 32) {
-            if constexpr (STREAM) {
-                if (j + kYAhead + 3 < ch.Tw && (!ragged || j + kYAhead >= ch.off)) {   // rows of this lane's own window only
+        // the tiles whose rows lie before the window of some lane run the guarded step, the rest of the frame the plain one
+        auto run_tiles = [&](auto guard, const int until) {
+            for (; j + 3 < ch.Tw && j < until; j += 4, yp += 4 * yld, pip += 4 * K * 32) {
+                if constexpr (STREAM) {
+                    if (j + kYAhead + 3 < ch.Tw && (!ragged || j + kYAhead >= ch.off)) {   // rows of this lane's own window only
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) prefetch_l1(yp + (kYAhead + u) * yld);
+                        for (int u = 0; u < 4; ++u) prefetch_l1(yp + (kYAhead + u) * yld);
+                    }
+                    const R c0 = yn[0], c1 = yn[1], c2v = yn[2], c3 = yn[3];
+                    load4(j + 4, yp + 4 * yld);
+                    step(guard, j, 0, 0, c0, true); step(guard, j + 1, 1, 1, c1, true); step(guard, j + 2, 2, 2, c2v, true); step(guard, j + 3, 3, 3, c3, true);
+                } else {
+                    step(guard, j, 0, 0, R(0), false); step(guard, j + 1, 1, 1, R(0), false); step(guard, j + 2, 2, 2, R(0), false); step(guard, j + 3, 3, 3, R(0), false);
                 }
-                const R c0 = yn[0], c1 = yn[1], c2v = yn[2], c3 = yn[3];
-                load4(j + 4, yp + 4 * yld);
-                step(j, 0, 0, c0, true); step(j + 1, 1, 1, c1, true); step(j + 2, 2, 2, c2v, true); step(j + 3, 3, 3, c3, true);
-            } else {
-                step(j, 0, 0, R(0), false); step(j + 1, 1, 1, R(0), false); step(j + 2, 2, 2, R(0), false); step(j + 3, 3, 3, R(0), false);
+                store_tile();
+                if constexpr (SIG) sp += 4 * ch.sld;
             }
-            store_tile();
-            if constexpr (SIG) sp += 4 * ch.sld;
-        }                                                            // (no tail: the rows end on a tile boundary)
+        };
+        if constexpr (RAGGED) run_tiles(std::true_type{}, ch.rag_rows);
+        run_tiles(std::false_type{}, ch.Tw);                        // (no tail: the rows end on a tile boundary)
         o.events = events;
         return o;
     }
@@ -769,401 +782,6 @@ struct GibbsWarp {
         return o;
     }
 
-    // ================================================================================================================
-    // Latency-optimised fp32 passes (HMC_LAT, K <= 4, plain sweep).  Same algorithm and streams as the passes above; what
-    // changes is the length of the dependent chain per time step, which bounds the kernel whenever a scheduler holds few
-    // warps (mid-width batches: one warp per scheduler) and is the top stall even with four.
-    //
-    // Forward (forwardupdate_P! :371-440): the recursion runs on an UNNORMALISED vector r_t = (r_{t-1} A) .* e_t * g_{t-2}
-    // with g_t = rsqrt(sum r_t): the scale only has to keep r in range, so it may lag — the normaliser's add-add-MUFU chain
-    // leaves the recursion, whose dependent path is then 3 FMAs + 1 multiply per step.  (log sum r_t obeys
-    // a_t = a_{t-1} - a_{t-2}/2 + log tot_t: roots of modulus 0.71, a stable filter; dividing by the full lagged sum would
-    // be marginally stable.)  The stored row is r_t * g_t^2 = pif[t,:], off the chain.
-    static constexpr bool kLat = HMC_LAT && sizeof(R) == 4 && !SMOOTH && !SIG && K <= 4;
-
-    template <bool RAGGED, bool STREAM = false>
-    static __device__ __noinline__ FwdOut forward_pass_lat(const Chain ch, const Emission<R, K> em, const Vec rho_in) {
-        FwdOut o;
-        o.events = 0;
-        const long long yld = STREAM ? ch.yld : 1ll;
-        constexpr bool ragged = RAGGED;
-        constexpr int KP = K / 2;
-        constexpr bool kOdd = (K & 1) != 0;
-        f2 negmu2[KP], q2[KP], c2[KP], A2[K][KP];
-        float negmu_l = 0.f, q_l = 0.f, c_l = 0.f, A_l[K];
-#pragma unroll
-        for (int p = 0; p < KP; ++p) {
-            negmu2[p] = mk2(-(float)em.mu[2 * p], -(float)em.mu[2 * p + 1]);
-            q2[p] = mk2((float)em.q[2 * p], (float)em.q[2 * p + 1]);
-            c2[p] = mk2((float)em.c[2 * p], (float)em.c[2 * p + 1]);
-#pragma unroll
-            for (int r = 0; r < K; ++r) A2[r][p] = mk2((float)ch.A[r][2 * p], (float)ch.A[r][2 * p + 1]);
-        }
-        if (kOdd) {
-            negmu_l = -(float)em.mu[K - 1]; q_l = (float)em.q[K - 1]; c_l = (float)em.c[K - 1];
-#pragma unroll
-            for (int r = 0; r < K; ++r) A_l[r] = (float)ch.A[r][K - 1];
-        }
-        float rr[K];                                                 // unnormalised filtered vector
-#pragma unroll
-        for (int s = 0; s < K; ++s) rr[s] = (float)rho_in.v[s];      // t = 1 uses ρ (:390); sums to one
-        float g1 = 1.f, g2 = 1.f;                                    // rsqrt(sum r) one and two steps back
-        float L1 = 0.f, L2 = 0.f, ll2 = 0.f;                         // lg2(sum r) one and two steps back, log2-likelihood
-        float pfn[K];                                                // the normalised row of the last step
-#pragma unroll
-        for (int s = 0; s < K; ++s) pfn[s] = rr[s];
-        const R* yp = ch.y0;
-        R* pip = ch.pi0;
-        R buf[4][K];
-        auto step = [&](int j, int u, int yo, R ypre, bool preloaded) {
-            if (!ragged || j >= ch.off) {
-                const float yt = (float)(preloaded ? ypre : ld_ro(yp + yo * yld));
-                const f2 y2 = splat2(yt);
-                f2 l2[KP > 0 ? KP : 1];
-                float l_l = -3.0e38f;
-#pragma unroll
-                for (int p = 0; p < KP; ++p) { const f2 d = y2 + negmu2[p]; l2[p] = fma2(d * d, q2[p], c2[p]); }
-                if (kOdd) { const float d = yt + negmu_l; l_l = fmaf(d * d, q_l, c_l); }
-                float m2 = l_l;
-#pragma unroll
-                for (int p = 0; p < KP; ++p) m2 = fmaxf(m2, fmaxf(l2[p].v.x, l2[p].v.y));
-                const f2 nm = splat2(-m2);
-                const f2 gg = splat2(g2);
-                f2 rn2[KP > 0 ? KP : 1];
-                float rn_l = 0.f;
-#pragma unroll
-                for (int p = 0; p < KP; ++p) {
-                    const f2 a = l2[p] + nm;
-                    const f2 ec = mk2(Real<float>::ex2(a.v.x), Real<float>::ex2(a.v.y)) * gg;      // off the chain
-                    f2 pred = splat2(rr[0]) * A2[0][p];
-#pragma unroll
-                    for (int r = 1; r < K; ++r) pred = fma2(splat2(rr[r]), A2[r][p], pred);
-                    rn2[p] = pred * ec;
-                }
-                if (kOdd) {
-                    const float ec = Real<float>::ex2(l_l - m2) * g2;
-                    float pred = rr[0] * A_l[0];
-#pragma unroll
-                    for (int r = 1; r < K; ++r) pred = fmaf(rr[r], A_l[r], pred);
-                    rn_l = pred * ec;
-                }
-#pragma unroll
-                for (int p = 0; p < KP; ++p) { rr[2 * p] = rn2[p].v.x; rr[2 * p + 1] = rn2[p].v.y; }
-                if (kOdd) rr[K - 1] = rn_l;
-                float tot = kOdd ? rn_l : 0.f;
-#pragma unroll
-                for (int p = 0; p < KP; ++p) tot += rn2[p].v.x + rn2[p].v.y;
-                float g;
-                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(tot));
-                const float inv = g * g;
-                const f2 inv2 = splat2(inv);
-#pragma unroll
-                for (int p = 0; p < KP; ++p) { const f2 w2 = rn2[p] * inv2; pfn[2 * p] = w2.v.x; pfn[2 * p + 1] = w2.v.y; }
-                if (kOdd) pfn[K - 1] = rn_l * inv;
-                if (LOGLIK) {
-                    // the reference's normaliser: tot_t = s_t / (s_{t-1} g_{t-2}),  lg2 g = -lg2(s)/2
-                    const float L = Real<float>::lg2(tot);
-                    ll2 += m2 + (L - L1) + 0.5f * L2;
-                    L2 = L1; L1 = L;
-                }
-                g2 = g1; g1 = g;
-#pragma unroll
-                for (int s = 0; s < K; ++s) buf[u][s] = (R)pfn[s];
-            }
-        };
-        auto store_tile = [&]() {
-#pragma unroll
-            for (int s = 0; s < K; ++s) st_quad(pip + s * 128, buf[0][s], buf[1][s], buf[2][s], buf[3][s]);
-        };
-        const int pad = (4 - (ch.Tw & 3)) & 3;
-        int j = 0;
-        {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                for (int s = 0; s < K; ++s) buf[u][s] = R(0);
-                const int jj = u - pad;
-                if (jj >= 0 && jj < ch.Tw) step(jj, u, jj, R(0), false);
-            }
-            store_tile();
-            j = (4 - pad < ch.Tw) ? 4 - pad : ch.Tw;
-            yp += (long long)j * yld; pip += 4 * K * 32;
-        }
-        R yn[4] = {R(0), R(0), R(0), R(0)};
-        auto load4 = [&](int jj, const R* p) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) yn[u] = (jj + u < ch.Tw && (!ragged || jj + u >= ch.off)) ? ld_ro(p + u * yld) : R(0);
-        };
-        if constexpr (STREAM) load4(j, yp);
-        for (; j + 3 < ch.Tw; j += 4, yp += 4 * yld, pip += 4 * K * 32) {
-            if constexpr (STREAM) {
-                if (j + kYAhead + 3 < ch.Tw && (!ragged || j + kYAhead >= ch.off)) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) prefetch_l1(yp + (kYAhead + u) * yld);
-                }
-                const R c0 = yn[0], c1 = yn[1], c2v = yn[2], c3 = yn[3];
-                load4(j + 4, yp + 4 * yld);
-                step(j, 0, 0, c0, true); step(j + 1, 1, 1, c1, true); step(j + 2, 2, 2, c2v, true); step(j + 3, 3, 3, c3, true);
-            } else {
-                step(j, 0, 0, R(0), false); step(j + 1, 1, 1, R(0), false); step(j + 2, 2, 2, R(0), false); step(j + 3, 3, 3, R(0), false);
-            }
-            store_tile();
-        }
-#pragma unroll
-        for (int s = 0; s < K; ++s) o.pf.v[s] = (R)pfn[s];
-        o.ll = (R)(ll2 * 0.6931471805599453f);
-        return o;
-    }
-
-    // Backward (update_X! :459-484 + the next sweep's statistics).  The draw X_t | X_{t+1} = x is decided by the signs of
-    //   d_i^x = cum_i^x - u cum_{K-1}^x,   cum^x = running sums of pif[t,:] .* A[:,x]     (state > i  <=>  d_i^x < 0).
-    // Rows and uniforms do not depend on the sampled path, so d_i^x is evaluated for EVERY entering state x ahead of time
-    // (packed FP32x2 over pairs of time steps: the 4 rows of a state in a ring tile are two register pairs) and the dependent
-    // chain of a step shrinks to: select d_i by the later state (K-1 selects deep) and compare with zero.  No selection table
-    // in shared memory.  Transition counts are packed by DESTINATION: rowD[j] holds one field per origin state i (n_ij).
-    struct LatOut { R Sd[K - 1], Qd[K - 1]; Row rowD[K]; int xN; bool bad; };
-
-    template <bool RAGGED, bool GATED, bool STREAM = false>
-    static __device__ __noinline__ LatOut backward_pass_lat(const Chain ch, const Vec pf_in, const RngKey key, const uint32_t sweep,
-                                                            const unsigned flags) {
-        LatOut o;
-        constexpr bool ragged = RAGGED;
-        const int Tw = ch.Tw, T = ch.T;
-        const long long ys = (!STREAM && !GATED) ? 1ll : ch.yld;
-        float Sd[K - 1], Qd[K - 1];
-        Row rowD[K];
-#pragma unroll
-        for (int i = 0; i < K - 1; ++i) { Sd[i] = 0.f; Qd[i] = 0.f; }
-#pragma unroll
-        for (int i = 0; i < K; ++i) rowD[i] = 0;
-        bool lt[K - 1];                                              // the later time step's state, one-hot (monotone)
-#pragma unroll
-        for (int i = 0; i < K - 1; ++i) lt[i] = false;
-        float ptn[K];                                                // the later time step's filtered row (quirk Q5 gate)
-#pragma unroll
-        for (int s = 0; s < K; ++s) ptn[s] = 1.f;
-        bool bad = false;
-        int xN = 0;
-        float Af[K][K];
-#pragma unroll
-        for (int r = 0; r < K; ++r)
-#pragma unroll
-            for (int x = 0; x < K; ++x) Af[r][x] = (float)ch.A[r][x];
-        const float cshift = (float)ch.c;
-        const float eps = Real<float>::eps();
-        // -u in (-1, 0): same words and rounding as u01
-        auto negu = [](uint32_t w) -> float { return fmaf(__uint2float_rz(w), -2.3283064365386963e-10f, -1.1641532182693481e-10f); };
-        // statistics and the transition current -> later once the current state (ltn) is known
-        auto book = [&](const bool (&ltn)[K - 1], const float (&pt)[K], float yt, bool first) {
-            if (!first) {
-                Row inc = (Row)1;
-#pragma unroll
-                for (int i = 1; i < K; ++i) inc = ltn[i - 1] ? ((Row)1 << (Pack::kBits * i)) : inc;
-#pragma unroll
-                for (int jx = 0; jx < K; ++jx) if (is_state(lt, jx)) rowD[jx] += inc;
-            }
-            const float d = yt - cshift;
-#pragma unroll
-            for (int i = 0; i < K - 1; ++i) if (is_state(ltn, i)) { Sd[i] += d; Qd[i] = fmaf(d, d, Qd[i]); }
-            const float gate = pick<float>(ltn, pt);               // pif[t, x_t]: the reference's `total` of the next step (Q5)
-            bad = bad || !(gate > eps);
-#pragma unroll
-            for (int i = 0; i < K - 1; ++i) lt[i] = ltn[i];
-            if (GATED) {
-#pragma unroll
-                for (int s = 0; s < K; ++s) ptn[s] = pt[s];
-            }
-        };
-        // d_i^x for one row (scalar form: head, tail and the gated re-run)
-        auto cand = [&](const float (&pt)[K], float nu, float (&dd)[K - 1][K]) {
-#pragma unroll
-            for (int x = 0; x < K; ++x) {
-                float c[K];
-                c[0] = pt[0] * Af[0][x];
-#pragma unroll
-                for (int r = 1; r < K; ++r) c[r] = fmaf(pt[r], Af[r][x], c[r - 1]);
-                if (GATED) {                                         // :472-480: p = 1/D when pif[t+1, x] <= eps()
-                    if (!(ptn[x] > eps)) {
-#pragma unroll
-                        for (int r = 0; r < K; ++r) c[r] = (float)(r + 1);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < K - 1; ++i) dd[i][x] = fmaf(nu, c[K - 1], c[i]);
-            }
-        };
-        auto decide = [&](const float (&dd)[K - 1][K], bool (&ltn)[K - 1]) {
-#pragma unroll
-            for (int i = 0; i < K - 1; ++i) ltn[i] = pick<float>(lt, dd[i]) < 0.f;
-        };
-        auto scalar_step = [&](const float (&pt)[K], float yt, uint32_t word) {
-            float dd[K - 1][K];
-            cand(pt, negu(word), dd);
-            bool ltn[K - 1];
-            decide(dd, ltn);
-            book(ltn, pt, yt, false);
-        };
-        const R* yp = ch.y0 + (long long)(Tw - 1) * ys;
-        const int pad = (4 - (Tw & 3)) & 3;
-        auto row_ptr = [&](int jrow) -> const R* {
-            const int jp = jrow + pad;
-            return ch.pi0 + (size_t)(jp >> 2) * (4 * K * 32) + (jp & 3);
-        };
-        uint4 w = rng_block_states(key, sweep, 0u);
-        if (T > 0) {
-            // X[N] ~ Categorical(pif[N,:]); with quirk Q1 the relabelled row is used with chain labels (:512-514)
-            R pN[K];
-            float pff[K];
-#pragma unroll
-            for (int s = 0; s < K; ++s) pff[s] = (float)pf_in.v[s];
-            if (flags & 1u) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    R vsel = R(0);
-#pragma unroll
-                    for (int s = 0; s < K; ++s) vsel = (ch.rank[s] == k) ? pf_in.v[s] : vsel;
-                    pN[k] = vsel;
-                }
-            } else {
-#pragma unroll
-                for (int s = 0; s < K; ++s) pN[s] = pf_in.v[s];
-            }
-            bool ltn[K - 1];
-            draw(pN, u01<R>(w.x), ltn);
-#pragma unroll
-            for (int i = 0; i < K - 1; ++i) xN += ltn[i] ? 1 : 0;
-            book(ltn, pff, (float)ld_ro(yp), true);
-        }
-        int i = 1;
-        auto load_row = [&](int u, float (&pt)[K], float& yt) {
-            const R* rp = row_ptr(Tw - 1 - (i + u));
-#pragma unroll
-            for (int s = 0; s < K; ++s) pt[s] = (float)ld_stream(rp + s * 128);
-            yt = (!ragged || i + u < T) ? (float)ld_ro(yp - (u + 1) * ys) : 0.f;
-        };
-        {
-            float p0[K], p1[K], p2[K], y0 = 0.f, y1 = 0.f, y2 = 0.f;
-            if (Tw > 1) load_row(0, p0, y0);
-            if (Tw > 2) load_row(1, p1, y1);
-            if (Tw > 3) load_row(2, p2, y2);
-            if (Tw > 1 && (!ragged || i + 0 < T)) scalar_step(p0, y0, w.y);
-            if (Tw > 2 && (!ragged || i + 1 < T)) scalar_step(p1, y1, w.z);
-            if (Tw > 3 && (!ragged || i + 2 < T)) scalar_step(p2, y2, w.w);
-            const int done = Tw > 3 ? 3 : Tw - 1;
-            i += done; yp -= done * ys;
-        }
-        {
-            constexpr int kGroupElems = 4 * K * 32;
-            constexpr int kChunksPerLane = (int)(kGroupElems * sizeof(R) / 16 / 32);
-            const int lane = threadIdx.x & 31;
-            R* const ring = reinterpret_cast<R*>(smem_base() + ch.ring_off);
-            const int n_groups = (Tw - i) / 4;
-            const R* gsrc = ch.pi0 - lane * 4 + (long long)(Tw + pad - 8) * K * 32;
-            const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)lane * 16u;
-            auto issue = [&](int g) {
-                if (g < n_groups) {
-                    const char* src = reinterpret_cast<const char*>(gsrc - (long long)g * kGroupElems) + lane * 16;
-                    const unsigned dst = ring_s + (unsigned)((g % kRing) * kGroupElems * (int)sizeof(R));
-#pragma unroll
-                    for (int m = 0; m < kChunksPerLane; ++m) cp_async16_s(dst + 512u * m, src + 512 * m);
-                }
-                cp_async_commit();
-            };
-#pragma unroll
-            for (int g = 0; g < kRing - 1; ++g) issue(g);
-            float ynx[4] = {0.f, 0.f, 0.f, 0.f};
-            auto loady4 = [&](int ii, const R* p) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) ynx[u] = (!ragged || ii + u < T) ? (float)ld_ro(p - (u + 1) * ys) : 0.f;
-            };
-            if constexpr (STREAM) { if (n_groups > 0) loady4(i, yp); }
-            for (int g = 0; g < n_groups; ++g, i += 4, yp -= 4 * ys) {
-                if (STREAM && i + kYAhead + 3 < T) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) prefetch_l1(yp - (kYAhead + u + 1) * ys);
-                }
-                issue(g + kRing - 1);
-                cp_async_wait<kRing - 1>();
-                __syncwarp();
-                const R* st = ring + (g % kRing) * kGroupElems + lane * 4;
-                // positions 0..3 of a tile = rows low..high; the steps of this iteration visit them high to low:
-                // hi = (position 2, position 3) = (step 1, step 0),  lo = (position 0, position 1) = (step 3, step 2)
-                f2 hi[K], lo[K];
-#pragma unroll
-                for (int s = 0; s < K; ++s) {
-                    const float4 v = *reinterpret_cast<const float4*>(st + s * 128);
-                    lo[s] = mk2(v.x, v.y); hi[s] = mk2(v.z, v.w);
-                }
-                float y0, y1, y2, y3;
-                if constexpr (STREAM) {
-                    y0 = ynx[0]; y1 = ynx[1]; y2 = ynx[2]; y3 = ynx[3];
-                    if (g + 1 < n_groups) loady4(i + 4, yp - 4 * ys);
-                } else {
-                    y0 = (!ragged || i + 0 < T) ? (float)ld_ro(yp - 1 * ys) : 0.f;
-                    y1 = (!ragged || i + 1 < T) ? (float)ld_ro(yp - 2 * ys) : 0.f;
-                    y2 = (!ragged || i + 2 < T) ? (float)ld_ro(yp - 3 * ys) : 0.f;
-                    y3 = (!ragged || i + 3 < T) ? (float)ld_ro(yp - 4 * ys) : 0.f;
-                }
-                w = rng_block_states(key, sweep, (uint32_t)(i >> 2));
-                if constexpr (GATED) {
-                    float p[K];
-#define HMC_LSTEP(u, HALF, PAIR, word, YT)                                                                            \
-    if (!ragged || i + (u) < T) {                                                                                        \
-        _Pragma("unroll") for (int s = 0; s < K; ++s) p[s] = PAIR[s].v.HALF;                                              \
-        scalar_step(p, YT, word);                                                                                        \
-    }
-                    HMC_LSTEP(0, y, hi, w.x, y0) HMC_LSTEP(1, x, hi, w.y, y1) HMC_LSTEP(2, y, lo, w.z, y2) HMC_LSTEP(3, x, lo, w.w, y3)
-#undef HMC_LSTEP
-                } else {
-                    // thresholds of all K entering states for the 4 steps, two steps per packed instruction
-                    f2 dh[K - 1][K], dl[K - 1][K];
-                    const f2 nuh = mk2(negu(w.y), negu(w.x)), nul = mk2(negu(w.w), negu(w.z));
-#pragma unroll
-                    for (int x = 0; x < K; ++x) {
-                        f2 ch_[K], cl_[K];
-                        ch_[0] = hi[0] * splat2(Af[0][x]); cl_[0] = lo[0] * splat2(Af[0][x]);
-#pragma unroll
-                        for (int r = 1; r < K; ++r) {
-                            ch_[r] = fma2(hi[r], splat2(Af[r][x]), ch_[r - 1]);
-                            cl_[r] = fma2(lo[r], splat2(Af[r][x]), cl_[r - 1]);
-                        }
-#pragma unroll
-                        for (int q = 0; q < K - 1; ++q) { dh[q][x] = fma2(nuh, ch_[K - 1], ch_[q]); dl[q][x] = fma2(nul, cl_[K - 1], cl_[q]); }
-                    }
-#define HMC_LSTEP(u, HALF, PAIR, DD, YT)                                                                              \
-    if (!ragged || i + (u) < T) {                                                                                        \
-        float dd[K - 1][K], p[K];                                                                                        \
-        _Pragma("unroll") for (int q = 0; q < K - 1; ++q) _Pragma("unroll") for (int x = 0; x < K; ++x) dd[q][x] = DD[q][x].v.HALF; \
-        _Pragma("unroll") for (int s = 0; s < K; ++s) p[s] = PAIR[s].v.HALF;                                              \
-        bool ltn[K - 1];                                                                                                 \
-        decide(dd, ltn);                                                                                                 \
-        book(ltn, p, YT, false);                                                                                         \
-    }
-                    HMC_LSTEP(0, y, hi, dh, y0) HMC_LSTEP(1, x, hi, dh, y1) HMC_LSTEP(2, y, lo, dl, y2) HMC_LSTEP(3, x, lo, dl, y3)
-#undef HMC_LSTEP
-                }
-                __syncwarp();
-            }
-            cp_async_wait<0>();
-        }
-        if (i < Tw) {
-            w = rng_block_states(key, sweep, (uint32_t)(i >> 2));
-            float p0[K], p1[K], p2[K], y0 = 0.f, y1 = 0.f, y2 = 0.f;
-            load_row(0, p0, y0);
-            if (i + 1 < Tw) load_row(1, p1, y1);
-            if (i + 2 < Tw) load_row(2, p2, y2);
-            if (!ragged || i + 0 < T) scalar_step(p0, y0, w.x);
-            if (i + 1 < Tw && (!ragged || i + 1 < T)) scalar_step(p1, y1, w.y);
-            if (i + 2 < Tw && (!ragged || i + 2 < T)) scalar_step(p2, y2, w.z);
-        }
-#pragma unroll
-        for (int q = 0; q < K - 1; ++q) { o.Sd[q] = (R)Sd[q]; o.Qd[q] = (R)Qd[q]; }
-#pragma unroll
-        for (int q = 0; q < K; ++q) o.rowD[q] = rowD[q];
-        o.xN = xN;
-        o.bad = bad;
-        return o;
-    }
     static __device__ __forceinline__ void run(const GibbsArgs& a, const int warp, const int lane, Entry* smem_tab) {
         const int slot = warp * 32 + lane;
         const int ns = a.n_slots;
@@ -1198,7 +816,7 @@ struct GibbsWarp {
         const int T = ch.T;
         const bool stream_y = a.yld != 1;     // distinct series per chain: y is streamed from HBM (prefetching passes)
         // padding lanes (T = 0) only exist in the last warp, which therefore counts as ragged
-        ch.ragged = __any_sync(0xffffffffu, ch.off != 0);
+        ch.rag_rows = (int)__reduce_max_sync(0xffffffffu, (unsigned)ch.off);
         const R totS = reinterpret_cast<const R*>(a.totS)[slot], totQ = reinterpret_cast<const R*>(a.totQ)[slot];
         const RngKey key{a.k0, a.k1, a.chain_id[slot]};
         R* __restrict__ const out = reinterpret_cast<R*>(a.out);
@@ -1250,14 +868,8 @@ struct GibbsWarp {
                 Vec rv;
 #pragma unroll
                 for (int s = 0; s < K; ++s) rv.v[s] = rho[s];
-                FwdOut fo;
-                if constexpr (kLat) {
-                    fo = stream_y ? (ch.ragged ? forward_pass_lat<true, true>(ch, em, rv) : forward_pass_lat<false, true>(ch, em, rv))
-                                  : (ch.ragged ? forward_pass_lat<true>(ch, em, rv) : forward_pass_lat<false>(ch, em, rv));
-                } else {
-                    fo = stream_y ? (ch.ragged ? forward_pass<true, false, true>(ch, em, rv) : forward_pass<false, false, true>(ch, em, rv))
-                                  : (ch.ragged ? forward_pass<true, false>(ch, em, rv) : forward_pass<false, false>(ch, em, rv));
-                }
+                FwdOut fo = stream_y ? (ch.rag_rows > 0 ? forward_pass<true, false, true>(ch, em, rv) : forward_pass<false, false, true>(ch, em, rv))
+                                     : (ch.rag_rows > 0 ? forward_pass<true, false>(ch, em, rv) : forward_pass<false, false>(ch, em, rv));
                 R chk = fo.pf.v[0];
 #pragma unroll
                 for (int s = 1; s < K; ++s) chk += fo.pf.v[s];
@@ -1343,36 +955,17 @@ struct GibbsWarp {
 
             // ---- 4. backward pass
             Back b;
-            if constexpr (!kLat) {
 #pragma unroll
-                for (int x = 0; x < K; ++x) {                       // this thread's private selection table
-                    Entry en;
+            for (int x = 0; x < K; ++x) {                           // this thread's private selection table
+                Entry en;
 #pragma unroll
-                    for (int r = 0; r < K; ++r) en.a[r] = ch.A[r][x];
-                    en.inc = (Row)1 << (Pack::kBits * x);
-                    smem_tab[x * kGibbsThreads + threadIdx.x] = en;
-                }
+                for (int r = 0; r < K; ++r) en.a[r] = ch.A[r][x];
+                en.inc = (Row)1 << (Pack::kBits * x);
+                smem_tab[x * kGibbsThreads + threadIdx.x] = en;
             }
             int xN;
             typename std::conditional<Pack::kFlush, TransAcc, NoAcc>::type flushed;
-            if constexpr (kLat) {
-                Vec pv;
-#pragma unroll
-                for (int s = 0; s < K; ++s) pv.v[s] = pf[s];
-                LatOut lo = stream_y ? (ch.ragged ? backward_pass_lat<true, false, true>(ch, pv, key, sweep, a.flags)
-                                                  : backward_pass_lat<false, false, true>(ch, pv, key, sweep, a.flags))
-                                     : (ch.ragged ? backward_pass_lat<true, false>(ch, pv, key, sweep, a.flags)
-                                                  : backward_pass_lat<false, false>(ch, pv, key, sweep, a.flags));
-                // quirk Q5 fired somewhere in the warp: redo the pass exactly (warp-uniform, see below)
-                if (__builtin_expect(__any_sync(0xffffffffu, lo.bad), 0)) lo = backward_pass_lat<true, true>(ch, pv, key, sweep, a.flags);
-                xN = lo.xN;
-#pragma unroll
-                for (int i = 0; i < K - 1; ++i) { b.Sd[i] = lo.Sd[i]; b.Qd[i] = lo.Qd[i]; }
-#pragma unroll
-                for (int i = 0; i < K; ++i)                         // rowD[j] holds one field per origin state i
-#pragma unroll
-                    for (int j = 0; j < K; ++j) trans[i][j] = (int)((lo.rowD[j] >> (Pack::kBits * i)) & (Row)Pack::kMaxT);
-            } else {
+            {
                 Vec pv;
 #pragma unroll
                 for (int s = 0; s < K; ++s) pv.v[s] = pf[s];
@@ -1380,9 +973,9 @@ struct GibbsWarp {
                 if (SMOOTH) {                                        // accumulates into memory: run gated in place
                     bo = backward_pass<true, true>(ch, pv, key, sweep, a.flags, save);
                 } else {
-                    bo = stream_y ? (ch.ragged ? backward_pass<true, false, true>(ch, pv, key, sweep, a.flags, save)
+                    bo = stream_y ? (ch.rag_rows > 0 ? backward_pass<true, false, true>(ch, pv, key, sweep, a.flags, save)
                                                : backward_pass<false, false, true>(ch, pv, key, sweep, a.flags, save))
-                                  : (ch.ragged ? backward_pass<true, false>(ch, pv, key, sweep, a.flags, save)
+                                  : (ch.rag_rows > 0 ? backward_pass<true, false>(ch, pv, key, sweep, a.flags, save)
                                                : backward_pass<false, false>(ch, pv, key, sweep, a.flags, save));
                     // quirk Q5 fired somewhere: redo the pass exactly (counter-based RNG: identical draws otherwise)
                     // (warp-uniform: the pass stages rows through the warp's cp.async ring and synchronises the warp, so every
@@ -1398,15 +991,13 @@ struct GibbsWarp {
             }
 
             // ---- unpack the statistics for the next sweep's draws
-            if constexpr (!kLat) {
 #pragma unroll
-                for (int i = 0; i < K; ++i)
+            for (int i = 0; i < K; ++i)
 #pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        trans[i][j] = b.tr.get(i, j);
-                        if constexpr (Pack::kFlush) trans[i][j] += flushed.n[i * K + j];
-                    }
-            }
+                for (int j = 0; j < K; ++j) {
+                    trans[i][j] = b.tr.get(i, j);
+                    if constexpr (Pack::kFlush) trans[i][j] += flushed.n[i * K + j];
+                }
             {
                 // occupation counts from the transition counts: n_i = sum_j n_ij + [X_N = i]
                 R sS = R(0), sQ = R(0);

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kWideThreads, sizeof(R) == 8 ? 3 : (W == 32 ? 
                 e = (R)Real<float>::ex2((float)(l - m2));
             } else {
                 const R z = (yt - mu) * isd;
-                e = (R)exp(-0.5 * (double)(z * z)) * nrm;
+                e = (R)exp_nonpos<false>(-0.5 * (double)(z * z)) * nrm;
             }
             // broadcast pf through shared memory (double-buffered: one __syncwarp per step is enough)
             R* const line = scratch + (t & 1) * W;

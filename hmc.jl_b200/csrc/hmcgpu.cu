@@ -4,6 +4,7 @@
 #include "gibbs_wide_kernel.cuh"
 #include "gibbs_pair_kernel.cuh"
 #include "gibbs_scan_kernel.cuh"
+#include "gibbs_seg_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -259,7 +260,7 @@ __global__ void filter_kernel(long long B, long long T, const double* __restrict
         R m2;
         if (sig && sig[t]) {                                  // z scaled by 1/(1+kappa), pdf by the same factor
             if constexpr (sizeof(R) == 8) {
-                em.eval_scaled((R)yb[t], k1, e);
+                em.template eval_scaled<true>((R)yb[t], k1, e);          // entry points keep libm's exp
                 m2 = R(0);
             } else {
                 // fp32: the scaled series point (y - mu)*k1 = (y*k1 - mu*k1) is not an affine image of y for all states at
@@ -275,7 +276,7 @@ __global__ void filter_kernel(long long B, long long T, const double* __restrict
                 m2 = (R)(mx + Real<float>::lg2((float)k1));
             }
         } else {
-            m2 = em.eval((R)yb[t], e);
+            m2 = em.template eval<true>((R)yb[t], e);
         }
         bool ok;
         const R tot = forward_step<R, K>(a, e, pf, ok);
@@ -1103,12 +1104,16 @@ struct hmcgpu_plan {
     bool wide = false;
     bool pair = false;   // fp32 paired kernel: a task is 64 chain slots (two chains per thread)
     bool seg = false;    // mid-width batch: L lanes per chain, each lane one contiguous time segment (gibbs_seg_kernel.cuh)
+    int seg_lanes = 0;   // L (a warp task holds 32 / L chains)
+    int seg_threads = 128; // threads per block of the segment kernel
     int n_groups = 1, n_bufs = 1;
     std::vector<cudaStream_t> gstreams;
     std::vector<cudaEvent_t> pool_events;
     std::vector<cudaEvent_t> timing_events;   // pairs around every sweep launch + one end-of-sweeps event per group (timing enabled)
     double launch_ms_sum = 0.0;
     DevBuf d_mu, d_sig2, d_A, d_pie, d_fc, d_ll, d_sum, d_sumsq, d_pibsum, d_fcsum;
+    DevBuf d_diag;       // segment kernel: chain-sweeps that fell back to the exact entering vectors
+    unsigned long long seg_fallbacks[2] = {0, 0};   // [0] chain-sweeps on the exact path, [1] speculative groups (sum over chain-sweeps)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     double gpu_ms = 0.0, sweep_ms = 0.0;
     long long n_launches = 0, n_sweep_launches = 0, h2d = 0, d2h = 0;
@@ -1217,7 +1222,10 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     // Narrow batches (the reference's own regime: one chain per end date) cannot fill the GPU with a thread per chain:
     // below kScanMaxChains chains the time-parallel warp-per-chain kernel is used (K <= 4, plain sweep, window in smem).
     {
-        long long lim = 12288;
+        // (the signals tier has no segment kernel: there the warp-per-chain kernel serves up to 12 288 chains; for the plain
+        //  sweep the segment kernel takes over from ~4000 chains — measured crossover on C2)
+        const bool seg_ok = !(p->is_signal != nullptr || p->pi_row_back != 0) && !(getenv("HMCGPU_SEG_LANES") && atoi(getenv("HMCGPU_SEG_LANES")) == 0);
+        long long lim = seg_ok ? 4096 : 12288;
         if (const char* e = getenv("HMCGPU_SCAN_MAX_CHAINS")) lim = atoll(e);
         const int tmax = p->precision == 32 ? (K == 2 ? scan_max_T<float, 2>() : K == 3 ? scan_max_T<float, 3>() : scan_max_T<float, 4>())
                                             : (K == 2 ? scan_max_T<double, 2>() : K == 3 ? scan_max_T<double, 3>() : scan_max_T<double, 4>());
@@ -1228,10 +1236,30 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         pl->scan = !pl->wide && K <= 4 && !pl->pair && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN) &&
                    (long long)nw * nc <= lim && pl->max_T <= tmax;
     }
-    const int ts = pl->pair ? 64 : 32;
     const long long n_real = (long long)nw * nc;
+    // Mid-width batches (too many chains for a warp each, too few to fill the schedulers with a thread each): L lanes per
+    // chain, one time segment per lane (gibbs_seg_kernel.cuh).  L is chosen so that the batch yields about one full wave of
+    // warps; HMCGPU_SEG_LANES forces it (0 = never).  K <= 4, plain sweep.
+    {
+        int lanes = 0;
+        if (!pl->wide && K <= 4 && !pl->sig && !pl->pair && !pl->scan && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN)) {
+            // measured on C2 (500 windows x c chains, B200): 4 lanes per chain are best up to ~38 000 chains, 2 lanes up to ~90 000,
+            // the thread-per-chain kernel beyond; in units of one wave of thread slots (16 warps per SM):
+            const long long full = (long long)ctx->sm_count * 16 * 32;
+            if (n_real * 2 <= full) lanes = 4;
+            else if (n_real * 4 <= 5 * full) lanes = 2;
+            if (const char* e = getenv("HMCGPU_SEG_LANES")) lanes = atoi(e);
+            if (lanes != 0 && lanes != 2 && lanes != 4) return fail(ctx, HMCGPU_ERR_ARG, "HMCGPU_SEG_LANES must be 0, 2 or 4");
+            const long long tmax = K == 2 ? seg_max_T<2>(lanes) : K == 3 ? seg_max_T<3>(lanes) : seg_max_T<4>(lanes);
+            if (lanes && pl->max_T > tmax) lanes = 0;
+        }
+        pl->seg = lanes != 0;
+        pl->seg_lanes = lanes;
+    }
+    const int ts = pl->pair ? 64 : 32;
     const int n_slots = (int)((n_real + ts - 1) / ts * ts);
-    const int n_warps = n_slots / ts;                       // number of warp tasks
+    const int cpt = pl->seg ? 32 / pl->seg_lanes : ts;      // chains per warp task
+    const int n_warps = n_slots / cpt;                      // number of warp tasks
     pl->n_slots = n_slots; pl->n_warps = n_warps;
     std::vector<int> slot_win(n_slots, -1), slot_chain(n_slots, 0), Ts(n_slots, 0), win_slot0(nw), warp_T(n_warps, 0);
     std::vector<long long> ybase(n_slots, 0), warp_off(n_warps, 0), wbase(nw), wbase_init(nw), x0_off(nw);
@@ -1258,11 +1286,17 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     std::vector<long long> slot_off(n_slots, 0);
     for (int wp = 0; wp < n_warps; ++wp) {
         int m = 0;
-        for (int l = 0; l < ts; ++l) m = std::max(m, Ts[wp * ts + l]);
+        for (int l = 0; l < cpt; ++l) m = std::max(m, Ts[wp * cpt + l]);
         warp_T[wp] = m;
         warp_off[wp] = pi_elems;
+        if (pl->seg) {
+            // segment kernel: every lane owns a frame of C = 4 ceil(T / 4L) rows (warp_T holds C), tiled like the thread kernel's
+            const int Cs = std::max(4, (m + 4 * pl->seg_lanes - 1) / (4 * pl->seg_lanes) * 4);
+            warp_T[wp] = Cs;
+            pi_elems += (long long)Cs * K * 32;
+        }
         // thread-per-chain kernels: rows right-aligned to tiles of 4 time steps (gibbs_kernel.cuh, st_quad)
-        if (!pl->wide) pi_elems += (long long)(pl->pair ? m : (m + 3) / 4 * 4) * K * ts;
+        else if (!pl->wide) pi_elems += (long long)(pl->pair ? m : (m + 3) / 4 * 4) * K * ts;
         else for (int l = 0; l < ts; ++l) { slot_off[wp * ts + l] = pi_elems; pi_elems += (long long)Ts[wp * ts + l] * K; }
     }
     // forecasts: realised y at end+h per window (NaN outside the series), horizons sorted ascending
@@ -1405,6 +1439,19 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     a.yfut = pl->yfut.p; a.flags = p->flags;
     a.sigw = pl->sigw.p; a.sbase = pl->sbase.as<long long>(); a.sld = sld; a.cntM = pl->cntM.as<int>(); a.Sm = pl->Sm.p; a.Qm = pl->Qm.p; a.totSm = pl->totSm.p; a.totQm = pl->totQm.p;
     a.totM = pl->totM.as<int>(); a.kappa = p->kappa; a.pi_back = p->pi_row_back;
+    a.seg_warm = 32;
+    if (const char* e = getenv("HMCGPU_SEG_WARMUP")) a.seg_warm = std::max(0, atoi(e));
+    a.seg_barriers = 2;
+    if (const char* e = getenv("HMCGPU_SEG_BARRIERS")) a.seg_barriers = atoi(e);
+    a.diag = nullptr;
+    if (pl->seg) {
+        // 256-thread blocks (8 warps stepping through the phases of a sweep together) when that still gives every SM a block
+        // and a half; otherwise 128
+        pl->seg_threads = (n_warps / (kSegThreads / 32) >= ctx->sm_count * 3 / 2) ? kSegThreads : 128;
+        if (const char* e = getenv("HMCGPU_SEG_THREADS")) pl->seg_threads = atoi(e);
+        CU(ctx, pl->d_diag.alloc(2 * sizeof(unsigned long long)));
+        a.diag = pl->d_diag.as<unsigned long long>();
+    }
     for (int g = 0; g < pl->n_groups; ++g) {
         cudaStream_t s2;
         CU(ctx, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
@@ -1451,6 +1498,7 @@ static int plan_run_t(hmcgpu_plan* pl) {
                                                             pl->totQm.as<R>(), pl->totM.as<int>());
     CU(ctx, cudaGetLastError());
     ++pl->n_launches;
+    if (pl->d_diag.p) CU(ctx, cudaMemsetAsync(pl->d_diag.p, 0, 2 * sizeof(unsigned long long), st));
     if (pl->d_sum.p) { CU(ctx, cudaMemsetAsync(pl->d_sum.p, 0, pl->d_sum.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_sumsq.p, 0, pl->d_sumsq.bytes, st)); }
     if (pl->pacc.p) { CU(ctx, cudaMemsetAsync(pl->pacc.p, 0, pl->pacc.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_pibsum.p, 0, pl->d_pibsum.bytes, st)); }
     if (pl->facc.p) { CU(ctx, cudaMemsetAsync(pl->facc.p, 0, pl->facc.bytes, st)); CU(ctx, cudaMemsetAsync(pl->d_fcsum.p, 0, pl->d_fcsum.bytes, st)); }
@@ -1564,6 +1612,7 @@ static int plan_run_t(hmcgpu_plan* pl) {
                 CU(ctx, (launch_gibbs_wide<R>(cfg, a, pl->K, pl->slot_pi_off.as<long long>(), gs)));
             } else if constexpr (K <= 4) {
                 if (pl->scan) CU(ctx, (launch_gibbs_scan<R, K>(cfg, a, gs)));
+                else if (pl->seg) CU(ctx, (launch_gibbs_seg<R, K>(cfg, a, pl->seg_lanes, pl->seg_threads, gs)));
                 else if constexpr (std::is_same<R, float>::value) {
                     if (pl->pair) CU(ctx, (launch_gibbs_pair<K>(cfg, a, gs)));
                     else CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
@@ -1608,6 +1657,15 @@ static int plan_run_t(hmcgpu_plan* pl) {
         float t = 0.f;
         CU(ctx, cudaEventElapsedTime(&t, pr.first, pr.second));
         pl->launch_ms_sum += t;
+    }
+    if (pl->d_diag.p) {
+        CU(ctx, cudaMemcpy(pl->seg_fallbacks, pl->d_diag.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (getenv("HMCGPU_VERBOSE")) {
+            const double cs = (double)pl->n_windows * pl->n_chains * (double)S;
+            fprintf(stderr, "[hmcgpu] segment kernel (%d lanes per chain, warm-up %d): %llu of %.0f chain-sweeps used the exact entering vectors; "
+                            "%.2f speculative groups of 4 steps per chain-sweep\n",
+                    pl->seg_lanes, pl->args.seg_warm, pl->seg_fallbacks[0], cs, (double)pl->seg_fallbacks[1] / cs);
+        }
     }
     pl->ran = true;
     return HMCGPU_OK;

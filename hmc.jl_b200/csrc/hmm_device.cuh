@@ -42,7 +42,7 @@ template <int K> struct Emission<float, K> {
         }
     }
     // e[s] proportional to pdf_s(y); returns log2 of the common factor that was divided out
-    __device__ __forceinline__ float eval(float y, float (&e)[K]) const {
+    template <bool EXACT = false> __device__ __forceinline__ float eval(float y, float (&e)[K]) const {
         float l[K];
 #pragma unroll
         for (int s = 0; s < K; ++s) { const float d = y - mu[s]; l[s] = fmaf(d * d, q[s], c[s]); }
@@ -55,6 +55,42 @@ template <int K> struct Emission<float, K> {
     }
 };
 
+// exp(x) for x <= 0 in fp64 without the libm call: x = n ln2 + f, |f| <= ln2/2, degree-11 Taylor polynomial of exp(f) (truncation
+// 2e-14 relative, result within ~1e-15 relative over [-708, 0]), 2^n added into the exponent field.  The fp64 sweeps spend most
+// of their arithmetic in the K exponentials per time step; north_star asks 1e-5 of the fp64 path.  The deterministic entry
+// points (hmcgpu_filter / smooth ...) keep libm's exp (Emission::eval<true>).
+#ifndef HMC_FAST_EXP64
+#define HMC_FAST_EXP64 1
+#endif
+__device__ __forceinline__ double exp_nonpos_fast(double x) {
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);         // round(x log2 e) in the low mantissa bits
+    const int n = __double2loint(t);
+    const double nd = t - 6755399441055744.0;
+    double f = fma(nd, -6.93147180369123816490e-01, x);                       // ln2 hi
+    f = fma(nd, -1.90821492927058770002e-10, f);                              // ln2 lo
+    double p = 2.505210838544172e-08;                                          // 1/11!
+    p = fma(p, f, 2.755731922398589e-07);
+    p = fma(p, f, 2.755731922398589e-06);
+    p = fma(p, f, 2.48015873015873e-05);
+    p = fma(p, f, 1.984126984126984e-04);
+    p = fma(p, f, 1.388888888888889e-03);
+    p = fma(p, f, 8.333333333333333e-03);
+    p = fma(p, f, 4.166666666666666e-02);
+    p = fma(p, f, 1.666666666666667e-01);
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    const int hi = __double2hiint(p) + (n << 20);                              // p in [0.7, 1.42): scale by 2^n (n >= -1021 here)
+    const double r = __hiloint2double(hi, __double2loint(p));
+    return x < -707.0 ? 0.0 : r;
+}
+template <bool EXACT> __device__ __forceinline__ double exp_nonpos(double x) {
+#if HMC_FAST_EXP64
+    if constexpr (!EXACT) return exp_nonpos_fast(x);
+#endif
+    return exp(x);
+}
+
 template <int K> struct Emission<double, K> {
     double mu[K], isd[K], nrm[K];
     __device__ __forceinline__ void prepare(const double (&m)[K], const double (&sig2)[K]) {
@@ -66,16 +102,16 @@ template <int K> struct Emission<double, K> {
             nrm[s] = 0.3989422804014327 / sd;
         }
     }
-    __device__ __forceinline__ double eval(double y, double (&e)[K]) const {
+    template <bool EXACT = false> __device__ __forceinline__ double eval(double y, double (&e)[K]) const {
 #pragma unroll
-        for (int s = 0; s < K; ++s) { const double z = (y - mu[s]) * isd[s]; e[s] = exp(-0.5 * (z * z)) * nrm[s]; }
+        for (int s = 0; s < K; ++s) { const double z = (y - mu[s]) * isd[s]; e[s] = exp_nonpos<EXACT>(-0.5 * (z * z)) * nrm[s]; }
         return 0.0;
     }
     // signal rows: Normal(mu, (1+kappa) sd) (src/Hmc.jl:382); sw = +-1/(1+kappa) or 1 (the sign only flags a signal)
-    __device__ __forceinline__ void eval_scaled(double y, double sw, double (&e)[K]) const {
+    template <bool EXACT = false> __device__ __forceinline__ void eval_scaled(double y, double sw, double (&e)[K]) const {
         const double a = fabs(sw);
 #pragma unroll
-        for (int s = 0; s < K; ++s) { const double z = (y - mu[s]) * isd[s] * a; e[s] = exp(-0.5 * (z * z)) * (nrm[s] * a); }
+        for (int s = 0; s < K; ++s) { const double z = (y - mu[s]) * isd[s] * a; e[s] = exp_nonpos<EXACT>(-0.5 * (z * z)) * (nrm[s] * a); }
     }
 };
 

@@ -18,12 +18,24 @@ pytestmark = pytest.mark.gpu
 RTOL64, RTOL32 = 1e-5, 1e-3
 
 
-@pytest.fixture(autouse=True, params=["auto", "thread"])
+@pytest.fixture(autouse=True, params=["auto", "thread", "seg"])
 def _sweep_kernel_choice(request, monkeypatch):
     """Narrow batches (most tests) are served by the time-parallel warp-per-chain kernel; every test also runs with that
-    kernel disabled so that the thread-per-chain kernels see the same small, ragged cases."""
-    if request.param == "thread":
+    kernel disabled so that the thread-per-chain kernels see the same small, ragged cases, and once more with the
+    mid-width kernel forced (4 lanes per chain, one time segment each; it takes the plain sweep for K <= 4 — other
+    problems fall through to the thread-per-chain kernels as in production)."""
+    if request.param in ("thread", "seg"):
         monkeypatch.setenv("HMCGPU_SCAN_MAX_CHAINS", "0")
+        monkeypatch.setenv("HMCGPU_SEG_LANES", "4" if request.param == "seg" else "0")
+    return request.param
+
+
+def test_the_forced_sweep_kernel_is_the_one_that_ran(H, ctx, _sweep_kernel_choice):
+    """hmcgpu_result.sweep_kernel reports the plan's choice: the three runs of every test really exercise three kernels."""
+    y, _ = synth_hmm(80, **K3_TRUTH)
+    o = _run(H, ctx, y, [1, 3], [70, 77], K=3, n_chains=3, burnin=2, nrun=2, seed=1, horizons=(1,), precision=32, flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS)
+    assert o.sweep_kernel == {"auto": 1, "thread": 0, "seg": 4}[_sweep_kernel_choice]
+    assert H.binding.KERNEL_NAMES[o.sweep_kernel].startswith({"auto": "gibbs_scan", "thread": "gibbs_sweeps", "seg": "gibbs_seg"}[_sweep_kernel_choice])
 
 
 def test_native_library_is_loaded(H, ctx):
