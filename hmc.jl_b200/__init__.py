@@ -10,4 +10,4 @@ from .api import (EstOpt, estimatemodel, estimatesignals, estimate_windows, shar
                   signal_summaries, calcdispersion, calccorr, write_signal_summaries, write_dispersion,
                   makeparams_states, sample_and_forecast_all, saveinsampleforecasts, smoothStates, savesmoothresults)
 from .binding import (Context, HmcGpuError, Plan, ProblemSpec, estimate, estimate_multi, load, lib_path,  # noqa: F401
-                      FLAG_REF_Q1, FLAG_DRAWS, FLAG_SUMMARY, FLAG_SMOOTHED_MEAN, FLAG_LOGLIK, SYMBOLS)
+                      FLAG_REF_Q1, FLAG_DRAWS, FLAG_SUMMARY, FLAG_SMOOTHED_MEAN, FLAG_LOGLIK, FLAG_FILTERED_MEAN, SYMBOLS)

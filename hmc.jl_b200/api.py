@@ -354,8 +354,7 @@ def write_summaries(out, K: int, horizons: Sequence[int], dates: Sequence, direc
     return paths
 
 
-def forecastinsample(opt: EstOpt, horizon_index: int = -1, ctx: Optional[B.Context] = None, probabilities: str = "smoothed",
-                     max_draws: int = 2000, rng: Optional[np.random.Generator] = None):
+def forecastinsample(opt: EstOpt, horizon_index: int = -1, ctx: Optional[B.Context] = None, probabilities: str = "smoothed"):
     """GPU version of the reference's in-sample table (forecastinsample + saveinsampleforecasts, src/Hmc.jl:683-705;
     the reference's own function is stale/un-callable): one full-sample estimation, then per date t of the sample the
     posterior means of the h-step forecast p[j,t,:]' A_j^h mu_j, its error vs y[t+h], y[t], y[t+h] and the state
@@ -366,9 +365,9 @@ def forecastinsample(opt: EstOpt, horizon_index: int = -1, ctx: Optional[B.Conte
     probabilities="filtered": p = pif, the real-time probabilities P(X_t | y_1..t, θ_j).  This is what the reference's PUBLISHED
         table data/output/official_insample/forecats_insample.csv contains (its code state stored the filtered rows: the
         published s1..s3 agree with the posterior mean of pif to a median 5e-4 and are far from pib in mid-sample,
-        tests/test_oracle.py::test_golden_insample_table_is_filtered).  Computed from up to `max_draws` evenly thinned
-        parameter draws of the same estimation with the batched filter entry point (hmcgpu_filter, one launch per chunk);
-        ρ, which the sampler redraws from its flat prior every sweep (:350-356), is drawn the same way here."""
+        tests/test_oracle.py::test_golden_insample_table_is_filtered).  Accumulated on the device by the forward pass of the
+        same estimation call, over every saved draw (HMCGPU_FLAG_FILTERED_MEAN); ρ is the sampler's own draw of each sweep
+        (:350-356)."""
     if probabilities not in ("smoothed", "filtered"):
         raise ValueError("probabilities must be 'smoothed' or 'filtered'")
     own = ctx is None
@@ -377,33 +376,12 @@ def forecastinsample(opt: EstOpt, horizon_index: int = -1, ctx: Optional[B.Conte
     y = np.asarray(opt.rawdata, dtype=np.float64)
     h = list(opt.horizons)[horizon_index]
     try:
-        if probabilities == "smoothed":
-            spec = B.ProblemSpec(y, [sr[0]], [sr[-1]], K=opt.D, n_chains=opt.n_chains, burnin=opt.burnin, nrun=opt.Nrun,
-                                 seed=opt.seed, horizons=list(opt.horizons), precision=opt.precision,
-                                 flags=B.FLAG_REF_Q1 | B.FLAG_SMOOTHED_MEAN)
-            o = B.estimate(ctx, spec)
-            fc = o.insample_forecast_mean[0][:, horizon_index]
-            probs = o.pib_mean[0]
-        else:
-            spec = B.ProblemSpec(y, [sr[0]], [sr[-1]], K=opt.D, n_chains=opt.n_chains, burnin=opt.burnin, nrun=opt.Nrun,
-                                 seed=opt.seed, horizons=[h], precision=opt.precision, flags=B.FLAG_REF_Q1 | B.FLAG_DRAWS)
-            o = B.estimate(ctx, spec)
-            R = o.mu[0].shape[1]
-            pick = np.unique(np.linspace(0, R - 1, min(R, max_draws)).round().astype(np.int64))
-            mu, s2 = o.mu[0].T[pick], o.sigma2[0].T[pick]
-            A = np.transpose(o.A[0], (2, 1, 0))[pick]                      # stored [s][r][draw] -> (draw, r, s)
-            rng = rng or np.random.default_rng(opt.seed)
-            rho = rng.dirichlet(np.ones(opt.D), size=len(pick))
-            w = np.einsum("brs,bs->br", np.linalg.matrix_power(A, h), mu)   # A_j^h mu_j
-            yw = y[sr[0] - 1:sr[-1]]
-            probs, fc = np.zeros((len(yw), opt.D)), np.zeros(len(yw))
-            for c0 in range(0, len(pick), 256):                             # bounded host buffers: 256 draws x T x K per chunk
-                sl = slice(c0, c0 + 256)
-                pif = ctx.filter(yw, A[sl], mu[sl], s2[sl], rho[sl], precision=opt.precision, want_totals=False).pif
-                probs += pif.sum(0)
-                fc += np.einsum("btk,bk->t", pif, w[sl])
-            probs /= len(pick)
-            fc /= len(pick)
+        flag = B.FLAG_SMOOTHED_MEAN if probabilities == "smoothed" else B.FLAG_FILTERED_MEAN
+        spec = B.ProblemSpec(y, [sr[0]], [sr[-1]], K=opt.D, n_chains=opt.n_chains, burnin=opt.burnin, nrun=opt.Nrun,
+                             seed=opt.seed, horizons=list(opt.horizons), precision=opt.precision, flags=B.FLAG_REF_Q1 | flag)
+        o = B.estimate(ctx, spec)
+        fc = o.insample_forecast_mean[0][:, horizon_index]
+        probs = o.pib_mean[0]
     finally:
         if own:
             ctx.close()

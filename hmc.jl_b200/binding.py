@@ -17,6 +17,7 @@ FLAG_DRAWS = 2
 FLAG_SUMMARY = 4
 FLAG_SMOOTHED_MEAN = 8
 FLAG_LOGLIK = 16
+FLAG_FILTERED_MEAN = 64   # pib_mean / insample_forecast_mean carry the FILTERED means (the reference's published in-sample table)
 
 ERR_ARG, ERR_CUDA, ERR_ALLOC, ERR_UNSUPPORTED, ERR_NODEVICE = -1, -2, -3, -4, -5
 
@@ -285,7 +286,7 @@ class ProblemSpec:
             o.loglik = np.empty((nw, R)) if self.flags & FLAG_LOGLIK else None
         if self.flags & FLAG_SUMMARY:
             o.summary_mean = np.empty((nw, F)); o.summary_var = np.empty((nw, F))
-        if self.flags & FLAG_SMOOTHED_MEAN:
+        if self.flags & (FLAG_SMOOTHED_MEAN | FLAG_FILTERED_MEAN):
             o.pib_mean = np.empty(int(self.T.sum()) * K)
             o.insample_forecast_mean = np.empty(int(self.T.sum()) * nh) if nh else None
         res = Result(_p(o.mu), _p(o.sigma2), _p(o.A), _p(o.pi_end), _p(o.forecasts), _p(o.loglik), _p(o.summary_mean),

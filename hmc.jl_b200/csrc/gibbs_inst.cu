@@ -15,7 +15,9 @@ namespace hmc {
 // calls f(kernel) with the variant the flags / window length select
 template <typename R, int K, bool WIDE, typename F> static auto with_variant(const GibbsLaunch& cfg, F f) {
     const bool smooth = cfg.flags & 8u /*HMCGPU_FLAG_SMOOTHED_MEAN*/, ll = cfg.flags & 16u /*HMCGPU_FLAG_LOGLIK*/;
-    if constexpr (K > 4) {   // K = 5..8: the plain sweep only (the host rejects smoothed means / signals for K > 4)
+    if constexpr (K > 4) {   // K = 5..8: the plain sweep and the smoothed means (the host rejects signals for K > 4)
+        if (smooth && ll) return f(gibbs_sweeps_kernel<R, K, true, true, WIDE>);
+        if (smooth) return f(gibbs_sweeps_kernel<R, K, true, false, WIDE>);
         if (ll) return f(gibbs_sweeps_kernel<R, K, false, true, WIDE>);
         return f(gibbs_sweeps_kernel<R, K, false, false, WIDE>);
     } else {
@@ -49,7 +51,7 @@ template <typename R, int K> cudaError_t launch_gibbs(const GibbsLaunch& cfg, co
         kern<<<grid, kGibbsThreads, smem, st>>>(a);
         return cudaGetLastError();
     };
-    const bool smooth = cfg.flags & 8u;
+    const bool smooth = cfg.flags & (8u | 64u);   // smoothed or filtered means: the A^h mu vectors of the in-sample forecasts live in shared memory
     const bool wr = K > 4 || wide_rows<K>(cfg);
     const size_t smem = wr ? gibbs_smem_bytes<R, K, true>(smooth, cfg.n_h) : gibbs_smem_bytes<R, K, false>(smooth, cfg.n_h);
     return with_rows<R, K>(cfg, [&](auto kern) { return go(kern, smem); });
@@ -62,7 +64,7 @@ template <typename R, int K> int gibbs_capacity_warps(const GibbsLaunch& cfg) {
         return per_sm * cfg.sm_count * (kGibbsThreads / 32);
     };
     const bool wr = K > 4 || wide_rows<K>(cfg);
-    const size_t smem = wr ? gibbs_smem_bytes<R, K, true>(cfg.flags & 8u, cfg.n_h) : gibbs_smem_bytes<R, K, false>(cfg.flags & 8u, cfg.n_h);
+    const size_t smem = wr ? gibbs_smem_bytes<R, K, true>(cfg.flags & (8u | 64u), cfg.n_h) : gibbs_smem_bytes<R, K, false>(cfg.flags & (8u | 64u), cfg.n_h);
     return with_rows<R, K>(cfg, [&](auto kern) { return q(kern, smem); });
 }
 

@@ -388,7 +388,9 @@ struct GibbsWarp {
     // allocation, and the per-sweep state of the caller is saved around the call instead of squeezing the hot loops.
     struct Vec { R v[K]; };
     struct FwdOut { Vec pf; R ll; int events; };
-    template <bool RAGGED, bool CHECKED, bool STREAM = false>
+    // FACC (HMCGPU_FLAG_FILTERED_MEAN, a saved draw): every filtered row is also added to the per-date sums (sorted labels) and
+    // its forecasts pif[t,:]' A^h mu to the in-sample forecast sums — the table the reference published (forecats_insample.csv).
+    template <bool RAGGED, bool CHECKED, bool STREAM = false, bool FACC = false>
     static __device__ HMC_FWD_ATTR FwdOut forward_pass(const Chain ch, const Emission<R, K> em, const Vec rho_in) {
         FwdOut o;
         R (&pf)[K] = o.pf.v;
@@ -503,6 +505,12 @@ struct GibbsWarp {
                 }
 #pragma unroll
                 for (int s = 0; s < K; ++s) buf[u][s] = pf[s];
+                if constexpr (FACC) {
+                    R* pap = ch.pacc0 + (size_t)j * K * 32;
+#pragma unroll
+                    for (int s = 0; s < K; ++s) st_stream(pap + ch.rank[s] * 32, ld_stream(pap + ch.rank[s] * 32) + pf[s]);
+                    insample_accumulate(ch, pf, ch.facc0 + (size_t)j * ch.n_hi * 32);
+                }
             }
         };
         auto store_tile = [&]() {
@@ -791,13 +799,15 @@ struct GibbsWarp {
         ch.off = ch.Tw - ch.T;
         ch.yld = a.yld;
         ch.pi0 = reinterpret_cast<R*>(a.pi) + a.warp_pi_off[warp] + lane * 4;
-        ch.pacc0 = SMOOTH ? reinterpret_cast<R*>(a.pib_acc) + a.warp_pi_off[warp] + lane : nullptr;
-        ch.n_hi = (SMOOTH && a.fc_acc) ? a.n_h : 0;
+        const bool filt = !SMOOTH && (a.flags & 64u /*HMCGPU_FLAG_FILTERED_MEAN*/) != 0u;   // filtered means: accumulated by the forward pass
+        const bool accum = SMOOTH || filt;
+        ch.pacc0 = accum ? reinterpret_cast<R*>(a.pib_acc) + a.warp_pi_off[warp] + lane : nullptr;
+        ch.n_hi = (accum && a.fc_acc) ? a.n_h : 0;
         ch.facc0 = ch.n_hi ? reinterpret_cast<R*>(a.fc_acc) + a.warp_pi_off[warp] / K * ch.n_hi + lane : nullptr;
         ch.mh_off = (unsigned)(gibbs_smem_bytes<R, K, WIDE>(false, 0) + threadIdx.x * sizeof(R));
         // realised future observations of this chain (forecast errors), cached once per launch: yf[j*threads + tid] for the
         // j-th sorted horizon — the per-draw global loads sat in front of every forecast store
-        const unsigned yf_off = (unsigned)(gibbs_smem_bytes<R, K, WIDE>(false, 0) + (SMOOTH ? sizeof(R) * (size_t)a.n_h * K * kGibbsThreads : 0)
+        const unsigned yf_off = (unsigned)(gibbs_smem_bytes<R, K, WIDE>(false, 0) + (accum ? sizeof(R) * (size_t)a.n_h * K * kGibbsThreads : 0)
                                            + threadIdx.x * sizeof(R));
         {
             R* yf = reinterpret_cast<R*>(smem_base() + yf_off);
@@ -860,6 +870,35 @@ struct GibbsWarp {
             for (int i = 0; i < K; ++i) hp.beta[i] = (R)(gs == 0 ? a.beta0[i] : a.beta[i]);
             events += draw_params<R, K, SIG>(cnt, Sd, Qd, trans, ch.c, hp, key, sweep, sig2, mu, rho, ch.A, &sg);
 
+            // ---- relabelling ranks (:501) and whether this sweep is a saved draw: both passes need them
+            ranks_of<R, K>(mu, ch.rank);
+            const long long draw_idx = gs - a.burnin;
+            const bool save = (draw_idx >= 0) && (T > 0);
+            if (accum && save && ch.n_hi > 0) {
+                // A^h mu for every requested horizon (chain labels), read back by the in-sample forecasts of the backward (SMOOTH) or forward (filtered means) pass
+                R* mh = reinterpret_cast<R*>(smem_base() + ch.mh_off);
+                R v[K];
+#pragma unroll
+                for (int s = 0; s < K; ++s) v[s] = mu[s];
+                int h = 0;
+                for (int j = 0; j < a.n_h; ++j) {
+                    for (; h < a.h_sorted[j]; ++h) {
+                        R nv[K];
+#pragma unroll
+                        for (int r = 0; r < K; ++r) {
+                            R acc = ch.A[r][0] * v[0];
+#pragma unroll
+                            for (int s = 1; s < K; ++s) acc = fma(ch.A[r][s], v[s], acc);
+                            nv[r] = acc;
+                        }
+#pragma unroll
+                        for (int s = 0; s < K; ++s) v[s] = nv[s];
+                    }
+#pragma unroll
+                    for (int s = 0; s < K; ++s) mh[(a.h_slot[j] * K + s) * kGibbsThreads] = v[s];
+                }
+            }
+
             // ---- 2. forward filter
             Emission<R, K> em;
             em.prepare(mu, sig2);
@@ -868,13 +907,23 @@ struct GibbsWarp {
                 Vec rv;
 #pragma unroll
                 for (int s = 0; s < K; ++s) rv.v[s] = rho[s];
-                FwdOut fo = stream_y ? (ch.rag_rows > 0 ? forward_pass<true, false, true>(ch, em, rv) : forward_pass<false, false, true>(ch, em, rv))
-                                     : (ch.rag_rows > 0 ? forward_pass<true, false>(ch, em, rv) : forward_pass<false, false>(ch, em, rv));
+                FwdOut fo;
+                bool facc_done = false;
+                if constexpr (!SMOOTH && !SIG) {
+                    if (filt && save) {                              // (warp-uniform up to padding lanes, whose T = 0 keeps them out of every row)
+                        // (the per-step checked form: a row that would be NaN must never reach the sums, so there is no re-run)
+                        fo = stream_y ? forward_pass<true, true, true, true>(ch, em, rv) : forward_pass<true, true, false, true>(ch, em, rv);
+                        facc_done = true;
+                    }
+                }
+                if (!facc_done)
+                    fo = stream_y ? (ch.rag_rows > 0 ? forward_pass<true, false, true>(ch, em, rv) : forward_pass<false, false, true>(ch, em, rv))
+                                  : (ch.rag_rows > 0 ? forward_pass<true, false>(ch, em, rv) : forward_pass<false, false>(ch, em, rv));
                 R chk = fo.pf.v[0];
 #pragma unroll
                 for (int s = 1; s < K; ++s) chk += fo.pf.v[s];
                 // a zero / non-finite normaliser anywhere leaves a NaN in the last row: redo the pass with per-step handling
-                if (__builtin_expect(T > 0 && !(chk > R(0.5) && chk < R(2)), 0)) fo = forward_pass<true, true>(ch, em, rv);
+                if (__builtin_expect(!facc_done && T > 0 && !(chk > R(0.5) && chk < R(2)), 0)) fo = forward_pass<true, true>(ch, em, rv);
 #pragma unroll
                 for (int s = 0; s < K; ++s) pf[s] = fo.pf.v[s];
                 ll = fo.ll;
@@ -883,9 +932,6 @@ struct GibbsWarp {
             // pf now holds pif[T,:] in chain labels
 
             // ---- 3. relabel (:501-513) and emit the draw in increasing-μ order
-            ranks_of<R, K>(mu, ch.rank);
-            const long long draw_idx = gs - a.burnin;
-            const bool save = (draw_idx >= 0) && (T > 0);
             if (save) {
                 const size_t i = (size_t)(draw_idx - a.draw0);
                 const size_t cs = (size_t)a.chunk * ns;             // stride between fields
@@ -928,30 +974,6 @@ struct GibbsWarp {
                 if (LOGLIK) o[(size_t)(f0 + 2 * a.n_h) * cs] = ll;
             }
 
-            if (SMOOTH && save && ch.n_hi > 0) {
-                // A^h mu for every requested horizon (chain labels), read back by the in-sample forecasts of the backward pass
-                R* mh = reinterpret_cast<R*>(smem_base() + ch.mh_off);
-                R v[K];
-#pragma unroll
-                for (int s = 0; s < K; ++s) v[s] = mu[s];
-                int h = 0;
-                for (int j = 0; j < a.n_h; ++j) {
-                    for (; h < a.h_sorted[j]; ++h) {
-                        R nv[K];
-#pragma unroll
-                        for (int r = 0; r < K; ++r) {
-                            R acc = ch.A[r][0] * v[0];
-#pragma unroll
-                            for (int s = 1; s < K; ++s) acc = fma(ch.A[r][s], v[s], acc);
-                            nv[r] = acc;
-                        }
-#pragma unroll
-                        for (int s = 0; s < K; ++s) v[s] = nv[s];
-                    }
-#pragma unroll
-                    for (int s = 0; s < K; ++s) mh[(a.h_slot[j] * K + s) * kGibbsThreads] = v[s];
-                }
-            }
 
             // ---- 4. backward pass
             Back b;

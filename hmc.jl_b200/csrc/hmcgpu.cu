@@ -1135,8 +1135,20 @@ static int validate_problem(hmcgpu_ctx* ctx, const hmcgpu_problem* p) {
     if (!p->y || p->y_len < 2 || p->n_series < 1) return fail(ctx, HMCGPU_ERR_ARG, "empty series");
     if (p->n_windows < 1 || !p->win_start || !p->win_end) return fail(ctx, HMCGPU_ERR_ARG, "no windows");
     if (!k_supported(p->K)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "K=%d not supported (2..32)", p->K);
-    if (!k_thread(p->K) && (p->flags & HMCGPU_FLAG_SMOOTHED_MEAN))
-        return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "smoothed means are only implemented for K <= 4");
+    if (!k_thread_sweep(p->K) && (p->flags & HMCGPU_FLAG_SMOOTHED_MEAN))
+        return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "smoothed means are only implemented for K <= 8 (thread-per-chain kernels)");
+    if (p->K > 4 && (p->flags & (HMCGPU_FLAG_SMOOTHED_MEAN | HMCGPU_FLAG_FILTERED_MEAN)) && p->n_h > 0) {
+        // the A^h mu vectors of the in-sample forecasts live in shared memory next to the selection tables and the rings
+        const size_t b = p->precision / 8;
+        const size_t need = (size_t)(p->K * b + 8 + 15) / 16 * 16 * p->K * 128 + b * 4 * 3 * 4 * p->K * 32 + b * (size_t)p->n_h * (p->K + 1) * 128;
+        if (need > 200 * 1024)
+            return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "K=%d with %d in-sample forecast horizons needs %zu KB of shared memory per block: use fewer horizons", p->K, p->n_h, need / 1024);
+    }
+    if (p->flags & HMCGPU_FLAG_FILTERED_MEAN) {
+        if (!k_thread_sweep(p->K)) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "filtered means are only implemented for K <= 8");
+        if (p->flags & HMCGPU_FLAG_SMOOTHED_MEAN) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "HMCGPU_FLAG_FILTERED_MEAN and HMCGPU_FLAG_SMOOTHED_MEAN share their output arrays: one per call");
+        if (p->is_signal || p->pi_row_back != 0) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "is_signal / pi_row_back cannot be combined with HMCGPU_FLAG_FILTERED_MEAN");
+    }
     if (p->n_chains < 1) return fail(ctx, HMCGPU_ERR_ARG, "n_chains < 1");
     // chain slots are indexed with 32-bit ints (padded to a multiple of 64); the Philox chain id is 32 bits as well
     if ((long long)p->n_windows * p->n_chains > 0x7fffffffLL - 64)
@@ -1212,7 +1224,8 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     // 64 for the fp32 paired kernel, which needs an even number of chains per window so that a pair shares its window)
     pl->wide = !k_thread_sweep(K);
     pl->sig = p->is_signal != nullptr || p->pi_row_back != 0;
-    pl->pair = !pl->wide && K <= 4 && !pl->sig && p->precision == 32 && nc % 2 == 0 && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN);
+    const unsigned kAccMean = HMCGPU_FLAG_SMOOTHED_MEAN | HMCGPU_FLAG_FILTERED_MEAN;   // per-date means: thread-per-chain kernels only
+    pl->pair = !pl->wide && K <= 4 && !pl->sig && p->precision == 32 && nc % 2 == 0 && !(p->flags & kAccMean);
     // Two chains per thread cut the instruction count by 30 % but need 168 registers (12 warps per SM): measured slower
     // than the scalar kernel unless the batch is far wider than the machine, so it is opt-in.
     {
@@ -1233,7 +1246,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         const size_t wb = (size_t)(p->precision / 8) * ((size_t)pl->max_T * (K + 1) + 4 * K);
         const long long blocks = std::max<long long>(1, std::min<long long>(5, (long long)((227 * 1024) / (4 * wb + 1024))));
         lim = lim * blocks / 5;
-        pl->scan = !pl->wide && K <= 4 && !pl->pair && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN) &&
+        pl->scan = !pl->wide && K <= 4 && !pl->pair && !(p->flags & kAccMean) &&
                    (long long)nw * nc <= lim && pl->max_T <= tmax;
     }
     const long long n_real = (long long)nw * nc;
@@ -1242,7 +1255,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     // warps; HMCGPU_SEG_LANES forces it (0 = never).  K <= 4, plain sweep.
     {
         int lanes = 0;
-        if (!pl->wide && K <= 4 && !pl->sig && !pl->pair && !pl->scan && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN)) {
+        if (!pl->wide && K <= 4 && !pl->sig && !pl->pair && !pl->scan && !(p->flags & kAccMean)) {
             // measured on C2 (500 windows x c chains, B200): 4 lanes per chain are best up to ~38 000 chains, 2 lanes up to ~90 000,
             // the thread-per-chain kernel beyond; in units of one wave of thread slots (16 warps per SM):
             const long long full = (long long)ctx->sm_count * 16 * 32;
@@ -1316,7 +1329,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     if (const char* e = getenv("HMCGPU_GROUPS")) pl->n_groups = std::max(1, std::min(8, atoi(e)));
     pl->n_groups = std::min(pl->n_groups, n_warps);
     // double-buffered draw chunks let the groups drift apart (not with the smoothing accumulators, which are shared)
-    pl->n_bufs = (pl->n_groups > 1 && !(p->flags & HMCGPU_FLAG_SMOOTHED_MEAN)) ? 2 : 1;
+    pl->n_bufs = (pl->n_groups > 1 && !(p->flags & kAccMean)) ? 2 : 1;
     // chunk of draws per buffer: bound the chunk buffers to ~2 GiB in total
     const size_t per_draw = (size_t)pl->F * n_slots * sizeof(R);
     long long chunk = std::max<long long>(1, (long long)((2ull << 30) / pl->n_bufs / per_draw));
@@ -1402,7 +1415,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         CU(ctx, pl->d_sum.alloc((size_t)nw * pl->F * sizeof(double)));
         CU(ctx, pl->d_sumsq.alloc((size_t)nw * pl->F * sizeof(double)));
     }
-    if (p->flags & HMCGPU_FLAG_SMOOTHED_MEAN) {
+    if (p->flags & kAccMean) {
         CU(ctx, pl->pacc.alloc((size_t)pi_elems * sizeof(R)));
         if (p->n_h > 0) {
             CU(ctx, pl->facc.alloc((size_t)pi_elems / K * p->n_h * sizeof(R)));
@@ -1552,7 +1565,7 @@ static int plan_run_t(hmcgpu_plan* pl) {
             CU(ctx, cudaGetLastError());
             ++pl->n_launches;
         }
-        if (pl->flags & HMCGPU_FLAG_SMOOTHED_MEAN) {
+        if (pl->flags & (HMCGPU_FLAG_SMOOTHED_MEAN | HMCGPU_FLAG_FILTERED_MEAN)) {
             tile_reduce_kernel<R><<<pl->n_windows, 256, 0, st>>>(Kr, Kr, pl->n_chains, pl->win_slot0.as<int>(), pl->wTd.as<int>(),
                                                                  pl->warp_pi_off.as<long long>(), pl->warp_T.as<int>(), pl->win_pib_off.as<long long>(),
                                                                  pl->pacc.as<R>(), pl->d_pibsum.as<double>());
@@ -1729,8 +1742,8 @@ static int plan_fetch_impl(hmcgpu_plan* pl, hmcgpu_result* r) {
         return fail(ctx, HMCGPU_ERR_ARG, "per-draw outputs requested without HMCGPU_FLAG_DRAWS");
     if ((r->summary_mean || r->summary_var) && !(pl->flags & HMCGPU_FLAG_SUMMARY))
         return fail(ctx, HMCGPU_ERR_ARG, "summary requested without HMCGPU_FLAG_SUMMARY");
-    if ((r->pib_mean || r->insample_forecast_mean) && !(pl->flags & HMCGPU_FLAG_SMOOTHED_MEAN))
-        return fail(ctx, HMCGPU_ERR_ARG, "pib_mean / insample_forecast_mean requested without HMCGPU_FLAG_SMOOTHED_MEAN");
+    if ((r->pib_mean || r->insample_forecast_mean) && !(pl->flags & (HMCGPU_FLAG_SMOOTHED_MEAN | HMCGPU_FLAG_FILTERED_MEAN)))
+        return fail(ctx, HMCGPU_ERR_ARG, "pib_mean / insample_forecast_mean requested without HMCGPU_FLAG_SMOOTHED_MEAN or HMCGPU_FLAG_FILTERED_MEAN");
     if (r->loglik && !(pl->flags & HMCGPU_FLAG_LOGLIK)) return fail(ctx, HMCGPU_ERR_ARG, "loglik requested without HMCGPU_FLAG_LOGLIK");
     CU(ctx, down(r->mu, pl->d_mu, nw * Rr * K * sizeof(double)));
     CU(ctx, down(r->sigma2, pl->d_sig2, nw * Rr * K * sizeof(double)));

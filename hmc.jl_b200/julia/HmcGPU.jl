@@ -24,6 +24,7 @@ const FLAG_REF_Q1 = UInt32(1)
 const FLAG_DRAWS = UInt32(2)
 const FLAG_SUMMARY = UInt32(4)
 const FLAG_SMOOTHED_MEAN = UInt32(8)
+const FLAG_FILTERED_MEAN = UInt32(64)
 const FLAG_LOGLIK = UInt32(16)
 
 # struct hmcgpu_problem (include/hmcgpu.h)

@@ -53,6 +53,9 @@ extern "C" {
 #define HMCGPU_FLAG_SUMMARY 4u       /* fill per-window posterior mean / variance (pooled over chains and draws) */
 #define HMCGPU_FLAG_SMOOTHED_MEAN 8u /* fill pib_mean: posterior mean of the smoothed state probabilities */
 #define HMCGPU_FLAG_LOGLIK 16u       /* compute the per-draw log-likelihood sum_t log(total_t) */
+#define HMCGPU_FLAG_FILTERED_MEAN 64u /* fill pib_mean / insample_forecast_mean with the posterior means of the FILTERED state
+                                        probabilities pif[t,:] and of pif[t,:]' A^h mu (what the reference's published in-sample table
+                                        data/output/official_insample/forecats_insample.csv holds); K <= 8, not with SMOOTHED_MEAN or signals */
 
 typedef struct hmcgpu_ctx hmcgpu_ctx;
 typedef struct hmcgpu_plan hmcgpu_plan;

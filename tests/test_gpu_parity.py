@@ -505,8 +505,8 @@ def test_error_paths(H, ctx):
     with pytest.raises(H.HmcGpuError) as e:
         _run(H, ctx, y, [1], [40], K=40)
     assert e.value.code == -4
-    with pytest.raises(H.HmcGpuError) as e:          # smoothing accumulators exist for the thread-per-chain kernels only
-        _run(H, ctx, y, [1], [40], K=8, flags=H.FLAG_SMOOTHED_MEAN)
+    with pytest.raises(H.HmcGpuError) as e:          # smoothing accumulators exist for the thread-per-chain kernels only (K <= 8)
+        _run(H, ctx, y, [1], [40], K=12, flags=H.FLAG_SMOOTHED_MEAN)
     assert e.value.code == -4
     with pytest.raises(H.HmcGpuError):
         _run(H, ctx, y, [10], [10], K=3)
@@ -642,19 +642,21 @@ def test_lane_kernel_fp32_posterior_and_loglik(H, ctx, oracle, K):
         assert abs(o.loglik[0][d] - lls[0]) < 6.0
 
 
-def test_insample_forecast_means(H, ctx, oracle):
+@pytest.mark.parametrize("K", [3, 5, 8])
+def test_insample_forecast_means(H, ctx, oracle, K):
     """forecastinsample (src/Hmc.jl:683-699): per-date posterior mean of pib[j,t,:]' A_j^h mu_j.  fp64 device chain vs the
-    oracle chain on the same Philox streams (pib_full + per-draw mu, A from the oracle), plus an fp32 Monte-Carlo check."""
-    y, _ = synth_hmm(172, **K3_TRUTH)
+    oracle chain on the same Philox streams (pib_full + per-draw mu, A from the oracle), plus an fp32 Monte-Carlo check.
+    K = 5 and 8: the smoothed means of the thread-per-chain kernels with flushed transition counters (:442-457 has no K limit)."""
+    y, _ = synth_hmm(172, **(K3_TRUTH if K == 3 else _truth(K)))
     hs = (1, 12)
     wins = ((1, 160), (5, 140))
-    o = _run(H, ctx, y, [w[0] for w in wins], [w[1] for w in wins], K=3, n_chains=2, burnin=2, nrun=5, seed=11, horizons=hs,
+    o = _run(H, ctx, y, [w[0] for w in wins], [w[1] for w in wins], K=K, n_chains=2, burnin=2, nrun=5, seed=11, horizons=hs,
              precision=64, flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_SMOOTHED_MEAN)
     for w, (s, e) in enumerate(wins):
         n = e - s + 1
-        ref_fc, ref_pib = np.zeros((n, len(hs))), np.zeros((n, 3))
+        ref_fc, ref_pib = np.zeros((n, len(hs))), np.zeros((n, K))
         for c in range(2):
-            r = oracle.gibbs(y[s - 1:e], 3, 2, 5, seed=11, chain=w * 2 + c, horizons=hs, y_future=[y[e - 1 + h] for h in hs],
+            r = oracle.gibbs(y[s - 1:e], K, 2, 5, seed=11, chain=w * 2 + c, horizons=hs, y_future=[y[e - 1 + h] for h in hs],
                              flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM, want_pib_full=True)
             for j in range(5):
                 for k, h in enumerate(hs):
@@ -674,16 +676,46 @@ def test_insample_forecast_means(H, ctx, oracle):
     np.testing.assert_allclose(a.insample_forecast_mean[0][-1], a.summary_mean[0][18:22:2], rtol=1e-4)
 
 
+def test_filtered_mean_accumulator_matches_the_filter_entry_point(H, ctx):
+    """HMCGPU_FLAG_FILTERED_MEAN against hmcgpu_filter on the SAME parameter draws (FLAG_DRAWS of the same call): the device sums
+    must equal the mean over draws of the filtered rows up to the flat-prior rho the sampler redraws every sweep (:350-356; it
+    only touches the first few rows), and the forecast sums the mean of pif' A^h mu.  K = 3 and K = 5, fp64 and fp32."""
+    for K, prec, tol in ((3, 64, 1e-9), (3, 32, 2e-4), (5, 64, 1e-9)):
+        tr = K3_TRUTH if K == 3 else _truth(K)
+        y, _ = synth_hmm(180, seed=4 + K, **tr)
+        hs = (1, 12)
+        o = _run(H, ctx, y, [1, 11], [160, 150], K=K, n_chains=3, burnin=40, nrun=30, seed=3, horizons=hs, precision=prec,
+                 flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_FILTERED_MEAN)
+        assert o.events == 0
+        for w, (s, e) in enumerate(((1, 160), (11, 150))):
+            yw = y[s - 1:e]
+            mu, s2 = o.mu[w].T, o.sigma2[w].T
+            A = np.transpose(o.A[w], (2, 1, 0))
+            R = len(mu)
+            rho = np.full((R, K), 1.0 / K)
+            pif = ctx.filter(yw, A, mu, s2, rho, precision=64, want_totals=False).pif            # [R, T, K], states already sorted
+            skip = 60                                                                             # rows where the sampler's random rho still matters
+            np.testing.assert_allclose(o.pib_mean[w][skip:], pif.mean(0)[skip:], atol=max(tol, 1e-6), rtol=0)
+            np.testing.assert_allclose(o.pib_mean[w].sum(1), 1.0, atol=1e-5)
+            for k, h in enumerate(hs):
+                wv = np.einsum("brs,bs->br", np.linalg.matrix_power(A, h), mu)
+                f = np.einsum("btk,bk->t", pif, wv) / R
+                np.testing.assert_allclose(o.insample_forecast_mean[w][skip:, k], f[skip:], atol=max(10 * tol, 1e-5), rtol=0)
+    with pytest.raises(H.HmcGpuError):
+        _run(H, ctx, y, [1], [100], K=3, n_chains=1, burnin=1, nrun=1, flags=H.FLAG_FILTERED_MEAN | H.FLAG_SMOOTHED_MEAN)
+
+
 def test_insample_filtered_table_matches_reference_publication(H, ctx):
-    """forecastinsample(probabilities="filtered") on the GPU (one estimation with draws + batched hmcgpu_filter over the thinned
-    draws) against the reference's published in-sample table, data/output/official_insample/forecats_insample.csv: its
-    s1..s3 are posterior means of the filtered probabilities (tests/test_oracle.py::test_golden_insample_table_is_filtered)."""
+    """forecastinsample(probabilities="filtered") on the GPU — ONE hmcgpu_estimate call whose forward pass accumulates the filtered
+    rows and their forecasts over every saved draw (HMCGPU_FLAG_FILTERED_MEAN) — against the reference's published in-sample
+    table, data/output/official_insample/forecats_insample.csv: its s1..s3 are posterior means of the filtered probabilities
+    (tests/test_oracle.py::test_golden_insample_table_is_filtered)."""
     y, dates = load_inflation()
     g = json.load(open(os.path.join(GOLDEN, "official_insample.json")))
     N = g["last_index"]
     opt = H.EstOpt(y, dates, sampleRange=range(1, N + 1), endIndex=N, horizons=[12], D=3, burnin=2000, Nrun=1500, n_chains=8,
                    precision=32)
-    t = H.forecastinsample(opt, ctx=ctx, probabilities="filtered", max_draws=2000)
+    t = H.forecastinsample(opt, ctx=ctx, probabilities="filtered")
     p = np.stack([t["s1"], t["s2"], t["s3"]], axis=1)
     np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-5)
     d = np.abs(p - np.array(g["probs"])).max(1)

@@ -79,7 +79,7 @@ def test_flag_and_error_constants_match_header(H):
     header = open(os.path.join(ROOT, "include", "hmcgpu.h")).read()
     jl = open(os.path.join(ROOT, "hmc.jl_b200", "julia", "HmcGPU.jl")).read()
     defs = {k: int(v) for k, v in re.findall(r"#define HMCGPU_((?:FLAG|ERR)_\w+) \(?(-?\d+)u?\)?", header)}
-    assert len(defs) == 10
+    assert len(defs) == 11
     for k, v in defs.items():
         assert getattr(B, k) == v, k
         if k.startswith("FLAG_"):
@@ -294,9 +294,10 @@ def test_insample_and_smoothed_writers_use_the_reference_headers(H, tmp_path):
 
 
 def test_forecastinsample_filtered_host_logic(H, oracle, monkeypatch):
-    """Host side of forecastinsample(probabilities="filtered") — draw thinning, layouts, A^h mu weights, chunked filter calls,
-    table columns — with the two C-ABI calls it makes replaced by oracle-backed stand-ins (no GPU here); the result is
-    checked against the reference's published in-sample table.  The GPU run of the same function is a -m gpu test."""
+    """Host side of forecastinsample(probabilities="filtered"): one estimation call with HMCGPU_FLAG_FILTERED_MEAN, whose per-date
+    means become the table.  The C-ABI call is replaced by an oracle-backed stand-in (no GPU here) that produces what the device
+    accumulates — the mean over the saved draws of pif[t,:] and of pif[t,:]' A^12 mu — and the table is checked against the
+    reference's published in-sample table.  The GPU run of the same function is a -m gpu test."""
     import json
     from types import SimpleNamespace
     from conftest import load_inflation
@@ -306,26 +307,28 @@ def test_forecastinsample_filtered_host_logic(H, oracle, monkeypatch):
     N = g["last_index"]
 
     def fake_estimate(ctx, spec):
-        assert spec.flags & B.FLAG_DRAWS and list(spec.horizons) == [12] and spec.win_end[0] == N
+        assert spec.flags & B.FLAG_FILTERED_MEAN and not spec.flags & B.FLAG_SMOOTHED_MEAN and list(spec.horizons) == [12] and spec.win_end[0] == N
         outs, _ = oracle.gibbs_batch([dict(y=spec.y[0, :N], K=spec.K, burnin=spec.burnin, nrun=spec.nrun, seed=spec.seed, chain=c,
                                            horizons=(12,), y_future=[spec.y[0, N - 1 + 12]]) for c in range(spec.n_chains)])
         cat = lambda k: np.concatenate([getattr(o, k) for o in outs])
-        return SimpleNamespace(mu=[cat("mu").T], sigma2=[cat("sigma2").T], A=[np.transpose(cat("A"), (2, 1, 0))], events=0)
-
-    calls = []
+        mu, s2, A = cat("mu"), cat("sigma2"), cat("A")
+        pick = np.linspace(0, len(mu) - 1, 300).round().astype(np.int64)                 # a thinned sample of the draws keeps the CPU test short
+        rng = np.random.default_rng(0)
+        probs, fc = np.zeros((N, spec.K)), np.zeros(N)
+        for j in pick:
+            pif = oracle.forward(spec.y[0, :N], A[j], mu[j], s2[j], rng.dirichlet(np.ones(spec.K)), want_Pf=False).pif
+            probs += pif
+            fc += pif @ (np.linalg.matrix_power(A[j], 12) @ mu[j])
+        return SimpleNamespace(pib_mean=[probs / len(pick)], insample_forecast_mean=[(fc / len(pick))[:, None]], events=0)
 
     class FakeCtx:
-        def filter(self, yw, A, mu, s2, rho, precision=64, want_totals=True):
-            calls.append(len(mu))
-            return SimpleNamespace(pif=np.stack([oracle.forward(yw, A[b], mu[b], s2[b], rho[b], want_Pf=False).pif for b in range(len(mu))]))
-
         def close(self):
             pass
 
     monkeypatch.setattr(B, "estimate", fake_estimate)
     opt = H.EstOpt(y, dates, sampleRange=range(1, N + 1), endIndex=N, horizons=[12], D=3, burnin=1500, Nrun=1500, n_chains=2)
-    t = H.forecastinsample(opt, ctx=FakeCtx(), probabilities="filtered", max_draws=300)
-    assert calls == [256, 44] and t["date"][0] == dates[0] and len(t["forecast"]) == N
+    t = H.forecastinsample(opt, ctx=FakeCtx(), probabilities="filtered")
+    assert t["date"][0] == dates[0] and len(t["forecast"]) == N
     p = np.stack([t["s1"], t["s2"], t["s3"]], axis=1)
     np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-9)
     d = np.abs(p - np.array(g["probs"])).max(1)
