@@ -176,6 +176,7 @@ struct GibbsArgs {
     const int* totM;             // [n_slots] number of signals in the window
     double kappa;
     int pi_back;                 // the pi_end field of a draw is the smoothed marginal pib[N - pi_back, :] (:893); 0 = last row
+    int all_signal;              // every time step of every series is a signal (the 'make everything a signal' runs, code/run_hmm.jl:160-176)
     // ---- segment kernel (gibbs_seg_kernel.cuh)
     int seg_warm;                // warm-up time steps in front of a segment
     int seg_barriers;            // block-wide phase barriers per sweep (0, 1: before the filter, 2: also before the sampler)
@@ -287,6 +288,8 @@ struct GibbsWarp {
 
     // book-keeping after X_t was drawn (one-hot in lt): transition x_t -> x_{t+1}, statistics, and the selections
     // the next (earlier) step needs
+    // (ALLSIG: every time step of the batch is a signal — the observation statistics are not kept at all)
+    template <bool ALLSIG = false>
     static __device__ __forceinline__ void commit(Back& b, const Chain& ch, const bool (&lt)[K - 1], const R (&pt)[K], R yt, R sw, bool first) {
         if (!first) {
 #pragma unroll
@@ -295,14 +298,16 @@ struct GibbsWarp {
         const R d = yt - ch.c, dd = d * d;
         bool obs = true;
         if constexpr (SIG) {                                       // signals keep their own statistics (:267-300)
-            obs = !(sw < R(0));
+            obs = ALLSIG ? false : !(sw < R(0));
 #pragma unroll
             for (int i = 0; i < K - 1; ++i)
                 if (!obs && is_state(lt, i)) { b.Sm[i] += d; b.Qm[i] += dd; b.Mi[i] += 1; }
         }
+        if constexpr (!(SIG && ALLSIG)) {
 #pragma unroll
-        for (int i = 0; i < K - 1; ++i)
-            if (obs && is_state(lt, i)) { b.Sd[i] += d; b.Qd[i] += dd; }
+            for (int i = 0; i < K - 1; ++i)
+                if (obs && is_state(lt, i)) { b.Sd[i] += d; b.Qd[i] += dd; }
+        }
         select_later(b, ch, lt, pt);
     }
     // what the next (earlier) step needs once this step's state (one-hot in lt) is known: column x of A, the packed-counter
@@ -344,7 +349,9 @@ struct GibbsWarp {
         }
     }
 
-    template <bool GATED>
+    // NBACK (signals tier): this step may still belong to the pi_back smoothing steps at the end of the window — compiled out of
+    // the hot loops, which only start once those steps are behind every lane of the warp
+    template <bool GATED, bool NBACK = true, bool ALLSIG = false>
     static __device__ __forceinline__ void back_step(Back& b, const Chain& ch, const R (&pt)[K], R* __restrict__ pap, R* __restrict__ fap,
                                                       R yt, R sw, uint32_t word, bool save, bool& bad) {
         R p[K];
@@ -368,7 +375,7 @@ struct GibbsWarp {
                 insample_accumulate(ch, b.pb, fap);
             }
         }
-        if constexpr (SIG) {
+        if constexpr (SIG && NBACK) {
             // samples.πb[:, endIndex, :] (:893): the smoothed marginal pi_back rows before the end of the window
             if (b.nback > 0) {
                 smooth_step<R, K>(ch.A, pt, b.pb);
@@ -378,7 +385,7 @@ struct GibbsWarp {
                 }
             }
         }
-        commit(b, ch, lt, pt, yt, sw, false);
+        commit<ALLSIG>(b, ch, lt, pt, yt, sw, false);
     }
 
     // forward filter (forwardupdate_P! :371-440); pif rows stored for the backward pass.  CHECKED = per-step handling
@@ -431,11 +438,11 @@ struct GibbsWarp {
         R buf[4][K];                                                 // the 4 rows of the current tile (stored together)
         // one step at row j = position u of its tile; yo / so: offsets (in rows) of y and of the z-scale from yp / sp
         // (guard: a std::integral_constant — the per-lane window test is compiled out for the rows where every lane is inside its window)
-        auto step = [&](auto guard, int j, int u, int yo, R ypre, bool preloaded) {
+        auto step = [&](auto guard, int j, int u, int yo, R ypre, bool preloaded, R swpre = R(1)) {
             if (!decltype(guard)::value || j >= ch.off) {
                 const R yt = preloaded ? ypre : ld_ro(yp + yo * yld);   // STREAM: loaded one iteration ahead by the caller
                 R sw = R(1);                                         // signals: sd x (1+kappa) (:382) <=> z scaled by 1/(1+kappa)
-                if constexpr (SIG) sw = ld_ro(sp + yo * ch.sld);
+                if constexpr (SIG) sw = preloaded ? swpre : ld_ro(sp + yo * ch.sld);   // STREAM: fetched with the observation
                 if constexpr (sizeof(R) == 4) {
                     const f2 y2 = splat2((float)yt);
                     const f2 sw2 = splat2((float)sw);
@@ -536,23 +543,32 @@ struct GibbsWarp {
         }
         // STREAM: the observations of the next 4 steps are fetched into registers one iteration ahead (from lines that
         // were pulled into L1 kYAhead steps ahead), so neither the DRAM nor the L1 latency sits in the dependent chain
-        R yn[4] = {R(0), R(0), R(0), R(0)};
-        auto load4 = [&](int jj, const R* p) {
+        R yn[4] = {R(0), R(0), R(0), R(0)}, sn[4] = {R(1), R(1), R(1), R(1)};
+        auto load4 = [&](int jj, const R* p, const R* q) {           // observations (and, SIG, their z-scales: one more streamed array per series)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) yn[u] = (jj + u < ch.Tw && (!ragged || jj + u >= ch.off)) ? ld_ro(p + u * yld) : R(0);
+            for (int u = 0; u < 4; ++u) {
+                const bool in = jj + u < ch.Tw && (!ragged || jj + u >= ch.off);
+                yn[u] = in ? ld_ro(p + u * yld) : R(0);
+                if constexpr (SIG) sn[u] = in ? ld_ro(q + u * ch.sld) : R(1);
+            }
         };
-        if constexpr (STREAM) load4(j, yp);
+        if constexpr (STREAM) load4(j, yp, sp);
         // the tiles whose rows lie before the window of some lane run the guarded step, the rest of the frame the plain one
         auto run_tiles = [&](auto guard, const int until) {
             for (; j + 3 < ch.Tw && j < until; j += 4, yp += 4 * yld, pip += 4 * K * 32) {
                 if constexpr (STREAM) {
                     if (j + kYAhead + 3 < ch.Tw && (!ragged || j + kYAhead >= ch.off)) {   // rows of this lane's own window only
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) prefetch_l1(yp + (kYAhead + u) * yld);
+                        for (int u = 0; u < 4; ++u) {
+                            prefetch_l1(yp + (kYAhead + u) * yld);
+                            if constexpr (SIG) { if (ch.sld != 1) prefetch_l1(sp + (kYAhead + u) * ch.sld); }   // (a mask shared by every series stays in L1)
+                        }
                     }
-                    const R c0 = yn[0], c1 = yn[1], c2v = yn[2], c3 = yn[3];
-                    load4(j + 4, yp + 4 * yld);
-                    step(guard, j, 0, 0, c0, true); step(guard, j + 1, 1, 1, c1, true); step(guard, j + 2, 2, 2, c2v, true); step(guard, j + 3, 3, 3, c3, true);
+                    const R c0 = yn[0], c1 = yn[1], c2v = yn[2], c3 = yn[3], z0 = sn[0], z1 = sn[1], z2 = sn[2], z3 = sn[3];
+                    const R* spn = sp;
+                    if constexpr (SIG) spn = sp + 4 * ch.sld;
+                    load4(j + 4, yp + 4 * yld, spn);
+                    step(guard, j, 0, 0, c0, true, z0); step(guard, j + 1, 1, 1, c1, true, z1); step(guard, j + 2, 2, 2, c2v, true, z2); step(guard, j + 3, 3, 3, c3, true, z3);
                 } else {
                     step(guard, j, 0, 0, R(0), false); step(guard, j + 1, 1, 1, R(0), false); step(guard, j + 2, 2, 2, R(0), false); step(guard, j + 3, 3, 3, R(0), false);
                 }
@@ -571,7 +587,7 @@ struct GibbsWarp {
     struct NoAcc {};
     struct TransAcc { int n[K * K]; };                               // flushed transition counts (K > 4)
     struct BackOut : std::conditional<Pack::kFlush, TransAcc, NoAcc>::type { Back b; int xN; bool bad; };
-    template <bool RAGGED, bool GATED, bool STREAM = false>
+    template <bool RAGGED, bool GATED, bool STREAM = false, bool ALLSIG = false>
     static __device__ HMC_BACK_ATTR BackOut backward_pass(const Chain ch, const Vec pf_in, const RngKey key, const uint32_t sweep,
                                                          const unsigned flags, const bool save) {
         BackOut o;
@@ -660,7 +676,7 @@ struct GibbsWarp {
             }
             R swN = R(1);
             if constexpr (SIG) swN = ld_ro(sp);
-            commit(b, ch, lt, pf, ld_ro(yp), swN, true);
+            commit<ALLSIG>(b, ch, lt, pf, ld_ro(yp), swN, true);
         }
         int i = 1;
         // one step; u = position inside the current group of 4 (pointers move once per group).  The filtered rows and
@@ -680,10 +696,11 @@ struct GibbsWarp {
             yt = (!ragged || i + u < T) ? ld_ro(yp - (u + 1) * ys) : R(0);
             st = load_sw(u);
         };
-#define HMC_BACK(u, word, PT, YT, ST)                                                                                  \
+#define HMC_BACK_NB(NB, u, word, PT, YT, ST)                                                                           \
     if (!ragged || i + (u) < T)                                                                                          \
-        back_step<GATED>(b, ch, PT, SMOOTH ? pap - ((u) + 1) * K * 32 : nullptr,                                         \
-                         SMOOTH ? ch.facc0 + (size_t)(Tw - 1 - (i + (u))) * ch.n_hi * 32 : nullptr, YT, ST, (word), save, bad);
+        back_step<GATED, NB, ALLSIG>(b, ch, PT, SMOOTH ? pap - ((u) + 1) * K * 32 : nullptr,                             \
+                                     SMOOTH ? ch.facc0 + (size_t)(Tw - 1 - (i + (u))) * ch.n_hi * 32 : nullptr, YT, ST, (word), save, bad);
+#define HMC_BACK(u, word, PT, YT, ST) HMC_BACK_NB(true, u, word, PT, YT, ST)
         {
             R p0[K], p1[K], p2[K], y0, y1, y2, s0 = R(1), s1 = R(1), s2 = R(1);
             if (Tw > 1) load_row(0, p0, y0, s0);
@@ -695,6 +712,17 @@ struct GibbsWarp {
             const int done = Tw > 3 ? 3 : Tw - 1;
             i += done; yp -= done * ys; if (SMOOTH) pap -= (size_t)done * K * 32;
             if constexpr (SIG) sp -= done * ss;
+        }
+        if constexpr (SIG) {
+            // the remaining pi_back smoothing steps (:893), whole groups of 4 straight from global memory: the ring loop below
+            // then runs without the smoother (warp-uniform: the pass is entered by the whole warp)
+            while (i + 3 < Tw && __any_sync(0xffffffffu, b.nback > 0)) {
+                R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3, s0 = R(1), s1 = R(1), s2 = R(1), s3 = R(1);
+                load_row(0, c0, y0, s0); load_row(1, c1, y1, s1); load_row(2, c2, y2, s2); load_row(3, c3, y3, s3);
+                w = rng_block_states(key, sweep, (uint32_t)(i >> 2));
+                HMC_BACK(0, w.x, c0, y0, s0) HMC_BACK(1, w.y, c1, y1, s1) HMC_BACK(2, w.z, c2, y2, s2) HMC_BACK(3, w.w, c3, y3, s3)
+                i += 4; yp -= 4 * ys; sp -= 4 * ss;
+            }
         }
 #if HMC_ASYNC
         {
@@ -709,7 +737,7 @@ struct GibbsWarp {
             // group g (0-based) holds rows [jlo, jlo+3], jlo = Tw - 8 - 4g  (the rows of steps i = 4+4g .. 7+4g, highest first)
             // running source pointer / ring stage of the next group to fetch (loop-carried: re-deriving them from g cost ~20
             // integer instructions per group)
-            const char* nsrc = reinterpret_cast<const char*>(ch.pi0 - lane * 4 + (long long)(Tw + pad - 8) * K * 32) + lane * 16;   // tile of group 0
+            const char* nsrc = reinterpret_cast<const char*>(ch.pi0 - lane * 4 + (long long)(Tw + pad - 4 - i) * K * 32) + lane * 16;   // tile of group 0 (rows of steps i..i+3; i is a multiple of 4 here)
             const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)lane * 16u;
             constexpr unsigned kGroupBytes = (unsigned)(kGroupElems * sizeof(R));
             unsigned nstage = 0;                                         // byte offset of the stage the next fetch fills
@@ -727,38 +755,45 @@ struct GibbsWarp {
 #pragma unroll
             for (int g = 0; g < kRing - 1; ++g) issue();
             unsigned rstage = 0;                                         // byte offset of the stage read in this iteration
-            R ynx[4] = {R(0), R(0), R(0), R(0)};
-            auto loady4 = [&](int ii, const R* p) {                      // observations of steps ii..ii+3 (rows below p)
+            R ynx[4] = {R(0), R(0), R(0), R(0)}, snx[4] = {R(1), R(1), R(1), R(1)};
+            auto loady4 = [&](int ii, const R* p, const R* q) {          // observations (SIG: and z-scales) of steps ii..ii+3 (rows below p / q)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) ynx[u] = (!ragged || ii + u < T) ? ld_ro(p - (u + 1) * ys) : R(0);
+                for (int u = 0; u < 4; ++u) {
+                    ynx[u] = (!ragged || ii + u < T) ? ld_ro(p - (u + 1) * ys) : R(0);
+                    if constexpr (SIG) snx[u] = (!ragged || ii + u < T) ? ld_ro(q - (u + 1) * ss) : R(1);
+                }
             };
-            if constexpr (STREAM) { if (n_groups > 0) loady4(i, yp); }
+            if constexpr (STREAM) { if (n_groups > 0) loady4(i, yp, sp); }
             for (int g = 0; g < n_groups; ++g, i += 4, yp -= 4 * ys, pap -= SMOOTH ? 4 * K * 32 : 0, sp -= 4 * ss) {
                 if constexpr (Pack::kFlush) { if ((since += 4) > Pack::kMaxT) flush(); }
                 if (STREAM && i + kYAhead + 3 < T) {                       // rows of steps i+kYAhead .. i+kYAhead+3 (this lane's window)
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) prefetch_l1(yp - (kYAhead + u + 1) * ys);
+                    for (int u = 0; u < 4; ++u) {
+                        prefetch_l1(yp - (kYAhead + u + 1) * ys);
+                        if constexpr (SIG) { if (ss != 1) prefetch_l1(sp - (kYAhead + u + 1) * ss); }
+                    }
                 }
                 issue();                                                 // group g + kRing - 1: overwrites the stage consumed in iteration g-1
                 cp_async_wait<kRing - 1>();                              // group g has landed (for this lane's chunks)
                 __syncwarp();                                            // ... and for every other lane's
                 const R* st = reinterpret_cast<const R*>(reinterpret_cast<const char*>(ring) + rstage) + lane * 4;
                 rstage = (rstage + kGroupBytes == kRing * kGroupBytes) ? 0u : rstage + kGroupBytes;
-                R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3;
+                R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3, s0 = R(1), s1 = R(1), s2 = R(1), s3 = R(1);
 #pragma unroll
                 for (int s = 0; s < K; ++s) ld_quad_shared(st + s * 128, c3[s], c2[s], c1[s], c0[s]);   // position 3 = highest row = first step
                 if constexpr (STREAM) {                                  // fetched one group ahead (see forward_pass)
                     y0 = ynx[0]; y1 = ynx[1]; y2 = ynx[2]; y3 = ynx[3];
-                    if (g + 1 < n_groups) loady4(i + 4, yp - 4 * ys);
+                    s0 = snx[0]; s1 = snx[1]; s2 = snx[2]; s3 = snx[3];
+                    if (g + 1 < n_groups) loady4(i + 4, yp - 4 * ys, sp - 4 * ss);
                 } else {
                     y0 = (!ragged || i + 0 < T) ? ld_ro(yp - 1 * ys) : R(0);
                     y1 = (!ragged || i + 1 < T) ? ld_ro(yp - 2 * ys) : R(0);
                     y2 = (!ragged || i + 2 < T) ? ld_ro(yp - 3 * ys) : R(0);
                     y3 = (!ragged || i + 3 < T) ? ld_ro(yp - 4 * ys) : R(0);
                 }
-                const R s0 = load_sw(0), s1 = load_sw(1), s2 = load_sw(2), s3 = load_sw(3);
+                if constexpr (!STREAM) { s0 = load_sw(0); s1 = load_sw(1); s2 = load_sw(2); s3 = load_sw(3); }
                 w = rng_block_states(key, sweep, (uint32_t)(i >> 2));
-                HMC_BACK(0, w.x, c0, y0, s0) HMC_BACK(1, w.y, c1, y1, s1) HMC_BACK(2, w.z, c2, y2, s2) HMC_BACK(3, w.w, c3, y3, s3)
+                HMC_BACK_NB(false, 0, w.x, c0, y0, s0) HMC_BACK_NB(false, 1, w.y, c1, y1, s1) HMC_BACK_NB(false, 2, w.z, c2, y2, s2) HMC_BACK_NB(false, 3, w.w, c3, y3, s3)
                 __syncwarp();                                            // all lanes are done with this stage
             }
             cp_async_wait<0>();
@@ -783,6 +818,7 @@ struct GibbsWarp {
             if (i + 2 < Tw) { HMC_BACK(2, w.z, p2, y2, s2) }
         }
 #undef HMC_BACK
+#undef HMC_BACK_NB
         flush();
         o.b = b;
         o.xN = xN;
@@ -995,6 +1031,17 @@ struct GibbsWarp {
                 if (SMOOTH) {                                        // accumulates into memory: run gated in place
                     bo = backward_pass<true, true>(ch, pv, key, sweep, a.flags, save);
                 } else {
+                    bool done_b = false;
+                    if constexpr (SIG) {
+                        if (a.all_signal) {                          // every time step a signal: no observation statistics (warp-uniform)
+                            bo = stream_y ? (ch.rag_rows > 0 ? backward_pass<true, false, true, true>(ch, pv, key, sweep, a.flags, save)
+                                                             : backward_pass<false, false, true, true>(ch, pv, key, sweep, a.flags, save))
+                                          : (ch.rag_rows > 0 ? backward_pass<true, false, false, true>(ch, pv, key, sweep, a.flags, save)
+                                                             : backward_pass<false, false, false, true>(ch, pv, key, sweep, a.flags, save));
+                            done_b = true;
+                        }
+                    }
+                    if (!done_b)
                     bo = stream_y ? (ch.rag_rows > 0 ? backward_pass<true, false, true>(ch, pv, key, sweep, a.flags, save)
                                                : backward_pass<false, false, true>(ch, pv, key, sweep, a.flags, save))
                                   : (ch.rag_rows > 0 ? backward_pass<true, false>(ch, pv, key, sweep, a.flags, save)

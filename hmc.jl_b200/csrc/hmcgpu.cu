@@ -1452,6 +1452,13 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     a.yfut = pl->yfut.p; a.flags = p->flags;
     a.sigw = pl->sigw.p; a.sbase = pl->sbase.as<long long>(); a.sld = sld; a.cntM = pl->cntM.as<int>(); a.Sm = pl->Sm.p; a.Qm = pl->Qm.p; a.totSm = pl->totSm.p; a.totQm = pl->totQm.p;
     a.totM = pl->totM.as<int>(); a.kappa = p->kappa; a.pi_back = p->pi_row_back;
+    a.all_signal = 0;
+    if (p->is_signal) {
+        const size_t nm = (size_t)p->y_len * sld;
+        size_t ones = 0;
+        for (size_t q = 0; q < nm; ++q) ones += p->is_signal[q] != 0;
+        a.all_signal = ones == nm;
+    }
     a.seg_warm = 32;
     if (const char* e = getenv("HMCGPU_SEG_WARMUP")) a.seg_warm = std::max(0, atoi(e));
     a.seg_barriers = 2;
