@@ -42,6 +42,9 @@ namespace hmc {
 #ifndef HMC_ASYNC
 #define HMC_ASYNC 1        // 1: backward rows are staged through a per-warp shared-memory ring with cp.async (LDGSTS)
 #endif
+#ifndef HMC_TMA
+#define HMC_TMA 0          // 1: the ring is filled by ONE 1-D bulk copy per group (cp.async.bulk, the TMA engine; SASS UBLKCP) issued by an
+#endif                     //    elected lane and completed on an mbarrier, instead of K*sizeof(R)/4 LDGSTS per lane (K <= 4 kernels)
 #ifndef HMC_RING_STAGES
 #define HMC_RING_STAGES 4  // groups of 4 rows in flight per warp
 #endif
@@ -59,6 +62,34 @@ __device__ __forceinline__ void cp_async16_s(unsigned saddr, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// ---- TMA 1-D bulk copy + mbarrier (HMC_TMA).  All waits are bounded: a lost completion turns into an error count, never a hang.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_inval(unsigned bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+constexpr int kTmaWaitSpins = 1 << 16;                               // try_wait sleeps in hardware between polls: far beyond any real latency
+static __device__ __noinline__ bool mbar_wait_bounded(unsigned bar, unsigned parity) {     // the cold path of a wait: false = the phase never completed
+    for (int spins = 0; spins < kTmaWaitSpins; ++spins)
+        if (mbar_try_wait(bar, parity)) return true;
+    return false;
+}
+__device__ __forceinline__ bool elect_one() {                        // one lane of the (converged) warp
+    unsigned ok;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(ok));
+    return ok != 0u;
+}
+
 // The passes are out-of-line functions, where pointers arriving through their by-value arguments would be generic
 // (LD.E/ST.E).  Shared memory is therefore always re-derived from the kernel's dynamic shared array, and global memory
 // goes through the explicit-space intrinsics below (LDG/STG in SASS).
@@ -586,14 +617,14 @@ struct GibbsWarp {
     // The i-th uniform consumed (i = 0 for X[N]) is word i&3 of Philox block i>>2 of this sweep.
     struct NoAcc {};
     struct TransAcc { int n[K * K]; };                               // flushed transition counts (K > 4)
-    struct BackOut : std::conditional<Pack::kFlush, TransAcc, NoAcc>::type { Back b; int xN; bool bad; };
+    struct BackOut : std::conditional<Pack::kFlush, TransAcc, NoAcc>::type { Back b; int xN; bool bad; bool lost; };   // lost: a bulk copy never completed (HMC_TMA)
     template <bool RAGGED, bool GATED, bool STREAM = false, bool ALLSIG = false>
     static __device__ HMC_BACK_ATTR BackOut backward_pass(const Chain ch, const Vec pf_in, const RngKey key, const uint32_t sweep,
                                                          const unsigned flags, const bool save) {
         BackOut o;
         Back b;                      // a local (registers): `o` is returned through memory when K > 4
         const R (&pf)[K] = pf_in.v;
-        bool bad = false;
+        bool bad = false, lost = false;
         int xN = 0;
         const int Tw = ch.Tw, T = ch.T;
         const long long ys = (!STREAM && !GATED) ? 1ll : ch.yld;       // see forward_pass
@@ -737,23 +768,67 @@ struct GibbsWarp {
             // group g (0-based) holds rows [jlo, jlo+3], jlo = Tw - 8 - 4g  (the rows of steps i = 4+4g .. 7+4g, highest first)
             // running source pointer / ring stage of the next group to fetch (loop-carried: re-deriving them from g cost ~20
             // integer instructions per group)
-            const char* nsrc = reinterpret_cast<const char*>(ch.pi0 - lane * 4 + (long long)(Tw + pad - 4 - i) * K * 32) + lane * 16;   // tile of group 0 (rows of steps i..i+3; i is a multiple of 4 here)
-            const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)lane * 16u;
+            constexpr bool kTma = HMC_TMA && K <= 4;
+            const char* nsrc = reinterpret_cast<const char*>(ch.pi0 - lane * 4 + (long long)(Tw + pad - 4 - i) * K * 32) + (kTma ? 0 : lane * 16);   // tile of group 0 (rows of steps i..i+3; i is a multiple of 4 here)
+            const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (kTma ? 0u : (unsigned)lane * 16u);
             constexpr unsigned kGroupBytes = (unsigned)(kGroupElems * sizeof(R));
             unsigned nstage = 0;                                         // byte offset of the stage the next fetch fills
             int nleft = n_groups;                                        // groups not fetched yet
-            auto issue = [&]() {
-                if (nleft > 0) {
+            // TMA: one mbarrier per ring stage of this warp, behind the rings; (re)initialised per pass.  The forward pass wrote the
+            // tiles through the generic proxy: a proxy fence orders those writes before the bulk copies read them.  Everything the
+            // copy is issued from is broadcast from lane 0 first: the compiler then keeps source, destination, barrier and counters
+            // in uniform registers and emits ONE UBLKCP per group (per-lane operands cost an ELECT/R2UR waterfall loop per copy).
+            unsigned long long usrc = 0;                                 // (uniform) source of the next fetch
+            unsigned uring = 0, ubar0 = 0, ufetch = 0;                   // (uniform) ring base, first mbarrier, groups fetched so far
+            int uleft = 0;
+            if constexpr (kTma) {
+                const unsigned wq = threadIdx.x >> 5;
+                const unsigned bar_l = (unsigned)__cvta_generic_to_shared(smem_base()) + ch.ring_off
+                                       + (unsigned)(sizeof(R) * ((kGibbsThreads / 32) - wq) * (kRing * 4 * K * 32)) + wq * (kRing * 8u);
+                const unsigned long long src_l = (unsigned long long)nsrc;
+                usrc = ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(src_l >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (unsigned)src_l, 0);
+                uring = __shfl_sync(0xffffffffu, ring_s, 0);
+                ubar0 = __shfl_sync(0xffffffffu, bar_l, 0);
+                uleft = __shfl_sync(0xffffffffu, n_groups, 0);
+                fence_proxy_async();
+                if (lane == 0) {
 #pragma unroll
-                    for (int m = 0; m < kChunksPerLane; ++m) cp_async16_s(ring_s + nstage + 512u * m, nsrc + 512 * m);
+                    for (int q = 0; q < kRing; ++q) mbar_init(ubar0 + 8u * q, 1u);
+                    fence_mbar_init();
                 }
-                cp_async_commit();                                       // (possibly empty) keeps the group count uniform
-                --nleft;
-                nsrc -= kGroupBytes;
-                nstage = (nstage + kGroupBytes == kRing * kGroupBytes) ? 0u : nstage + kGroupBytes;
-            };
+                __syncwarp();
+            }
+            // HMC_TMA = groups per bulk copy G (1 or 2): the ring holds kRing/G copy stages, each with its own mbarrier.  The groups
+            // of one copy are contiguous in memory in DESCENDING step order, so inside a stage of G = 2 the later group comes first.
+            constexpr int kG = kTma ? HMC_TMA : 1, kCopies = kRing / kG;
+            static_assert(!kTma || (kRing % kG == 0 && kCopies >= 2), "ring stages must hold whole copies");
+            auto issue = [&]() {                                         // TMA: one call per COPY (G groups); cp.async: per group
+                if constexpr (kTma) {
+                    if (uleft > 0) {
+                        const unsigned n = uleft >= kG ? (unsigned)kG : 1u;          // groups in this copy (the last one may be short)
+                        if (elect_one()) {
+                            mbar_expect_tx(ubar0 + 8u * ufetch, kGroupBytes * n);
+                            bulk_g2s(uring + kGroupBytes * kG * ufetch + kGroupBytes * ((unsigned)kG - n),
+                                     reinterpret_cast<const void*>(usrc - kGroupBytes * (n - 1u)), kGroupBytes * n, ubar0 + 8u * ufetch);
+                        }
+                    }
+                    ufetch = (ufetch + 1u == (unsigned)kCopies) ? 0u : ufetch + 1u;
+                    uleft -= kG;
+                    usrc -= kGroupBytes * kG;
+                } else {
+                    if (nleft > 0) {
 #pragma unroll
-            for (int g = 0; g < kRing - 1; ++g) issue();
+                        for (int m = 0; m < kChunksPerLane; ++m) cp_async16_s(ring_s + nstage + 512u * m, nsrc + 512 * m);
+                    }
+                    cp_async_commit();                                   // (possibly empty) keeps the group count uniform
+                    --nleft;
+                    nsrc -= kGroupBytes;
+                    nstage = (nstage + kGroupBytes == kRing * kGroupBytes) ? 0u : nstage + kGroupBytes;
+                }
+            };
+            unsigned uread = 0, uparity = 0;                             // (uniform, TMA) copy stage being consumed and its phase parity
+#pragma unroll
+            for (int g = 0; g < (kTma ? kCopies : kRing) - 1; ++g) issue();
             unsigned rstage = 0;                                         // byte offset of the stage read in this iteration
             R ynx[4] = {R(0), R(0), R(0), R(0)}, snx[4] = {R(1), R(1), R(1), R(1)};
             auto loady4 = [&](int ii, const R* p, const R* q) {          // observations (SIG: and z-scales) of steps ii..ii+3 (rows below p / q)
@@ -773,10 +848,18 @@ struct GibbsWarp {
                         if constexpr (SIG) { if (ss != 1) prefetch_l1(sp - (kYAhead + u + 1) * ss); }
                     }
                 }
-                issue();                                                 // group g + kRing - 1: overwrites the stage consumed in iteration g-1
-                cp_async_wait<kRing - 1>();                              // group g has landed (for this lane's chunks)
-                __syncwarp();                                            // ... and for every other lane's
-                const R* st = reinterpret_cast<const R*>(reinterpret_cast<const char*>(ring) + rstage) + lane * 4;
+                if (!kTma || kG == 1 || (g & (kG - 1)) == 0) issue();    // group g + kRing - 1 (TMA: the copy kCopies-1 ahead): overwrites what iteration g-1 finished with
+                if constexpr (kTma) {
+                    if (kG == 1 || (g & (kG - 1)) == 0) {                // first group of a copy: wait for it
+                        const unsigned bar = ubar0 + 8u * uread;
+                        if (!mbar_try_wait(bar, uparity)) lost |= !mbar_wait_bounded(bar, uparity);   // the first poll almost always succeeds (issued kCopies-1 copies ago)
+                        if (++uread == (unsigned)kCopies) { uread = 0u; uparity ^= 1u; }
+                    }
+                } else {
+                    cp_async_wait<kRing - 1>();                          // group g has landed (for this lane's chunks)
+                    __syncwarp();                                        // ... and for every other lane's
+                }
+                const R* st = reinterpret_cast<const R*>(reinterpret_cast<const char*>(ring) + (kG == 2 ? ((g & 1) ? rstage - kGroupBytes : rstage + kGroupBytes) : rstage)) + lane * 4;
                 rstage = (rstage + kGroupBytes == kRing * kGroupBytes) ? 0u : rstage + kGroupBytes;
                 R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3, s0 = R(1), s1 = R(1), s2 = R(1), s3 = R(1);
 #pragma unroll
@@ -796,7 +879,15 @@ struct GibbsWarp {
                 HMC_BACK_NB(false, 0, w.x, c0, y0, s0) HMC_BACK_NB(false, 1, w.y, c1, y1, s1) HMC_BACK_NB(false, 2, w.z, c2, y2, s2) HMC_BACK_NB(false, 3, w.w, c3, y3, s3)
                 __syncwarp();                                            // all lanes are done with this stage
             }
-            cp_async_wait<0>();
+            if constexpr (kTma) {
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < kRing; ++q) mbar_inval(ubar0 + 8u * q);
+                }
+                __syncwarp();
+            } else {
+                cp_async_wait<0>();
+            }
         }
 #else
         for (; i + 3 < Tw; i += 4, yp -= 4 * ys, pap -= SMOOTH ? 4 * K * 32 : 0, sp -= 4 * ss) {
@@ -823,6 +914,7 @@ struct GibbsWarp {
         o.b = b;
         o.xN = xN;
         o.bad = bad;
+        o.lost = lost;
         return o;
     }
 
@@ -1053,6 +1145,7 @@ struct GibbsWarp {
                 }
                 b = bo.b;
                 xN = bo.xN;
+                if (bo.lost) events += 1 << 20;                      // a bulk copy never completed: the sweep used stale rows — reported, never silent
                 if constexpr (Pack::kFlush) {
 #pragma unroll
                     for (int q = 0; q < K * K; ++q) flushed.n[q] = bo.n[q];
@@ -1119,6 +1212,7 @@ struct GibbsWarp {
 template <typename R, int K, bool WIDE> __host__ __device__ constexpr size_t gibbs_smem_bytes(bool smooth, int n_h) {
     return sizeof(GibbsEntry<R, K, WIDE>) * K * kGibbsThreads                                    // selection tables
            + (HMC_ASYNC ? sizeof(R) * (size_t)(kGibbsThreads / 32) * gibbs_ring_stages<R, K>() * 4 * K * 32 : 0)      // cp.async rings
+           + (HMC_TMA ? (size_t)(kGibbsThreads / 32) * gibbs_ring_stages<R, K>() * 8 : 0)                              // their mbarriers (HMC_TMA)
            + (smooth ? sizeof(R) * (size_t)n_h * K * kGibbsThreads : 0)                           // A^h mu (in-sample forecasts)
            + sizeof(R) * (size_t)n_h * kGibbsThreads;                                             // realised y at end+h, per thread
 }

@@ -7,6 +7,8 @@
 #include "gibbs_seg_kernel.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -32,6 +34,10 @@ struct hmcgpu_ctx {
     std::string err;
     int sm_count = 0;
     std::shared_ptr<DevPool> pool;      // recycled device buffers (see DevPool)
+    // pinned staging buffers of large host -> device uploads (staged_upload); allocated on first use, freed with the context
+    void* stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_free[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
 };
 
 static thread_local std::string g_create_err;
@@ -182,6 +188,10 @@ extern "C" void hmcgpu_ctx_destroy(hmcgpu_ctx* ctx) {
     cudaDeviceSynchronize();
     if (tl_pool == ctx->pool) tl_pool.reset();
     if (ctx->pool) ctx->pool->release_all();
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+        if (ctx->stage_free[i]) cudaEventDestroy(ctx->stage_free[i]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -616,6 +626,100 @@ struct Xfer {
 };
 
 #define TRY(x) do { int rc__ = (x); if (rc__ != 0) return rc__; } while (0)
+
+// Large uploads from the caller's (pageable) memory.  A plain cudaMemcpyAsync from pageable memory is staged by the driver on
+// ONE thread at a few GB/s (measured: the 1 GB series upload of the wide batch C4 was twice its device time).  Here the copy is
+// cut into chunks that several host threads copy into one of two pinned buffers while the DMA engine drains the other: one
+// cudaMemcpyAsync per chunk, limited by host memory bandwidth / PCIe instead of a single core.  HMCGPU_STAGE_MB sets the
+// chunk size (0: plain copy), HMCGPU_STAGE_THREADS the copying threads.
+static cudaError_t staged_upload(hmcgpu_ctx* ctx, void* dev, const void* host, size_t bytes, cudaStream_t st) {
+    const size_t chunk = [] { const char* e = getenv("HMCGPU_STAGE_MB"); return (size_t)std::max(0ll, std::min(1024ll, e ? atoll(e) : 32ll)) << 20; }();
+    const int n_thr = [] {
+        const char* e = getenv("HMCGPU_STAGE_THREADS");
+        const int hw = (int)std::thread::hardware_concurrency();
+        return std::max(1, std::min(64, e ? atoi(e) : std::min(8, hw > 1 ? hw / 2 : 1)));
+    }();
+    if (chunk == 0 || bytes < 2 * chunk) return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st);
+    if (ctx->stage_bytes != chunk) {
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->stage[i]) { cudaFreeHost(ctx->stage[i]); ctx->stage[i] = nullptr; }
+            cudaError_t e = cudaHostAlloc(&ctx->stage[i], chunk, cudaHostAllocDefault);
+            if (e != cudaSuccess) { ctx->stage[i] = nullptr; ctx->stage_bytes = 0; cudaGetLastError(); return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st); }
+            if (!ctx->stage_free[i] && (e = cudaEventCreateWithFlags(&ctx->stage_free[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        ctx->stage_bytes = chunk;
+    }
+    const char* src = static_cast<const char*>(host);
+    char* dst = static_cast<char*>(dev);
+    // persistent copy threads for this upload: thread t copies its slice of every chunk; the caller's thread drives the DMA
+    struct Shared { std::mutex mu; std::condition_variable cv; long long filling = -1; int done = 0; bool quit = false; } sh;
+    const size_t n_chunks = (bytes + chunk - 1) / chunk;
+    auto chunk_len = [&](size_t c) { return std::min(chunk, bytes - c * chunk); };
+    auto worker = [&](int t) {
+        long long seen = -1;
+        for (;;) {
+            long long c;
+            {
+                std::unique_lock<std::mutex> lk(sh.mu);
+                sh.cv.wait(lk, [&] { return sh.quit || sh.filling > seen; });
+                if (sh.quit) return;
+                c = seen = sh.filling;
+            }
+            const size_t len = chunk_len((size_t)c), per = (len / n_thr + 63) & ~(size_t)63;
+            const size_t lo = std::min(len, per * t), hi = (t == n_thr - 1) ? len : std::min(len, per * (t + 1));
+            if (hi > lo) memcpy(static_cast<char*>(ctx->stage[c & 1]) + lo, src + (size_t)c * chunk + lo, hi - lo);
+            {
+                std::lock_guard<std::mutex> lk(sh.mu);
+                ++sh.done;
+            }
+            sh.cv.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_thr; ++t) pool.emplace_back(worker, t);
+    cudaError_t rc = cudaSuccess;
+    for (size_t c = 0; c < n_chunks && rc == cudaSuccess; ++c) {
+        if (c >= 2) rc = cudaEventSynchronize(ctx->stage_free[c & 1]);          // the DMA out of this buffer (chunk c-2) has finished
+        if (rc != cudaSuccess) break;
+        {
+            std::lock_guard<std::mutex> lk(sh.mu);
+            sh.filling = (long long)c; sh.done = 0;
+        }
+        sh.cv.notify_all();
+        {                                                                        // the caller's thread copies slice 0
+            const size_t len = chunk_len(c), per = (len / n_thr + 63) & ~(size_t)63;
+            const size_t hi = n_thr == 1 ? len : std::min(len, per);
+            memcpy(ctx->stage[c & 1], src + c * chunk, hi);
+        }
+        {
+            std::unique_lock<std::mutex> lk(sh.mu);
+            sh.cv.wait(lk, [&] { return sh.done == n_thr - 1; });
+        }
+        rc = cudaMemcpyAsync(dst + c * chunk, ctx->stage[c & 1], chunk_len(c), cudaMemcpyHostToDevice, st);
+        if (rc == cudaSuccess) rc = cudaEventRecord(ctx->stage_free[c & 1], st);
+    }
+    {
+        std::lock_guard<std::mutex> lk(sh.mu);
+        sh.quit = true;
+    }
+    sh.cv.notify_all();
+    for (auto& t : pool) t.join();
+    // the staging buffers are reused by the next upload on this context: it starts by overwriting them, so drain the DMA first
+    if (rc == cudaSuccess) rc = cudaEventSynchronize(ctx->stage_free[(n_chunks - 1) & 1]);
+    return rc;
+}
+
+// HMCGPU_VERBOSE=1: wall-clock phases of an estimation on stderr
+struct PhaseTrace {
+    const bool on = getenv("HMCGPU_VERBOSE") != nullptr && atoi(getenv("HMCGPU_VERBOSE")) != 0;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[hmcgpu] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 static int check_common(hmcgpu_ctx* ctx, int K, long long B, long long T) {
     if (!ctx) return HMCGPU_ERR_ARG;
@@ -1341,11 +1445,13 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         cudaError_t e = b.alloc(bytes);
         if (e != cudaSuccess) return e;
         pl->h2d += (long long)bytes;
-        return cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, st);
+        return staged_upload(ctx, b.p, host, bytes, st);
     };
     DevBuf yin;
     const size_t ny = (size_t)p->y_len * nser;
+    PhaseTrace tr;
     CU(ctx, up(yin, p->y, ny * sizeof(double)));
+    tr.mark("  series upload enqueued");
     CU(ctx, pl->y64.alloc(ny * sizeof(double)));
     CU(ctx, pl->yr.alloc(ny * sizeof(R)));
     y_layout_kernel<R><<<grid_for((long long)ny, 256), 256, 0, st>>>(p->y_len, nser, yin.as<double>(), pl->y64.as<double>(), pl->yr.as<R>());
@@ -1479,7 +1585,9 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     }
     CU(ctx, cudaEventCreate(&pl->ev0)); CU(ctx, cudaEventCreate(&pl->ev1));
     CU(ctx, cudaEventCreate(&pl->evk0)); CU(ctx, cudaEventCreate(&pl->evk1));
+    tr.mark("  tables, allocations, init");
     CU(ctx, cudaStreamSynchronize(st));
+    tr.mark("  stream drained");
     return HMCGPU_OK;
 }
 
@@ -1815,10 +1923,15 @@ extern "C" void hmcgpu_plan_destroy(hmcgpu_plan* pl) {
 extern "C" int hmcgpu_estimate(hmcgpu_ctx* ctx, const hmcgpu_problem* p, hmcgpu_result* r) {
     if (!r) return fail(ctx, HMCGPU_ERR_ARG, "result is NULL");
     hmcgpu_plan* pl = nullptr;
+    PhaseTrace tr;
     TRY(hmcgpu_plan_create(ctx, p, &pl));
+    tr.mark("plan_create (upload, init)");
     int rc = hmcgpu_plan_run(pl);
+    tr.mark("plan_run (all sweeps)");
     if (rc == 0) rc = hmcgpu_plan_fetch(pl, r);
+    tr.mark("plan_fetch (download)");
     hmcgpu_plan_destroy(pl);
+    tr.mark("plan_destroy");
     return rc;
 }
 

@@ -399,6 +399,26 @@ def test_multiple_series_time_major_layout(H, ctx):
         np.testing.assert_array_equal(single.forecasts[0], o.forecasts[s])
 
 
+def test_staged_upload_of_large_series_is_bit_identical(H, ctx, monkeypatch):
+    """Series uploads above two staging chunks go through pinned double buffers filled by several host threads
+    (hmcgpu.cu::staged_upload); the results must not depend on the chunk size, the thread count or on staging at all.
+    3000 series x 700 observations = 16.8 MB: staged with 1 MB chunks (odd tail chunk, uneven thread slices)."""
+    rng = np.random.default_rng(11)
+    base = np.stack([synth_hmm(700, seed=s, **K3_TRUTH)[0] for s in range(8)])
+    ys = np.ascontiguousarray(np.tile(base, (375, 1)) + 1e-3 * rng.standard_normal((3000, 700)))
+    kw = dict(K=3, n_chains=1, burnin=4, nrun=4, seed=5, horizons=(1,), precision=64, flags=H.FLAG_REF_Q1 | H.FLAG_SUMMARY,
+              win_series=np.arange(3000))
+    outs = []
+    for mb, thr in (("0", "1"), ("1", "3"), ("1", "8"), ("5", "2")):
+        monkeypatch.setenv("HMCGPU_STAGE_MB", mb)
+        monkeypatch.setenv("HMCGPU_STAGE_THREADS", thr)
+        outs.append(_run(H, ctx, ys, [1] * 3000, [690] * 3000, **kw))
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o.summary_mean, outs[0].summary_mean)
+        np.testing.assert_array_equal(o.summary_var, outs[0].summary_var)
+    assert outs[0].h2d_bytes == outs[1].h2d_bytes
+
+
 def test_plan_run_is_repeatable_and_device_resident(H, ctx):
     y, _ = synth_hmm(220, **K3_TRUTH)
     spec = H.ProblemSpec(y, [1, 1], [200, 150], K=3, n_chains=40, burnin=20, nrun=30, seed=3, horizons=(12,), precision=32,
