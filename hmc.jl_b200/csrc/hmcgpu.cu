@@ -954,12 +954,18 @@ __device__ double block_select(const double* y, size_t yld, int N, int k, unsign
     unsigned long long prefix = 0, mask = 0;
     for (int bit = 63; bit >= 0; --bit) {
         const unsigned long long b = 1ull << bit;
-        unsigned long long c = 0;
+        unsigned cl = 0;
         for (int i = threadIdx.x; i < N; i += blockDim.x) {
             const unsigned long long key = orderable(y[(size_t)i * yld]);
-            c += ((key & mask) == prefix && !(key & b)) ? 1ull : 0ull;
+            cl += ((key & mask) == prefix && !(key & b)) ? 1u : 0u;
         }
-        c = block_reduce<unsigned long long>(c, sh, [](unsigned long long a, unsigned long long b2) { return a + b2; });
+        // integer count: one warp reduction, one shared-memory line of per-warp sums, two barriers per bit
+        cl = __reduce_add_sync(0xffffffffu, cl);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cl;
+        __syncthreads();
+        unsigned long long c = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) c += sh[q];
+        __syncthreads();
         if ((unsigned long long)k >= c) { prefix |= b; k -= (int)c; }
         mask |= b;
     }
@@ -1094,16 +1100,36 @@ __global__ void sigw_kernel(long long y_len, int S, const unsigned char* __restr
     out[i] = f ? (R)(-1.0 / (1.0 + kappa)) : R(1);
 }
 
-// y (fp64, series-major as the host gives it) -> time-major fp64 and R copies
+// y (fp64, series-major as the host gives it) -> time-major copy in the sweep precision (yr[t * n_series + s]); 32 x 32 tiles
+// through shared memory so that both the reads (along time) and the writes (along the series) are coalesced
 template <typename R>
-__global__ void y_layout_kernel(long long y_len, int n_series, const double* __restrict__ in, double* __restrict__ y64, R* __restrict__ yr) {
+__global__ void __launch_bounds__(256) y_layout_kernel(long long y_len, int n_series, const double* __restrict__ in, R* __restrict__ yr) {
+    __shared__ double tile[32][33];
+    const long long s0 = (long long)blockIdx.x * 32, t0 = (long long)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const long long sidx = s0 + j, t = t0 + tx;
+        if (sidx < n_series && t < y_len) tile[j][tx] = in[sidx * y_len + t];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const long long t = t0 + j, sidx = s0 + tx;
+        if (sidx < n_series && t < y_len) yr[t * n_series + sidx] = (R)tile[tx][j];
+    }
+}
+
+// per-window posterior summaries from the accumulated sums: mean and (population) variance over the n saved draws of a window;
+// the log-likelihood field (last of the F) is zero unless it was produced
+__global__ void summary_finish_kernel(long long n_elems, int F, double n, int has_loglik, const double* __restrict__ sum,
+                                      const double* __restrict__ sumsq, double* __restrict__ mean, double* __restrict__ var) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= y_len * n_series) return;
-    const long long t = i / n_series;
-    const int s = (int)(i % n_series);
-    const double v = in[(long long)s * y_len + t];
-    y64[i] = v;
-    yr[i] = (R)v;
+    if (i >= n_elems) return;
+    const bool zero = !has_loglik && (int)(i % F) == F - 1;
+    const double m = sum[i] / n;
+    mean[i] = zero ? 0.0 : m;
+    var[i] = zero ? 0.0 : fmax(0.0, __dsub_rn(sumsq[i] / n, __dmul_rn(m, m)));      // rounded operation by operation, as the host did
 }
 
 template <typename R>
@@ -1200,7 +1226,7 @@ struct hmcgpu_plan {
     int n_slots = 0, n_warps = 0, chunk = 0, max_T = 0;
     GibbsArgs args{};
     // device buffers
-    DevBuf y64, yr, wbase, wTd, wi, slot_win, slot_chain, T, ybase, warp_T, warp_pi_off, pi, pacc, facc, cnt, trans, Sd, Qd,
+    DevBuf yr, wbase, wTd, wi, slot_win, slot_chain, T, ybase, warp_T, warp_pi_off, pi, pacc, facc, cnt, trans, Sd, Qd,
         events, cshift, xi, xi_user, chain_id, out, yfut_w, yfut, win_slot0, win_pib_off, totS, totQ, slot_pi_off;
     DevBuf sigmask, sigmask_tm, sigw, sbase, wsbase, wbase_init, X0, x0_off, cntM, Sm, Qm, totSm, totQm, totM;    // signals tier / user initial states
     bool sig = false;    // SIG kernels: signal mask and / or pi_row_back
@@ -1384,8 +1410,9 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     long long x0_total = 0;
     for (int w = 0; w < nw; ++w) {
         const int ser = p->win_series ? p->win_series[w] : 0;
-        wbase[w] = (long long)(p->win_start[w] - 1) * nser + ser;       // time-major [y_len][n_series]
-        wbase_init[w] = (long long)(p->win_start[w] - 1) * nser + (p->win_init_series ? p->win_init_series[w] : ser);
+        // the window statistics read the fp64 series as uploaded (series-major: a window is contiguous)
+        wbase[w] = (long long)ser * p->y_len + (p->win_start[w] - 1);
+        wbase_init[w] = (long long)(p->win_init_series ? p->win_init_series[w] : ser) * p->y_len + (p->win_start[w] - 1);
         x0_off[w] = x0_total;
         x0_total += pl->wT[w];
     }
@@ -1395,7 +1422,8 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         const unsigned long long wid = p->win_id ? (unsigned long long)p->win_id[w] : (unsigned long long)w;
         for (int cidx = 0; cidx < nc; ++cidx) {
             const int slot = j * nc + cidx;
-            slot_win[slot] = w; slot_chain[slot] = cidx; Ts[slot] = pl->wT[w]; ybase[slot] = wbase[w];
+            slot_win[slot] = w; slot_chain[slot] = cidx; Ts[slot] = pl->wT[w];
+            ybase[slot] = (long long)(p->win_start[w] - 1) * nser + (p->win_series ? p->win_series[w] : 0);   // time-major [y_len][n_series] (the sweeps)
             chain_id[slot] = (unsigned)(wid * (unsigned long long)nc + (unsigned long long)cidx);
         }
     }
@@ -1452,9 +1480,9 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     PhaseTrace tr;
     CU(ctx, up(yin, p->y, ny * sizeof(double)));
     tr.mark("  series upload enqueued");
-    CU(ctx, pl->y64.alloc(ny * sizeof(double)));
     CU(ctx, pl->yr.alloc(ny * sizeof(R)));
-    y_layout_kernel<R><<<grid_for((long long)ny, 256), 256, 0, st>>>(p->y_len, nser, yin.as<double>(), pl->y64.as<double>(), pl->yr.as<R>());
+    if ((p->y_len + 31) / 32 > 65535) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "series longer than %d observations", 65535 * 32);
+    y_layout_kernel<R><<<dim3((unsigned)((nser + 31) / 32), (unsigned)((p->y_len + 31) / 32)), 256, 0, st>>>(p->y_len, nser, yin.as<double>(), pl->yr.as<R>());
     CU(ctx, cudaGetLastError());
     CU(ctx, up(pl->wbase, wbase.data(), nw * sizeof(long long)));
     CU(ctx, up(pl->wTd, pl->wT.data(), nw * sizeof(int)));
@@ -1533,7 +1561,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     const size_t smem = (size_t)pl->max_T;
     if (smem > 200 * 1024) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "window longer than %d observations", 200 * 1024);
     if (smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute(window_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    window_init_kernel<<<nw, 256, smem, st>>>(K, pl->y64.as<double>(), nser, pl->wbase.as<long long>(), pl->wbase_init.as<long long>(),
+    window_init_kernel<<<nw, 256, smem, st>>>(K, yin.as<double>(), 1, pl->wbase.as<long long>(), pl->wbase_init.as<long long>(),
                                               pl->wTd.as<int>(), p->is_signal ? pl->sigmask_tm.as<unsigned char>() : nullptr,
                                               pl->wsbase.as<long long>(), sld, pl->X0.as<long long>(),
                                               pl->x0_off.as<long long>(), pl->wi.as<WinInit>());
@@ -1866,12 +1894,19 @@ static int plan_fetch_impl(hmcgpu_plan* pl, hmcgpu_result* r) {
     CU(ctx, down(r->pi_end, pl->d_pie, nw * Rr * K * sizeof(double)));
     CU(ctx, down(r->forecasts, pl->d_fc, nw * Rr * 2 * pl->n_h * sizeof(double)));
     CU(ctx, down(r->loglik, pl->d_ll, nw * Rr * sizeof(double)));
-    std::vector<double> sum, sumsq, pibsum, fcsum;
+    std::vector<double> pibsum, fcsum;
     std::vector<int> ev(pl->n_slots);
+    DevBuf d_mean, d_var;                                     // (released after the stream has drained, below)
     if (r->summary_mean || r->summary_var) {
-        sum.resize((size_t)nw * pl->F); sumsq.resize((size_t)nw * pl->F);
-        CU(ctx, down(sum.data(), pl->d_sum, sum.size() * sizeof(double)));
-        CU(ctx, down(sumsq.data(), pl->d_sumsq, sumsq.size() * sizeof(double)));
+        // finished on the device and copied straight into the caller's arrays (no host-side pass over n_windows x F values)
+        const long long ne = (long long)nw * pl->F;
+        CU(ctx, d_mean.alloc((size_t)ne * sizeof(double)));
+        CU(ctx, d_var.alloc((size_t)ne * sizeof(double)));
+        summary_finish_kernel<<<grid_for(ne, 256), 256, 0, st>>>(ne, pl->F, (double)Rr, (pl->flags & HMCGPU_FLAG_LOGLIK) ? 1 : 0,
+                                                                 pl->d_sum.as<double>(), pl->d_sumsq.as<double>(), d_mean.as<double>(), d_var.as<double>());
+        CU(ctx, cudaGetLastError());
+        CU(ctx, down(r->summary_mean, d_mean, (size_t)ne * sizeof(double)));
+        CU(ctx, down(r->summary_var, d_var, (size_t)ne * sizeof(double)));
     }
     if (r->pib_mean) { pibsum.resize((size_t)pl->pib_total); CU(ctx, down(pibsum.data(), pl->d_pibsum, pibsum.size() * sizeof(double))); }
     if (r->insample_forecast_mean && pl->d_fcsum.p) {
@@ -1881,16 +1916,6 @@ static int plan_fetch_impl(hmcgpu_plan* pl, hmcgpu_result* r) {
     CU(ctx, down(ev.data(), pl->events, ev.size() * sizeof(int)));
     CU(ctx, cudaStreamSynchronize(st));
     const double n = (double)Rr;
-    for (size_t i = 0; i < sum.size(); ++i) {
-        const double m = sum[i] / n;
-        if (r->summary_mean) r->summary_mean[i] = m;
-        if (r->summary_var) r->summary_var[i] = std::max(0.0, sumsq[i] / n - m * m);
-    }
-    if (!sum.empty() && !(pl->flags & HMCGPU_FLAG_LOGLIK))      // the log-likelihood field is only produced with HMCGPU_FLAG_LOGLIK
-        for (int w = 0; w < nw; ++w) {
-            if (r->summary_mean) r->summary_mean[(size_t)w * pl->F + pl->F - 1] = 0.0;
-            if (r->summary_var) r->summary_var[(size_t)w * pl->F + pl->F - 1] = 0.0;
-        }
     for (size_t i = 0; i < pibsum.size(); ++i) r->pib_mean[i] = pibsum[i] / n;
     for (size_t i = 0; i < fcsum.size(); ++i) r->insample_forecast_mean[i] = fcsum[i] / n;
     // slot order -> caller order
