@@ -713,6 +713,11 @@ static cudaError_t staged_upload(hmcgpu_ctx* ctx, void* dev, const void* host, s
 struct PhaseTrace {
     const bool on = getenv("HMCGPU_VERBOSE") != nullptr && atoi(getenv("HMCGPU_VERBOSE")) != 0;
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void sync_mark(cudaStream_t st, const char* what) {      // (tracing only) drains the stream first: device time of what was queued
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        mark(what);
+    }
     void mark(const char* what) {
         if (!on) return;
         const auto t1 = std::chrono::steady_clock::now();
@@ -1390,7 +1395,9 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
             // the thread-per-chain kernel beyond; in units of one wave of thread slots (16 warps per SM):
             const long long full = (long long)ctx->sm_count * 16 * 32;
             if (n_real * 2 <= full) lanes = 4;
-            else if (n_real * 4 <= 5 * full) lanes = 2;
+            // (2 lanes only when the chains share one series: a batch of distinct series streams every observation from HBM in each
+            //  of the segment kernel's passes — C4, 65 536 series: 143 ms with 2 lanes, 139 ms with 4, 109 ms with a thread per chain)
+            else if (n_real * 4 <= 5 * full && nser == 1) lanes = 2;
             if (const char* e = getenv("HMCGPU_SEG_LANES")) lanes = atoi(e);
             if (lanes != 0 && lanes != 2 && lanes != 4) return fail(ctx, HMCGPU_ERR_ARG, "HMCGPU_SEG_LANES must be 0, 2 or 4");
             const long long tmax = K == 2 ? seg_max_T<2>(lanes) : K == 3 ? seg_max_T<3>(lanes) : seg_max_T<4>(lanes);
@@ -1484,6 +1491,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     if ((p->y_len + 31) / 32 > 65535) return fail(ctx, HMCGPU_ERR_UNSUPPORTED, "series longer than %d observations", 65535 * 32);
     y_layout_kernel<R><<<dim3((unsigned)((nser + 31) / 32), (unsigned)((p->y_len + 31) / 32)), 256, 0, st>>>(p->y_len, nser, yin.as<double>(), pl->yr.as<R>());
     CU(ctx, cudaGetLastError());
+    tr.sync_mark(st, "  series layout kernel");
     CU(ctx, up(pl->wbase, wbase.data(), nw * sizeof(long long)));
     CU(ctx, up(pl->wTd, pl->wT.data(), nw * sizeof(int)));
     CU(ctx, up(pl->slot_win, slot_win.data(), n_slots * sizeof(int)));
@@ -1566,6 +1574,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
                                               pl->wsbase.as<long long>(), sld, pl->X0.as<long long>(),
                                               pl->x0_off.as<long long>(), pl->wi.as<WinInit>());
     CU(ctx, cudaGetLastError());
+    tr.sync_mark(st, "  tables, allocations, window statistics");
     yfut_kernel<R><<<grid_for(n_slots, 128), 128, 0, st>>>(n_slots, p->n_h, pl->slot_win.as<int>(), pl->yfut_w.as<double>(), pl->yfut.as<R>());
     CU(ctx, cudaGetLastError());
 
