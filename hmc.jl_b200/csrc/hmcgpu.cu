@@ -954,26 +954,54 @@ __device__ T block_reduce(T v, T* sh, Op op) {   // deterministic tree, result b
     return r;
 }
 
-// k-th smallest (0-based) by radix select on the order-preserving 64-bit image of the doubles
+// k-th smallest (0-based) by radix select on the order-preserving 64-bit image of the doubles: passes of 4 bits from the top,
+// per-warp histograms in shared memory (sh: at least 8 x 16 + 16 + 2 words), bins summed by 16 threads and walked by one; as soon
+// as the selected bin holds a single candidate (typically after the exponent and ~3 mantissa digits) that element is the answer
 __device__ double block_select(const double* y, size_t yld, int N, int k, unsigned long long* sh) {
+    unsigned* const hist = reinterpret_cast<unsigned*>(sh);       // [warp][16]
+    const int nwarp = (int)(blockDim.x >> 5), warp = (int)(threadIdx.x >> 5);
+    unsigned* const bins = hist + nwarp * 16;                     // [16] block totals
+    unsigned* const pick = bins + 16;                             // [0] digit, [1] k inside the bin, [2] candidates in the bin
+    unsigned long long* const found = sh + 128;                   // the single remaining candidate (behind the histograms in the 256 x 8-byte scratch)
     unsigned long long prefix = 0, mask = 0;
-    for (int bit = 63; bit >= 0; --bit) {
-        const unsigned long long b = 1ull << bit;
-        unsigned cl = 0;
+    for (int shift = 60; shift >= 0; shift -= 4) {
+        for (int q = threadIdx.x; q < nwarp * 16; q += blockDim.x) hist[q] = 0u;
+        __syncthreads();
         for (int i = threadIdx.x; i < N; i += blockDim.x) {
             const unsigned long long key = orderable(y[(size_t)i * yld]);
-            cl += ((key & mask) == prefix && !(key & b)) ? 1u : 0u;
+            if ((key & mask) == prefix) atomicAdd(&hist[warp * 16 + (int)((key >> shift) & 15ull)], 1u);
         }
-        // integer count: one warp reduction, one shared-memory line of per-warp sums, two barriers per bit
-        cl = __reduce_add_sync(0xffffffffu, cl);
-        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cl;
         __syncthreads();
-        unsigned long long c = 0;
-        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) c += sh[q];
+        if (threadIdx.x < 16) {
+            unsigned c = 0;
+            for (int w = 0; w < nwarp; ++w) c += hist[w * 16 + threadIdx.x];
+            bins[threadIdx.x] = c;
+        }
         __syncthreads();
-        if ((unsigned long long)k >= c) { prefix |= b; k -= (int)c; }
-        mask |= b;
+        if (threadIdx.x == 0) {
+            int digit = 15, kk = k;
+            for (int b = 0; b < 16; ++b) {
+                if ((unsigned)kk < bins[b]) { digit = b; break; }
+                kk -= (int)bins[b];
+            }
+            pick[0] = (unsigned)digit; pick[1] = (unsigned)kk; pick[2] = bins[digit];
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)pick[0] << shift;
+        mask |= 15ull << shift;
+        k = (int)pick[1];
+        if (pick[2] == 1u && shift > 0) {                         // one candidate left: fetch it
+            for (int i = threadIdx.x; i < N; i += blockDim.x) {
+                const unsigned long long key = orderable(y[(size_t)i * yld]);
+                if ((key & mask) == prefix) *found = key;
+            }
+            __syncthreads();
+            prefix = *found;
+            __syncthreads();
+            break;
+        }
     }
+    __syncthreads();
     return from_orderable(prefix);
 }
 
@@ -1029,34 +1057,42 @@ __global__ void __launch_bounds__(256) window_init_kernel(int K, const double* _
         x0[i] = (unsigned char)best;
     }
     __syncthreads();
-    // statistics of X0 in serial time order (deterministic): thread i < K -> state i, thread K+j -> transition pair j
-    const int tid = threadIdx.x;
-    for (int q = tid; q < K + K * K; q += blockDim.x) {
-        if (q < K) {
-            double c = 0.0, sdv = 0.0, qd = 0.0, cm = 0.0, sm = 0.0, qm = 0.0;
-            for (int i = 0; i < N; ++i)
-                if (x0[i] == q) {
-                    const double d = y[i * ld] - mean;
-                    if (sg && sg[(size_t)i * sld]) { cm += 1.0; sm += d; qm += d * d; }
-                    else { c += 1.0; sdv += d; qd += d * d; }
-                }
-            out[w].cnt[q] = c; out[w].Sd[q] = sdv; out[w].Qd[q] = qd;
-            out[w].cntM[q] = cm; out[w].Sm[q] = sm; out[w].Qm[q] = qm;
-        } else {
-            const int j = q - K, r = j / K, s2 = j % K;
-            double c = 0.0;
-            for (int i = 0; i + 1 < N; ++i) c += (x0[i] == r && x0[i + 1] == s2) ? 1.0 : 0.0;
-            out[w].trans[j] = c;
+    // statistics of X0, deterministic (fixed reduction trees; the integer counts are exact in any order).  Transition pairs: integer
+    // atomics on a shared K x K table.  Per-state sums: one warp per state, lanes striding through time, shuffle tree.  (A single
+    // thread per quantity walking the window in time order made this kernel 15 ms for 65 536 windows of 2000 observations.)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = (int)(blockDim.x >> 5);
+    __shared__ int trc[32 * 32];
+    __shared__ double stat[6][32];
+    for (int q = tid; q < K * K; q += blockDim.x) trc[q] = 0;
+    __syncthreads();
+    for (int i = tid; i + 1 < N; i += blockDim.x) atomicAdd(&trc[(int)x0[i] * K + (int)x0[i + 1]], 1);
+    for (int q = warp; q < K; q += nwarp) {
+        double c = 0.0, sdv = 0.0, qd = 0.0, cm = 0.0, sm = 0.0, qm = 0.0;
+        for (int i = lane; i < N; i += 32)
+            if (x0[i] == q) {
+                const double d = y[i * ld] - mean;
+                if (sg && sg[(size_t)i * sld]) { cm += 1.0; sm += d; qm += d * d; }
+                else { c += 1.0; sdv += d; qd += d * d; }
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, o); sdv += __shfl_xor_sync(0xffffffffu, sdv, o); qd += __shfl_xor_sync(0xffffffffu, qd, o);
+            cm += __shfl_xor_sync(0xffffffffu, cm, o); sm += __shfl_xor_sync(0xffffffffu, sm, o); qm += __shfl_xor_sync(0xffffffffu, qm, o);
         }
+        if (lane == 0) { stat[0][q] = c; stat[1][q] = sdv; stat[2][q] = qd; stat[3][q] = cm; stat[4][q] = sm; stat[5][q] = qm; }
     }
+    __syncthreads();
+    for (int q = tid; q < K; q += blockDim.x) {
+        out[w].cnt[q] = stat[0][q]; out[w].Sd[q] = stat[1][q]; out[w].Qd[q] = stat[2][q];
+        out[w].cntM[q] = stat[3][q]; out[w].Sm[q] = stat[4][q]; out[w].Qm[q] = stat[5][q];
+    }
+    for (int j = tid; j < K * K; j += blockDim.x) out[w].trans[j] = (double)trc[j];
     if (tid == 0) {
         out[w].mean = mean;
+        // window totals of both classes = the per-state sums added in state order (the kernels derive the last state's statistics
+        // as total minus the others: the two are consistent to the last bit by construction)
         double a = 0.0, b = 0.0, am = 0.0, bm = 0.0, m = 0.0;
-        for (int i = 0; i < N; ++i) {
-            const double d = y[i * ld] - mean;
-            if (sg && sg[(size_t)i * sld]) { am += d; bm += d * d; m += 1.0; }
-            else { a += d; b += d * d; }
-        }
+        for (int q = 0; q < K; ++q) { a += stat[1][q]; b += stat[2][q]; am += stat[4][q]; bm += stat[5][q]; m += stat[3][q]; }
         out[w].totS = a; out[w].totQ = b; out[w].totSm = am; out[w].totQm = bm; out[w].totM = m;
     }
 }
