@@ -30,7 +30,7 @@ SYMBOLS = [
     "hmcgpu_build_info", "hmcgpu_ctx_trim",
 ]
 KERNEL_NAMES = {0: "gibbs_sweeps_kernel (thread per chain)", 1: "gibbs_scan_kernel (warp per chain, time-parallel)",
-                2: "gibbs_wide_kernel (lane per state)", 3: "gibbs_pair_kernel (two chains per thread)",
+                2: "gibbs_wide_kernel (lane per state)", 3: "(reserved)",
                 4: "gibbs_seg_kernel (L lanes per chain, one time segment per lane)"}
 
 _dp = C.POINTER(C.c_double)

@@ -6,9 +6,6 @@
 #include "gibbs_scan_kernel.cuh"
 #include "gibbs_seg_kernel.cuh"
 #endif
-#ifdef HMC_WITH_PAIR
-#include "gibbs_pair_kernel.cuh"
-#endif
 
 namespace hmc {
 
@@ -70,24 +67,6 @@ template <typename R, int K> int gibbs_capacity_warps(const GibbsLaunch& cfg) {
 
 template cudaError_t launch_gibbs<HMC_R, HMC_K>(const GibbsLaunch&, const GibbsArgs&, cudaStream_t);
 
-#ifdef HMC_WITH_PAIR
-// fp32 only: two chains per thread, packed FP32x2 arithmetic (gibbs_pair_kernel.cuh); a task is 64 chains
-template <int K> cudaError_t launch_gibbs_pair(const GibbsLaunch& cfg, const GibbsArgs& a, cudaStream_t st) {
-    const unsigned grid = (unsigned)((a.n_tasks + kGibbsThreads / 32 - 1) / (kGibbsThreads / 32));
-    const bool ll = cfg.flags & 16u;
-    auto go = [&](auto kern, size_t smem) -> cudaError_t {
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-        kern<<<grid, kGibbsThreads, smem, st>>>(a);
-        return cudaGetLastError();
-    };
-    if (wide_rows<K>(cfg)) return ll ? go(gibbs_pair_kernel<K, true, true>, kPairSmemBytes<K, true>()) : go(gibbs_pair_kernel<K, false, true>, kPairSmemBytes<K, true>());
-    return ll ? go(gibbs_pair_kernel<K, true, false>, kPairSmemBytes<K, false>()) : go(gibbs_pair_kernel<K, false, false>, kPairSmemBytes<K, false>());
-}
-template cudaError_t launch_gibbs_pair<HMC_K>(const GibbsLaunch&, const GibbsArgs&, cudaStream_t);
-#endif
 template int gibbs_capacity_warps<HMC_R, HMC_K>(const GibbsLaunch&);
 
 #if HMC_K <= 4

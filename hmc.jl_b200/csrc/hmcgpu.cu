@@ -2,7 +2,6 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --shared (see hmc.jl_b200/build.py).
 #include "../../include/hmcgpu.h"
 #include "gibbs_wide_kernel.cuh"
-#include "gibbs_pair_kernel.cuh"
 #include "gibbs_scan_kernel.cuh"
 #include "gibbs_seg_kernel.cuh"
 
@@ -1273,7 +1272,6 @@ struct hmcgpu_plan {
     bool sig = false;    // SIG kernels: signal mask and / or pi_row_back
     bool scan = false;   // narrow batch: one warp per chain, time-parallel (gibbs_scan_kernel.cuh)
     bool wide = false;
-    bool pair = false;   // fp32 paired kernel: a task is 64 chain slots (two chains per thread)
     bool seg = false;    // mid-width batch: L lanes per chain, each lane one contiguous time segment (gibbs_seg_kernel.cuh)
     int seg_lanes = 0;   // L (a warp task holds 32 / L chains)
     int seg_threads = 128; // threads per block of the segment kernel
@@ -1391,18 +1389,10 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     std::iota(pl->order.begin(), pl->order.end(), 0);
     std::stable_sort(pl->order.begin(), pl->order.end(), [&](int a, int b) { return pl->wT[a] > pl->wT[b]; });
 
-    // slots: windows by decreasing T, chains consecutive; padded to a multiple of the task size (32 chains per warp task,
-    // 64 for the fp32 paired kernel, which needs an even number of chains per window so that a pair shares its window)
+    // slots: windows by decreasing T, chains consecutive; padded to a multiple of the task size (32 chains per warp task)
     pl->wide = !k_thread_sweep(K);
     pl->sig = p->is_signal != nullptr || p->pi_row_back != 0;
     const unsigned kAccMean = HMCGPU_FLAG_SMOOTHED_MEAN | HMCGPU_FLAG_FILTERED_MEAN;   // per-date means: thread-per-chain kernels only
-    pl->pair = !pl->wide && K <= 4 && !pl->sig && p->precision == 32 && nc % 2 == 0 && !(p->flags & kAccMean);
-    // Two chains per thread cut the instruction count by 30 % but need 168 registers (12 warps per SM): measured slower
-    // than the scalar kernel unless the batch is far wider than the machine, so it is opt-in.
-    {
-        const char* e = getenv("HMCGPU_PAIR");
-        pl->pair = pl->pair && e && atoi(e) != 0;
-    }
     // Narrow batches (the reference's own regime: one chain per end date) cannot fill the GPU with a thread per chain:
     // below kScanMaxChains chains the time-parallel warp-per-chain kernel is used (K <= 4, plain sweep, window in smem).
     {
@@ -1417,7 +1407,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         const size_t wb = (size_t)(p->precision / 8) * ((size_t)pl->max_T * (K + 1) + 4 * K);
         const long long blocks = std::max<long long>(1, std::min<long long>(5, (long long)((227 * 1024) / (4 * wb + 1024))));
         lim = lim * blocks / 5;
-        pl->scan = !pl->wide && K <= 4 && !pl->pair && !(p->flags & kAccMean) &&
+        pl->scan = !pl->wide && K <= 4 && !(p->flags & kAccMean) &&
                    (long long)nw * nc <= lim && pl->max_T <= tmax;
     }
     const long long n_real = (long long)nw * nc;
@@ -1426,7 +1416,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     // warps; HMCGPU_SEG_LANES forces it (0 = never).  K <= 4, plain sweep.
     {
         int lanes = 0;
-        if (!pl->wide && K <= 4 && !pl->sig && !pl->pair && !pl->scan && !(p->flags & kAccMean)) {
+        if (!pl->wide && K <= 4 && !pl->sig && !pl->scan && !(p->flags & kAccMean)) {
             // measured on C2 (500 windows x c chains, B200): 4 lanes per chain are best up to ~38 000 chains, 2 lanes up to ~90 000,
             // the thread-per-chain kernel beyond; in units of one wave of thread slots (16 warps per SM):
             const long long full = (long long)ctx->sm_count * 16 * 32;
@@ -1442,7 +1432,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         pl->seg = lanes != 0;
         pl->seg_lanes = lanes;
     }
-    const int ts = pl->pair ? 64 : 32;
+    const int ts = 32;
     const int n_slots = (int)((n_real + ts - 1) / ts * ts);
     const int cpt = pl->seg ? 32 / pl->seg_lanes : ts;      // chains per warp task
     const int n_warps = n_slots / cpt;                      // number of warp tasks
@@ -1484,7 +1474,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
             pi_elems += (long long)Cs * K * 32;
         }
         // thread-per-chain kernels: rows right-aligned to tiles of 4 time steps (gibbs_kernel.cuh, st_quad)
-        else if (!pl->wide) pi_elems += (long long)(pl->pair ? m : (m + 3) / 4 * 4) * K * ts;
+        else if (!pl->wide) pi_elems += (long long)((m + 3) / 4 * 4) * K * ts;
         else for (int l = 0; l < ts; ++l) { slot_off[wp * ts + l] = pi_elems; pi_elems += (long long)Ts[wp * ts + l] * K; }
     }
     // forecasts: realised y at end+h per window (NaN outside the series), horizons sorted ascending
@@ -1814,10 +1804,7 @@ static int plan_run_t(hmcgpu_plan* pl) {
             } else if constexpr (K <= 4) {
                 if (pl->scan) CU(ctx, (launch_gibbs_scan<R, K>(cfg, a, gs)));
                 else if (pl->seg) CU(ctx, (launch_gibbs_seg<R, K>(cfg, a, pl->seg_lanes, pl->seg_threads, gs)));
-                else if constexpr (std::is_same<R, float>::value) {
-                    if (pl->pair) CU(ctx, (launch_gibbs_pair<K>(cfg, a, gs)));
-                    else CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
-                } else CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
+                else CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
             } else {
                 CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
             }
@@ -1977,7 +1964,7 @@ static int plan_fetch_impl(hmcgpu_plan* pl, hmcgpu_result* r) {
     r->gpu_ms = pl->gpu_ms; r->sweep_kernel_ms = pl->sweep_ms; r->n_launches = pl->n_launches;
     r->n_sweep_launches = pl->n_sweep_launches; r->h2d_bytes = pl->h2d; r->d2h_bytes = d2h; r->state_steps = pl->state_steps;
     r->sweep_launch_ms_sum = pl->launch_ms_sum;
-    r->sweep_kernel = pl->wide ? HMCGPU_KERNEL_LANE : pl->scan ? HMCGPU_KERNEL_SCAN : pl->pair ? HMCGPU_KERNEL_PAIR : pl->seg ? HMCGPU_KERNEL_SEG : HMCGPU_KERNEL_THREAD;
+    r->sweep_kernel = pl->wide ? HMCGPU_KERNEL_LANE : pl->scan ? HMCGPU_KERNEL_SCAN : pl->seg ? HMCGPU_KERNEL_SEG : HMCGPU_KERNEL_THREAD;
     r->n_tasks = pl->n_warps;
     return bad;
 }

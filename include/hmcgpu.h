@@ -149,7 +149,7 @@ typedef struct hmcgpu_result {
 #define HMCGPU_KERNEL_THREAD 0  /* one thread per chain (gibbs_sweeps_kernel), wide batches, K <= 8 */
 #define HMCGPU_KERNEL_SCAN 1    /* one warp per chain, time-parallel scans (gibbs_scan_kernel), narrow batches */
 #define HMCGPU_KERNEL_LANE 2    /* one lane per state (gibbs_wide_kernel), K = 9..32 */
-#define HMCGPU_KERNEL_PAIR 3    /* two chains per thread (gibbs_pair_kernel), opt-in */
+#define HMCGPU_KERNEL_PAIR 3    /* reserved (the two-chains-per-thread kernel of round 1 was removed: slower than the default at every width) */
 #define HMCGPU_KERNEL_SEG 4     /* L lanes per chain, each lane a contiguous time segment (gibbs_seg_kernel), mid-width batches */
 
 int hmcgpu_version(void);
