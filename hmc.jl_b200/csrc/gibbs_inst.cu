@@ -108,6 +108,7 @@ template <typename R, int K> cudaError_t launch_gibbs_seg(const GibbsLaunch& cfg
     switch (lanes) {
         case 2: return ll ? go(gibbs_seg_kernel<R, K, 2, true>) : go(gibbs_seg_kernel<R, K, 2, false>);
         case 4: return ll ? go(gibbs_seg_kernel<R, K, 4, true>) : go(gibbs_seg_kernel<R, K, 4, false>);
+        case 8: return ll ? go(gibbs_seg_kernel<R, K, 8, true>) : go(gibbs_seg_kernel<R, K, 8, false>);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -53,6 +53,11 @@ template <typename R> __host__ __device__ constexpr size_t wide_group_bytes(int 
     return (sizeof(R) * ((size_t)K * wide_row_stride(K) + 2 * (size_t)W) + sizeof(int) * (size_t)K * K + 15) / 16 * 16;
 }
 
+#ifndef HMC_WIDE_PACKED
+#define HMC_WIDE_PACKED 0   // 1: the fp32 matrix-vector step of the forward recursion as W/2 FFMA2 in two accumulation chains instead of W FFMA in
+                            // four.  Measured SLOWER (K = 32: 2.74 vs 2.92e9 state-steps/s, K = 16: 5.53 vs 5.65e9, same box): the step is latency-bound
+                            // and the packed form halves its independent chains.  Kept as an A/B knob.
+#endif
 #ifndef HMC_WIDE_MINBLOCKS32
 #define HMC_WIDE_MINBLOCKS32 5
 #endif
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(kWideThreads, sizeof(R) == 8 ? 3 : (W == 32 ? 
         // column s of A in registers (zero outside K x K): pred_s = sum_r pf_r A[r][s]
         // (fp32: kept as W/2 packed pairs, so the matrix-vector step below is W/2 FFMA2 instead of W FFMA — same products, same
         //  four accumulation chains, bit-identical sums)
-        constexpr bool kPacked = sizeof(R) == 4;
+        constexpr bool kPacked = HMC_WIDE_PACKED && sizeof(R) == 4;
         R Ac[kPacked ? 1 : W];
         f2 Ac2[kPacked ? W / 2 : 1];
 #pragma unroll

@@ -1425,7 +1425,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
             //  of the segment kernel's passes — C4, 65 536 series: 143 ms with 2 lanes, 139 ms with 4, 109 ms with a thread per chain)
             else if (n_real * 4 <= 5 * full && nser == 1) lanes = 2;
             if (const char* e = getenv("HMCGPU_SEG_LANES")) lanes = atoi(e);
-            if (lanes != 0 && lanes != 2 && lanes != 4) return fail(ctx, HMCGPU_ERR_ARG, "HMCGPU_SEG_LANES must be 0, 2 or 4");
+            if (lanes != 0 && lanes != 2 && lanes != 4 && lanes != 8) return fail(ctx, HMCGPU_ERR_ARG, "HMCGPU_SEG_LANES must be 0, 2, 4 or 8");
             const long long tmax = K == 2 ? seg_max_T<2>(lanes) : K == 3 ? seg_max_T<3>(lanes) : seg_max_T<4>(lanes);
             if (lanes && pl->max_T > tmax) lanes = 0;
         }

@@ -26,7 +26,8 @@ def _sweep_kernel_choice(request, monkeypatch):
     problems fall through to the thread-per-chain kernels as in production)."""
     if request.param in ("thread", "seg"):
         monkeypatch.setenv("HMCGPU_SCAN_MAX_CHAINS", "0")
-        monkeypatch.setenv("HMCGPU_SEG_LANES", "4" if request.param == "seg" else "0")
+        # (HMC_TEST_SEG_LANES=2 / 8: the same suite on the other segment counts)
+        monkeypatch.setenv("HMCGPU_SEG_LANES", os.environ.get("HMC_TEST_SEG_LANES", "4") if request.param == "seg" else "0")
     return request.param
 
 
