@@ -91,6 +91,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             return LIB                          # side libraries are never rebuilt implicitly
         if "-DHMC_DEV_F3" in DEFS:              # fp32, K=3 only: the bench path, for quick A/B builds
             units = [u for u in UNITS if u[0] in ("hmcgpu", "build_info", "gibbs_float_3", "gibbs_wide_float")]
+        if "-DHMC_DEV_D3" in DEFS:              # fp64, K=3 only
+            units = [u for u in UNITS if u[0] in ("hmcgpu", "build_info", "gibbs_double_3", "gibbs_wide_double")]
     want = source_hash()
     if not force and os.path.exists(LIB) and built_hash(LIB) == want:
         return LIB                              # e.g. on the GPU box: the prebuilt library travels, the objects do not

@@ -222,6 +222,8 @@ static bool k_thread_sweep(int K) {
     }
 #ifdef HMC_DEV_F3   /* experiment builds: only the fp32 K=3 sweep kernels are linked */
 #define DISPATCH_RUN(pl, rc) do { if ((pl)->precision == 32) { if ((pl)->wide) rc = plan_run_t<float, 0>(pl); else if ((pl)->K == 3) rc = plan_run_t<float, 3>(pl); } } while (0)
+#elif defined(HMC_DEV_D3)   /* ... or only the fp64 K=3 ones */
+#define DISPATCH_RUN(pl, rc) do { if ((pl)->precision == 64) { if ((pl)->wide) rc = plan_run_t<double, 0>(pl); else if ((pl)->K == 3) rc = plan_run_t<double, 3>(pl); } } while (0)
 #else
 #define DISPATCH_K8(K, ...)                         \
     switch (K) {                                    \
