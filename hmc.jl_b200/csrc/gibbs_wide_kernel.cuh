@@ -55,8 +55,8 @@ template <typename R> __host__ __device__ constexpr size_t wide_group_bytes(int 
 
 #ifndef HMC_WIDE_PACKED
 #define HMC_WIDE_PACKED 0   // 1: the fp32 matrix-vector step of the forward recursion as W/2 FFMA2 in two accumulation chains instead of W FFMA in
-                            // four.  Measured SLOWER (K = 32: 2.74 vs 2.92e9 state-steps/s, K = 16: 5.53 vs 5.65e9, same box): the step is latency-bound
-                            // and the packed form halves its independent chains.  Kept as an A/B knob.
+                            // four.  Measured a wash (K = 32: 2.73 vs 2.76e9 state-steps/s, K = 16: 5.51 vs 5.46e9, same box, back to back): the
+                            // step is latency-bound, the 16 saved issue slots buy nothing.  Kept as an A/B knob, off.
 #endif
 #ifndef HMC_WIDE_MINBLOCKS32
 #define HMC_WIDE_MINBLOCKS32 5
@@ -216,8 +216,13 @@ __global__ void __launch_bounds__(kWideThreads, sizeof(R) == 8 ? 3 : (W == 32 ? 
 #pragma unroll
                 for (int r0 = 0; r0 < W; r0 += kVec) {
                     const V v = *reinterpret_cast<const V*>(line + r0);
-                    acc[(r0 / 2) & 3] = fma((R)v.x, Ac[r0], acc[(r0 / 2) & 3]);
-                    acc[(r0 / 2 + 1) & 3] = fma((R)v.y, Ac[r0 + 1], acc[(r0 / 2 + 1) & 3]);
+                    if constexpr (sizeof(R) == 4) {
+                        acc[0] = fma((R)v.x, Ac[r0], acc[0]); acc[1] = fma((R)v.y, Ac[r0 + 1], acc[1]);
+                        acc[2] = fma((R)v.z, Ac[r0 + 2], acc[2]); acc[3] = fma((R)v.w, Ac[r0 + 3], acc[3]);
+                    } else {
+                        acc[(r0 / 2) & 3] = fma((R)v.x, Ac[r0], acc[(r0 / 2) & 3]);
+                        acc[(r0 / 2 + 1) & 3] = fma((R)v.y, Ac[r0 + 1], acc[(r0 / 2 + 1) & 3]);
+                    }
                 }
             }
             const R pred = (acc[0] + acc[1]) + (acc[2] + acc[3]);
