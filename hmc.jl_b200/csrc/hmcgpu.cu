@@ -1276,6 +1276,12 @@ struct hmcgpu_plan {
     bool wide = false;
     bool seg = false;    // mid-width batch: L lanes per chain, each lane one contiguous time segment (gibbs_seg_kernel.cuh)
     int seg_lanes = 0;   // L (a warp task holds 32 / L chains)
+    // Mixed segment counts (mid-width batches with spare thread slots): the n_long longest windows run with 8 lanes per chain,
+    // in their own slot range [0, long_slots) with their own warp-task tables (task id = slot / 4)
+    int n_long = 0, long_slots = 0;
+    DevBuf warp_T_long, warp_pi_off_long;
+    struct Group { int task0, stride, n_tasks, lanes; bool long_class; };
+    std::vector<Group> groups;                // one stream each (plan_run)
     int seg_threads = 128; // threads per block of the segment kernel
     int n_groups = 1, n_bufs = 1;
     std::vector<cudaStream_t> gstreams;
@@ -1433,11 +1439,29 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         }
         pl->seg = lanes != 0;
         pl->seg_lanes = lanes;
+        // With 4 lanes per chain and thread slots to spare, the sweep time is the serial time of the LONGEST windows (every warp is
+        // resident from the start; a 16 000-chain batch leaves a fifth of the slots empty).  The longest tenth of the windows (in
+        // `order`) then gets 8 lanes per chain — half the dependent steps per sweep — as far as the slots last.  Measured on C2
+        // (HMCGPU_SEG_LONG sweep, scripts/r2_call_j.sh): 50 of 500 windows +7 % at 16 chains per window, +2 % at 24, +4 % at 32;
+        // 100 windows +7 % at 32 but -5 % at 24; 300 or all of them lose everywhere (8 lanes pay more per-sweep work per chain).
+        // HMCGPU_SEG_MIXED=0 disables it; a forced HMCGPU_SEG_LANES is uniform.
+        if (lanes == 4 && !getenv("HMCGPU_SEG_LANES") && !(getenv("HMCGPU_SEG_MIXED") && atoi(getenv("HMCGPU_SEG_MIXED")) == 0)) {
+            const long long full = (long long)ctx->sm_count * 16 * 32;
+            const long long spare = full * 115 / 100 - n_real * 4;
+            long long n8 = spare > 0 ? std::min<long long>(nw / 10, spare / ((long long)nc * 4)) : 0;
+            while (n8 > 0 && pl->wT[pl->order[n8 - 1]] < 128) --n8;          // (segments of fewer than 16 steps are all warm-up)
+            if (const char* e = getenv("HMCGPU_SEG_LONG")) n8 = std::max(0ll, std::min<long long>(nw, atoll(e)));
+            const long long tmax8 = K == 2 ? seg_max_T<2>(8) : K == 3 ? seg_max_T<3>(8) : seg_max_T<4>(8);
+            if (n8 * nc >= 32 && pl->max_T <= tmax8) pl->n_long = (int)n8;
+        }
     }
     const int ts = 32;
-    const int n_slots = (int)((n_real + ts - 1) / ts * ts);
+    // slots: [long class (8 lanes), padded to 32][the rest, padded to 32]
+    const int long_slots = (int)(((long long)pl->n_long * nc + ts - 1) / ts * ts);
+    pl->long_slots = long_slots;
+    const int n_slots = long_slots + (int)((n_real - (long long)pl->n_long * nc + ts - 1) / ts * ts);
     const int cpt = pl->seg ? 32 / pl->seg_lanes : ts;      // chains per warp task
-    const int n_warps = n_slots / cpt;                      // number of warp tasks
+    const int n_warps = n_slots / cpt;                      // number of warp tasks (task id = slot / cpt; ids below long_slots / cpt are unused when there is a long class)
     pl->n_slots = n_slots; pl->n_warps = n_warps;
     std::vector<int> slot_win(n_slots, -1), slot_chain(n_slots, 0), Ts(n_slots, 0), win_slot0(nw), warp_T(n_warps, 0);
     std::vector<long long> ybase(n_slots, 0), warp_off(n_warps, 0), wbase(nw), wbase_init(nw), x0_off(nw);
@@ -1453,10 +1477,11 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     }
     for (int j = 0; j < nw; ++j) {
         const int w = pl->order[j];
-        win_slot0[w] = j * nc;
+        const int s0w = j < pl->n_long ? j * nc : long_slots + (j - pl->n_long) * nc;
+        win_slot0[w] = s0w;
         const unsigned long long wid = p->win_id ? (unsigned long long)p->win_id[w] : (unsigned long long)w;
         for (int cidx = 0; cidx < nc; ++cidx) {
-            const int slot = j * nc + cidx;
+            const int slot = s0w + cidx;
             slot_win[slot] = w; slot_chain[slot] = cidx; Ts[slot] = pl->wT[w];
             ybase[slot] = (long long)(p->win_start[w] - 1) * nser + (p->win_series ? p->win_series[w] : 0);   // time-major [y_len][n_series] (the sweeps)
             chain_id[slot] = (unsigned)(wid * (unsigned long long)nc + (unsigned long long)cidx);
@@ -1464,7 +1489,18 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     }
     long long pi_elems = 0;
     std::vector<long long> slot_off(n_slots, 0);
-    for (int wp = 0; wp < n_warps; ++wp) {
+    // the long class first (8 lanes per chain: 4 chains per task, task id = slot / 4)
+    std::vector<int> warp_T_long(long_slots / 4, 0);
+    std::vector<long long> warp_off_long(long_slots / 4, 0);
+    for (int wp = 0; wp < long_slots / 4; ++wp) {
+        int m = 0;
+        for (int l = 0; l < 4; ++l) m = std::max(m, Ts[wp * 4 + l]);
+        const int Cs = std::max(4, (m + 31) / 32 * 4);
+        warp_T_long[wp] = Cs;
+        warp_off_long[wp] = pi_elems;
+        pi_elems += (long long)Cs * K * 32;
+    }
+    for (int wp = long_slots / cpt; wp < n_warps; ++wp) {
         int m = 0;
         for (int l = 0; l < cpt; ++l) m = std::max(m, Ts[wp * cpt + l]);
         warp_T[wp] = m;
@@ -1492,9 +1528,23 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
         }
 
     // task groups: interleaved subsets of the (longest-first) warp tasks, each driven through its own stream
-    pl->n_groups = (pl->wide || pl->scan) ? 1 : (n_warps >= 1024 ? 4 : (n_warps >= 256 ? 2 : 1));
-    if (const char* e = getenv("HMCGPU_GROUPS")) pl->n_groups = std::max(1, std::min(8, atoi(e)));
-    pl->n_groups = std::min(pl->n_groups, n_warps);
+    {
+        auto n_groups_for = [&](int tasks) {
+            int g = (pl->wide || pl->scan) ? 1 : (tasks >= 1024 ? 4 : (tasks >= 256 ? 2 : 1));
+            if (const char* e = getenv("HMCGPU_GROUPS")) g = std::max(1, std::min(8, atoi(e)));
+            return std::max(1, std::min(g, tasks));
+        };
+        const int t_long = long_slots / 4, t_first = long_slots / cpt, t_rest = n_warps - t_first;
+        if (t_long > 0) {
+            const int g = n_groups_for(t_long);
+            for (int q = 0; q < g; ++q) pl->groups.push_back({q, g, (t_long - q + g - 1) / g, 8, true});
+        }
+        if (t_rest > 0) {
+            const int g = n_groups_for(t_rest);
+            for (int q = 0; q < g; ++q) pl->groups.push_back({t_first + q, g, (t_rest - q + g - 1) / g, pl->seg_lanes, false});
+        }
+        pl->n_groups = (int)pl->groups.size();
+    }
     // double-buffered draw chunks let the groups drift apart (not with the smoothing accumulators, which are shared)
     pl->n_bufs = (pl->n_groups > 1 && !(p->flags & kAccMean)) ? 2 : 1;
     // chunk of draws per buffer: bound the chunk buffers to ~2 GiB in total
@@ -1528,6 +1578,10 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     CU(ctx, up(pl->ybase, ybase.data(), n_slots * sizeof(long long)));
     CU(ctx, up(pl->warp_T, warp_T.data(), n_warps * sizeof(int)));
     CU(ctx, up(pl->warp_pi_off, warp_off.data(), n_warps * sizeof(long long)));
+    if (long_slots > 0) {
+        CU(ctx, up(pl->warp_T_long, warp_T_long.data(), warp_T_long.size() * sizeof(int)));
+        CU(ctx, up(pl->warp_pi_off_long, warp_off_long.data(), warp_off_long.size() * sizeof(long long)));
+    }
     if (pl->wide) CU(ctx, up(pl->slot_pi_off, slot_off.data(), n_slots * sizeof(long long)));
     CU(ctx, up(pl->chain_id, chain_id.data(), n_slots * sizeof(unsigned)));
     CU(ctx, up(pl->win_slot0, win_slot0.data(), nw * sizeof(int)));
@@ -1638,7 +1692,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p) {
     if (pl->seg) {
         // 256-thread blocks (8 warps stepping through the phases of a sweep together) when that still gives every SM a block
         // and a half; otherwise 128
-        pl->seg_threads = (n_warps / (kSegThreads / 32) >= ctx->sm_count * 3 / 2) ? kSegThreads : 128;
+        pl->seg_threads = ((n_warps - long_slots / cpt + long_slots / 4) / (kSegThreads / 32) >= ctx->sm_count * 3 / 2) ? kSegThreads : 128;
         if (const char* e = getenv("HMCGPU_SEG_THREADS")) pl->seg_threads = atoi(e);
         CU(ctx, pl->d_diag.alloc(2 * sizeof(unsigned long long)));
         a.diag = pl->d_diag.as<unsigned long long>();
@@ -1798,14 +1852,17 @@ static int plan_run_t(hmcgpu_plan* pl) {
                 a.out = pl->out.p;
             }
             a.sweep0 = s0; a.n_sweeps = (int)n;
-            a.task0 = g; a.task_stride = G; a.n_tasks = (pl->n_warps - g + G - 1) / G;
+            const hmcgpu_plan::Group& grp = pl->groups[g];
+            a.task0 = grp.task0; a.task_stride = grp.stride; a.n_tasks = grp.n_tasks;
+            a.warp_T = grp.long_class ? pl->warp_T_long.as<int>() : pl->warp_T.as<int>();
+            a.warp_pi_off = grp.long_class ? pl->warp_pi_off_long.as<long long>() : pl->warp_pi_off.as<long long>();
             cudaEvent_t lt0 = nullptr, lt1 = nullptr;
             if (launch_timing) { CU(ctx, timing_event(&lt0)); CU(ctx, timing_event(&lt1)); CU(ctx, cudaEventRecord(lt0, gs)); }
             if constexpr (K == 0) {
                 CU(ctx, (launch_gibbs_wide<R>(cfg, a, pl->K, pl->slot_pi_off.as<long long>(), gs)));
             } else if constexpr (K <= 4) {
                 if (pl->scan) CU(ctx, (launch_gibbs_scan<R, K>(cfg, a, gs)));
-                else if (pl->seg) CU(ctx, (launch_gibbs_seg<R, K>(cfg, a, pl->seg_lanes, pl->seg_threads, gs)));
+                else if (pl->seg) CU(ctx, (launch_gibbs_seg<R, K>(cfg, a, grp.lanes, pl->seg_threads, gs)));
                 else CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
             } else {
                 CU(ctx, (launch_gibbs<R, K>(cfg, a, gs)));
@@ -1852,6 +1909,7 @@ static int plan_run_t(hmcgpu_plan* pl) {
         CU(ctx, cudaMemcpy(pl->seg_fallbacks, pl->d_diag.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         if (getenv("HMCGPU_VERBOSE")) {
             const double cs = (double)pl->n_windows * pl->n_chains * (double)S;
+            if (pl->n_long) fprintf(stderr, "[hmcgpu] segment kernel: the %d longest of %d windows with 8 lanes per chain\n", pl->n_long, pl->n_windows);
             fprintf(stderr, "[hmcgpu] segment kernel (%d lanes per chain, warm-up %d): %llu of %.0f chain-sweeps used the exact entering vectors; "
                             "%.2f speculative groups of 4 steps per chain-sweep\n",
                     pl->seg_lanes, pl->args.seg_warm, pl->seg_fallbacks[0], cs, (double)pl->seg_fallbacks[1] / cs);
@@ -1967,7 +2025,7 @@ static int plan_fetch_impl(hmcgpu_plan* pl, hmcgpu_result* r) {
     r->n_sweep_launches = pl->n_sweep_launches; r->h2d_bytes = pl->h2d; r->d2h_bytes = d2h; r->state_steps = pl->state_steps;
     r->sweep_launch_ms_sum = pl->launch_ms_sum;
     r->sweep_kernel = pl->wide ? HMCGPU_KERNEL_LANE : pl->scan ? HMCGPU_KERNEL_SCAN : pl->seg ? HMCGPU_KERNEL_SEG : HMCGPU_KERNEL_THREAD;
-    r->n_tasks = pl->n_warps;
+    r->n_tasks = pl->n_warps - pl->long_slots / (pl->seg ? 32 / pl->seg_lanes : 32) + pl->long_slots / 4;
     return bad;
 }
 

@@ -237,6 +237,40 @@ def test_gibbs_first_sweeps_follow_the_oracle_chain(H, ctx, oracle):
             np.testing.assert_allclose(o.loglik[0][sl], r.loglik, rtol=1e-9)
 
 
+def test_mixed_segment_counts_follow_the_oracle_chain(H, ctx, oracle, monkeypatch):
+    """Mid-width plans with thread slots to spare give their LONGEST windows 8 lanes per chain and the rest 4 (two slot ranges with
+    their own warp-task tables, one stream group per class).  Forced here on a small ragged batch (HMCGPU_SEG_LONG = number of
+    long windows): every chain of both classes must follow the oracle's chain, and the split must not move any window's results
+    to another window (slot ranges, padding between the classes, summaries per window)."""
+    monkeypatch.setenv("HMCGPU_SCAN_MAX_CHAINS", "0")
+    monkeypatch.delenv("HMCGPU_SEG_LANES", raising=False)
+    monkeypatch.setenv("HMCGPU_SEG_LONG", "5")
+    y, _ = synth_hmm(420, seed=21, **K3_TRUTH)
+    ends = [400, 160, 333, 250, 129, 380, 90, 301, 64, 222, 199, 147]          # 12 windows; the 5 longest (T >= 250) form the long class
+    starts = [1, 3, 2, 1, 1, 9, 5, 1, 2, 4, 1, 1]
+    nc = 7                                                                       # 35 long chains (padding inside the class), 49 others
+    o = _run(H, ctx, y, starts, ends, K=3, n_chains=nc, burnin=1, nrun=3, seed=13, horizons=(1, 2), precision=64,
+             flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_LOGLIK | H.FLAG_SUMMARY)
+    assert o.events == 0 and o.sweep_kernel == 4
+    for w, (s, e) in enumerate(zip(starts, ends)):
+        for c in (0, nc - 1):
+            r = oracle.gibbs(y[s - 1:e], 3, 1, 3, seed=13, chain=w * nc + c, horizons=(1, 2), y_future=[y[e], y[e + 1]],
+                             flags=oracle.FLAG_REF_Q1 | oracle.FLAG_PIF_FORM)
+            sl = slice(c * 3, (c + 1) * 3)
+            np.testing.assert_allclose(o.mu[w][:, sl].T, r.mu, rtol=1e-7, atol=1e-9)
+            np.testing.assert_allclose(o.sigma2[w][:, sl].T, r.sigma2, rtol=1e-7)
+            np.testing.assert_allclose(np.transpose(o.A[w][:, :, sl], (2, 1, 0)), r.A, rtol=1e-7, atol=1e-12)
+            np.testing.assert_allclose(o.loglik[w][sl], r.loglik, rtol=1e-8)
+    # the same batch with one segment count for every window: same chains (fp64: to rounding), same per-window summaries
+    monkeypatch.setenv("HMCGPU_SEG_MIXED", "0")
+    monkeypatch.delenv("HMCGPU_SEG_LONG")
+    u = _run(H, ctx, y, starts, ends, K=3, n_chains=nc, burnin=1, nrun=3, seed=13, horizons=(1, 2), precision=64,
+             flags=H.FLAG_REF_Q1 | H.FLAG_DRAWS | H.FLAG_LOGLIK | H.FLAG_SUMMARY)
+    np.testing.assert_allclose(o.summary_mean, u.summary_mean, rtol=1e-7, atol=1e-9)
+    for w in range(len(ends)):
+        np.testing.assert_allclose(o.mu[w], u.mu[w], rtol=1e-7, atol=1e-9)
+
+
 @pytest.mark.parametrize("K,T", [(2, 37), (3, 2), (3, 33), (3, 1500), (4, 334)])
 def test_chunk_shapes_follow_the_oracle_chain(H, ctx, oracle, K, T):
     """Window lengths that stress the time-parallel kernel's chunking (idle lanes, one step per lane, chunks longer than
