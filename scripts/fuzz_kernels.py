@@ -1,6 +1,7 @@
 """Differential fuzzing of the sweep kernels on the GPU box: random shapes (K, window lengths, ragged batches, chains,
 signal masks, kappa, pi_row_back, user X0) are estimated in fp64 with two kernels that must produce the same chains (same
-Philox streams): K = 2..4 time-parallel warp-per-chain vs thread-per-chain; K = 5..8 thread-per-chain vs lane-per-state.
+Philox streams): K = 2..4 time-parallel warp-per-chain vs thread-per-chain; K = 5..8 thread-per-chain vs lane-per-state; K = 2..4 plain sweeps also on the segment kernel
+(2 / 4 / 8 lanes per chain, or mixed 8 + 4) vs thread-per-chain.
 python scripts/fuzz_kernels.py [n] [seed]"""
 import os, sys
 import numpy as np
@@ -36,19 +37,40 @@ for case in range(n_cases):
     if rng.random() < 0.3:
         kw.update(X0=[rng.integers(1, K + 1, int(e - s + 1)) for s, e in zip(ws, we)])
     outs = {}
-    for mode in ("first", "second"):
-        if K <= 4:
-            os.environ["HMCGPU_SCAN_MAX_CHAINS"] = "1000000" if mode == "first" else "0"
-        else:
-            os.environ["HMCGPU_LANE_KERNEL"] = "0" if mode == "first" else "1"
-        outs[mode] = H.estimate(ctx, H.ProblemSpec(y, ws, we, **kw))
-    a, b = outs["first"], outs["second"]
-    ok = a.events == b.events
-    for k in ("mu", "sigma2", "A", "pi_end", "forecasts", "loglik"):
-        for w in range(nw):
-            x, z = np.asarray(getattr(a, k)[w]), np.asarray(getattr(b, k)[w])
-            fin = np.isfinite(z)
-            ok = ok and np.array_equal(np.isfinite(x), fin) and np.allclose(x[fin], z[fin], rtol=1e-6, atol=1e-9)
+    for v in ("HMCGPU_SEG_LANES", "HMCGPU_SEG_LONG", "HMCGPU_SCAN_MAX_CHAINS", "HMCGPU_LANE_KERNEL"):
+        os.environ.pop(v, None)
+    run = lambda: H.estimate(ctx, H.ProblemSpec(y, ws, we, **kw))
+    if K <= 4:
+        os.environ["HMCGPU_SCAN_MAX_CHAINS"] = "1000000"
+        outs["scan"] = run()
+        os.environ["HMCGPU_SCAN_MAX_CHAINS"] = "0"; os.environ["HMCGPU_SEG_LANES"] = "0"
+        outs["thread"] = run()
+        pairs = [(outs["scan"], outs["thread"])]
+        if "is_signal" not in kw:              # plain sweep: the segment kernel with 2 / 4 / 8 lanes per chain, or mixed 8 + 4
+            choice = str(rng.choice(["2", "4", "8", "mixed"]))
+            if choice == "mixed":
+                kw["n_chains"] = int(rng.integers(8, 36))          # (a long class needs at least 32 chains)
+                ref = run()                                          # thread-per-chain, the same chains
+                os.environ.pop("HMCGPU_SEG_LANES")
+                os.environ["HMCGPU_SEG_LONG"] = str(int(rng.integers(1, nw + 1)))
+                pairs.append((run(), ref))
+            else:
+                os.environ["HMCGPU_SEG_LANES"] = choice
+                pairs.append((run(), outs["thread"]))
+    else:
+        os.environ["HMCGPU_LANE_KERNEL"] = "0"
+        outs["thread"] = run()
+        os.environ["HMCGPU_LANE_KERNEL"] = "1"
+        outs["lane"] = run()
+        pairs = [(outs["thread"], outs["lane"])]
+    ok = True
+    for a, b in pairs:
+        ok = ok and a.events == b.events
+        for k in ("mu", "sigma2", "A", "pi_end", "forecasts", "loglik"):
+            for w in range(nw):
+                x, z = np.asarray(getattr(a, k)[w]), np.asarray(getattr(b, k)[w])
+                fin = np.isfinite(z)
+                ok = ok and x.shape == z.shape and np.array_equal(np.isfinite(x), fin) and np.allclose(x[fin], z[fin], rtol=1e-6, atol=1e-9)
     if not ok:
         bad += 1
         print("MISMATCH case", case, dict(K=K, ws=ws.tolist(), we=we.tolist(), **{k: (v if np.isscalar(v) else "...") for k, v in kw.items()}), flush=True)
