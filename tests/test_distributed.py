@@ -103,6 +103,14 @@ def test_single_process_gather_is_a_permutation():
     local = np.arange(8.0).reshape(4, 2)
     out = H.gather_window_summaries(local, shard, 4)
     np.testing.assert_array_equal(out[shard], local)
+    # one process holding every window in order: nothing is moved (no 45 MB copy per call on the wide batches)
+    ident = H.gather_window_summaries(local, np.arange(4), 4)
+    np.testing.assert_array_equal(ident, local)
+    assert np.shares_memory(ident, local)
+    # ... but a shard that is only a prefix of the windows still yields the full table
+    part = H.gather_window_summaries(local[:2], np.arange(2), 4)
+    assert part.shape == (4, 2)
+    np.testing.assert_array_equal(part[:2], local[:2])
 
 
 def test_bench_reference_arm_under_torchrun_prints_one_line_from_rank0():
