@@ -125,6 +125,17 @@ __device__ __forceinline__ void ld_quad_shared(const double* p, double& a, doubl
     const double2 v = *reinterpret_cast<const double2*>(p), w = *(reinterpret_cast<const double2*>(p) + 1);
     a = v.x; b = v.y; c = w.x; d = w.y;
 }
+// the same through a 32-bit shared-window address (ld.shared.v4 / 2 x ld.shared.v2.f64): no generic-to-shared base in the loop
+#ifndef HMC_RING_LDS32
+#define HMC_RING_LDS32 1
+#endif
+__device__ __forceinline__ void lds_quad(unsigned saddr, float& a, float& b, float& c, float& d) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(saddr));
+}
+__device__ __forceinline__ void lds_quad(unsigned saddr, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(saddr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(d) : "r"(saddr + 16u));
+}
 // a 16-byte-aligned struct read from a 32-bit shared-window address (ld.shared.v4 per 16 bytes)
 template <typename T> __device__ __forceinline__ void lds_struct(unsigned saddr, T& out) {
     static_assert(sizeof(T) % 16 == 0 && alignof(T) >= 16, "16-byte granules");
@@ -141,7 +152,7 @@ constexpr int kGibbsThreads = 128;
 constexpr int kGibbsMinBlocks = HMC_MINBLOCKS;   // 4 blocks x 128 threads per SM -> 128 registers, 16 resident warps (5 blocks / 96 registers was the best before the tiled spill layout; measured again after it: 4 is +5 %)
 // K = 5..8 keep K x K matrices per thread: 2 blocks per SM (shared-memory tables and rings allow no more), 255 registers
 #ifndef HMC_MINBLOCKS_F64
-#define HMC_MINBLOCKS_F64 3
+#define HMC_MINBLOCKS_F64 4
 #endif
 #ifndef HMC_MINBLOCKS_K56
 #define HMC_MINBLOCKS_K56 3
@@ -149,12 +160,17 @@ constexpr int kGibbsMinBlocks = HMC_MINBLOCKS;   // 4 blocks x 128 threads per S
 #ifndef HMC_MINBLOCKS_SIG
 #define HMC_MINBLOCKS_SIG 4
 #endif
-// fp64 state needs twice the registers: 3 blocks per SM (168 registers) instead of spilling at 96
+// fp64 state needs twice the registers: 4 blocks per SM at 128 registers with a depth-3 ring (7.27e10 on C2) or 3 at 168 with depth 4
+// (7.06e10); 2 blocks at 255 registers 5.6e10, 96 registers spill (scripts/r2_call_h.sh)
 template <typename R, int K, bool SIG> constexpr int gibbs_min_blocks() {
     return K > 6 ? 2 : (K > 4 ? HMC_MINBLOCKS_K56 : (sizeof(R) == 8 ? HMC_MINBLOCKS_F64 : (SIG ? HMC_MINBLOCKS_SIG : kGibbsMinBlocks)));
 }
 // cp.async ring depth: the ring of a warp is stages x 4 rows x K x 32 lanes
-template <typename R, int K> __host__ __device__ constexpr int gibbs_ring_stages() { return K <= 4 ? kRing : (sizeof(R) == 4 ? 3 : 2); }
+// (fp64, K <= 4: depth 3 — with depth 4 the shared memory of a block allows only 3 blocks per SM; 4 blocks at depth 3 measured +3 %)
+#ifndef HMC_RING_STAGES_F64
+#define HMC_RING_STAGES_F64 3
+#endif
+template <typename R, int K> __host__ __device__ constexpr int gibbs_ring_stages() { return K <= 4 ? (sizeof(R) == 8 ? HMC_RING_STAGES_F64 : kRing) : (sizeof(R) == 4 ? 3 : 2); }
 
 struct GibbsArgs {
     int n_slots;                 // chains incl. padding, multiple of 32
@@ -772,6 +788,7 @@ struct GibbsWarp {
             const char* nsrc = reinterpret_cast<const char*>(ch.pi0 - lane * 4 + (long long)(Tw + pad - 4 - i) * K * 32) + (kTma ? 0 : lane * 16);   // tile of group 0 (rows of steps i..i+3; i is a multiple of 4 here)
             const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (kTma ? 0u : (unsigned)lane * 16u);
             constexpr unsigned kGroupBytes = (unsigned)(kGroupElems * sizeof(R));
+            const unsigned ring_rd = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)(lane * 4 * sizeof(R));   // this lane's rows of state 0, stage 0
             unsigned nstage = 0;                                         // byte offset of the stage the next fetch fills
             int nleft = n_groups;                                        // groups not fetched yet
             // TMA: one mbarrier per ring stage of this warp, behind the rings; (re)initialised per pass.  The forward pass wrote the
@@ -859,11 +876,15 @@ struct GibbsWarp {
                     cp_async_wait<kRing - 1>();                          // group g has landed (for this lane's chunks)
                     __syncwarp();                                        // ... and for every other lane's
                 }
-                const R* st = reinterpret_cast<const R*>(reinterpret_cast<const char*>(ring) + (kG == 2 ? ((g & 1) ? rstage - kGroupBytes : rstage + kGroupBytes) : rstage)) + lane * 4;
+                const unsigned roff = (kG == 2 ? ((g & 1) ? rstage - kGroupBytes : rstage + kGroupBytes) : rstage);
+                const R* st = reinterpret_cast<const R*>(reinterpret_cast<const char*>(ring) + roff) + lane * 4;
                 rstage = (rstage + kGroupBytes == kRing * kGroupBytes) ? 0u : rstage + kGroupBytes;
                 R c0[K], c1[K], c2[K], c3[K], y0, y1, y2, y3, s0 = R(1), s1 = R(1), s2 = R(1), s3 = R(1);
 #pragma unroll
-                for (int s = 0; s < K; ++s) ld_quad_shared(st + s * 128, c3[s], c2[s], c1[s], c0[s]);   // position 3 = highest row = first step
+                for (int s = 0; s < K; ++s) {                            // position 3 = highest row = first step
+                    if constexpr (HMC_RING_LDS32) lds_quad(ring_rd + roff + (unsigned)(s * 128 * sizeof(R)), c3[s], c2[s], c1[s], c0[s]);
+                    else ld_quad_shared(st + s * 128, c3[s], c2[s], c1[s], c0[s]);
+                }
                 if constexpr (STREAM) {                                  // fetched one group ahead (see forward_pass)
                     y0 = ynx[0]; y1 = ynx[1]; y2 = ynx[2]; y3 = ynx[3];
                     s0 = snx[0]; s1 = snx[1]; s2 = snx[2]; s3 = snx[3];
