@@ -278,6 +278,7 @@ struct SegWarp {
         const int n_groups = C >> 2;
         const char* nsrc = reinterpret_cast<const char*>(ch.pi0 - lane * 4 + (long long)(C - 4) * K * 32) + lane * 16;   // tile of group 0
         const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)lane * 16u;
+        const unsigned ring_rd = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)(lane * 4 * sizeof(R));   // this lane's rows of state 0, stage 0
         unsigned nstage = 0, rstage = 0;
         int nleft = n_groups;
         auto issue = [&]() {
@@ -314,10 +315,11 @@ struct SegWarp {
             issue();
             cp_async_wait<kRing - 1>();
             __syncwarp();
-            const R* st = reinterpret_cast<const R*>(reinterpret_cast<const char*>(ring) + rstage) + lane * 4;
+            // (read through a 32-bit shared address computed once per pass, like the thread-per-chain kernel's ring loop)
+            const unsigned rd = ring_rd + rstage;
             rstage = (rstage + kGroupBytes == kRing * kGroupBytes) ? 0u : rstage + kGroupBytes;
 #pragma unroll
-            for (int k = 0; k < K; ++k) ld_quad_shared(st + k * 128, gr.c[3][k], gr.c[2][k], gr.c[1][k], gr.c[0][k]);
+            for (int k = 0; k < K; ++k) lds_quad(rd + (unsigned)(k * 128 * sizeof(R)), gr.c[3][k], gr.c[2][k], gr.c[1][k], gr.c[0][k]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) gr.y[u] = (!guard_y || 4 * g + u < n) ? ld_ro(yp - u * ys) : R(0);
             yp -= 4 * ys;
