@@ -641,6 +641,12 @@ static cudaError_t staged_upload(hmcgpu_ctx* ctx, void* dev, const void* host, s
         return std::max(1, std::min(64, e ? atoi(e) : std::min(8, hw > 1 ? hw / 2 : 1)));
     }();
     if (chunk == 0 || bytes < 2 * chunk) return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st);
+    {   // a caller that already hands over page-locked memory needs no staging: the DMA engine reads it directly
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost)
+            return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st);
+        cudaGetLastError();
+    }
     if (ctx->stage_bytes != chunk) {
         for (int i = 0; i < 2; ++i) {
             if (ctx->stage[i]) { cudaFreeHost(ctx->stage[i]); ctx->stage[i] = nullptr; }
@@ -677,7 +683,17 @@ static cudaError_t staged_upload(hmcgpu_ctx* ctx, void* dev, const void* host, s
         }
     };
     std::vector<std::thread> pool;
-    for (int t = 1; t < n_thr; ++t) pool.emplace_back(worker, t);
+    try {
+        for (int t = 1; t < n_thr; ++t) pool.emplace_back(worker, t);
+    } catch (...) {                                                              // no threads to be had: stop the ones that started, plain copy
+        {
+            std::lock_guard<std::mutex> lk(sh.mu);
+            sh.quit = true;
+        }
+        sh.cv.notify_all();
+        for (auto& t : pool) t.join();
+        return cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st);
+    }
     cudaError_t rc = cudaSuccess;
     for (size_t c = 0; c < n_chunks && rc == cudaSuccess; ++c) {
         if (c >= 2) rc = cudaEventSynchronize(ctx->stage_free[c & 1]);          // the DMA out of this buffer (chunk c-2) has finished
