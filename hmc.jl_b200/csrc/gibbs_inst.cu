@@ -50,7 +50,8 @@ template <typename R, int K> cudaError_t launch_gibbs(const GibbsLaunch& cfg, co
     };
     const bool smooth = cfg.flags & (8u | 64u);   // smoothed or filtered means: the A^h mu vectors of the in-sample forecasts live in shared memory
     const bool wr = K > 4 || wide_rows<K>(cfg);
-    const size_t smem = wr ? gibbs_smem_bytes<R, K, true>(smooth, cfg.n_h) : gibbs_smem_bytes<R, K, false>(smooth, cfg.n_h);
+    const size_t ysm = a.y_sm_elems > 0 ? ((size_t)a.y_sm_elems * sizeof(R) + 15) / 16 * 16 : 0;   // the block's copy of the one series
+    const size_t smem = (wr ? gibbs_smem_bytes<R, K, true>(smooth, cfg.n_h) : gibbs_smem_bytes<R, K, false>(smooth, cfg.n_h)) + ysm;
     return with_rows<R, K>(cfg, [&](auto kern) { return go(kern, smem); });
 }
 

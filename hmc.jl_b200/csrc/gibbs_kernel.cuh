@@ -100,6 +100,35 @@ __device__ __forceinline__ unsigned char* smem_base() {
 template <typename T> __device__ __forceinline__ T ld_stream(const T* p) { return __ldcg(p); }     // pif rows: L2 only
 template <typename T> __device__ __forceinline__ T ld_ro(const T* p) { return __ldg(p); }          // y: read-only, L1
 template <typename T> __device__ __forceinline__ void st_stream(T* p, T v) { __stcg(p, v); }
+// Where a pass reads its observations from: global memory (read-only path, L1) or — the windows of ONE short series, the headline
+// case — a copy of the series in shared memory, addressed through the 32-bit shared window (no 64-bit pointer arithmetic, no
+// memory descriptor to move into a uniform register in front of every load).  Pointer-like: + / - in elements, ld() reads.
+template <typename T, bool SM> struct YRef;
+template <typename T> struct YRef<T, false> {
+    const T* p;
+    __device__ __forceinline__ YRef operator+(long long d) const { return YRef{p + d}; }
+    __device__ __forceinline__ YRef operator-(long long d) const { return YRef{p - d}; }
+    __device__ __forceinline__ YRef& operator+=(long long d) { p += d; return *this; }
+    __device__ __forceinline__ YRef& operator-=(long long d) { p -= d; return *this; }
+    __device__ __forceinline__ T ld() const { return __ldg(p); }
+    __device__ __forceinline__ const void* gptr() const { return p; }
+};
+template <typename T> struct YRef<T, true> {
+    unsigned a;                                                       // byte address in the shared window
+    __device__ __forceinline__ YRef operator+(long long d) const { return YRef{a + (unsigned)((int)d * (int)sizeof(T))}; }
+    __device__ __forceinline__ YRef operator-(long long d) const { return YRef{a - (unsigned)((int)d * (int)sizeof(T))}; }
+    __device__ __forceinline__ YRef& operator+=(long long d) { a += (unsigned)((int)d * (int)sizeof(T)); return *this; }
+    __device__ __forceinline__ YRef& operator-=(long long d) { a -= (unsigned)((int)d * (int)sizeof(T)); return *this; }
+    __device__ __forceinline__ T ld() const {
+        T v;
+        if constexpr (sizeof(T) == 4) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+        else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+        return v;
+    }
+    __device__ __forceinline__ const void* gptr() const { return nullptr; }
+};
+// observations of one series kept in shared memory by the thread-per-chain kernel (GibbsArgs::y_sm_elems): at most this many bytes
+constexpr int kYSmemMaxBytes = 8 * 1024;    // (1024 fp64 observations; tables + rings + forecasts are ~61 KB per block at 3 blocks per SM)
 // Batches of distinct series (yld > 1) stream y from HBM once per pass: the rows are pulled into L1 kYAhead steps ahead
 // of their use so the DRAM latency does not sit in front of every group of 4 steps.  (Windows of ONE series keep y in L1.)
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -223,6 +252,7 @@ struct GibbsArgs {
     const int* totM;             // [n_slots] number of signals in the window
     double kappa;
     int pi_back;                 // the pi_end field of a draw is the smoothed marginal pib[N - pi_back, :] (:893); 0 = last row
+    int y_sm_elems;              // > 0: ONE series of this many observations (yld = 1), copied into shared memory by every block of the thread-per-chain kernel
     int all_signal;              // every time step of every series is a signal (the 'make everything a signal' runs, code/run_hmm.jl:160-176)
     // ---- segment kernel (gibbs_seg_kernel.cuh)
     int seg_warm;                // warm-up time steps in front of a segment
@@ -283,7 +313,12 @@ struct GibbsWarp {
     using Entry = GibbsEntry<R, K, WIDE>;
 
     // per-sweep constants of one chain
-    struct Chain : std::conditional<SIG, SigChain<R>, NoSig>::type {
+    // (fp64 only: row 0 of the lane's frame in the shared-memory copy of the series, byte address.  The fp32 struct must NOT grow: it
+    //  is passed BY VALUE to the out-of-line passes, and four more bytes push it over the size ptxas passes in registers — the
+    //  kernel's frame went from 424 to 2208 bytes and C2 x 256 lost 3 %)
+    struct NoYsm {};
+    struct WithYsm { unsigned ysm; };
+    struct Chain : std::conditional<SIG, SigChain<R>, NoSig>::type, std::conditional<sizeof(R) == 8, WithYsm, NoYsm>::type {
         R A[K][K];
         R c;                      // shift of the sufficient statistics
         int rank[K];              // position of each chain label in increasing-mu order
@@ -444,8 +479,10 @@ struct GibbsWarp {
     struct FwdOut { Vec pf; R ll; int events; };
     // FACC (HMCGPU_FLAG_FILTERED_MEAN, a saved draw): every filtered row is also added to the per-date sums (sorted labels) and
     // its forecasts pif[t,:]' A^h mu to the in-sample forecast sums — the table the reference published (forecats_insample.csv).
-    template <bool RAGGED, bool CHECKED, bool STREAM = false, bool FACC = false>
+    // (YSM: the observations come from the shared-memory copy of the series — hot single-series variants only)
+    template <bool RAGGED, bool CHECKED, bool STREAM = false, bool FACC = false, bool YSM = false>
     static __device__ HMC_FWD_ATTR FwdOut forward_pass(const Chain ch, const Emission<R, K> em, const Vec rho_in) {
+        static_assert(!YSM || (!STREAM && !CHECKED), "shared-memory observations: unit stride");
         FwdOut o;
         R (&pf)[K] = o.pf.v;
         R& ll = o.ll;
@@ -456,7 +493,8 @@ struct GibbsWarp {
 #pragma unroll
         for (int s = 0; s < K; ++s) pf[s] = rho[s];                  // t = 1 uses ρ (:390)
         ll = R(0);
-        const R* yp = ch.y0;
+        YRef<R, YSM> yp;
+        if constexpr (YSM) yp.a = ch.ysm; else yp.p = ch.y0;
         const R* sp = nullptr;                                       // z-scale of the emission per row (SIG)
         if constexpr (SIG) sp = ch.s0;
         R* pip = ch.pi0;
@@ -487,7 +525,7 @@ struct GibbsWarp {
         // (guard: a std::integral_constant — the per-lane window test is compiled out for the rows where every lane is inside its window)
         auto step = [&](auto guard, int j, int u, int yo, R ypre, bool preloaded, R swpre = R(1)) {
             if (!decltype(guard)::value || j >= ch.off) {
-                const R yt = preloaded ? ypre : ld_ro(yp + yo * yld);   // STREAM: loaded one iteration ahead by the caller
+                const R yt = preloaded ? ypre : (yp + yo * yld).ld();   // STREAM: loaded one iteration ahead by the caller
                 R sw = R(1);                                         // signals: sd x (1+kappa) (:382) <=> z scaled by 1/(1+kappa)
                 if constexpr (SIG) sw = preloaded ? swpre : ld_ro(sp + yo * ch.sld);   // STREAM: fetched with the observation
                 if constexpr (sizeof(R) == 4) {
@@ -591,11 +629,11 @@ struct GibbsWarp {
         // STREAM: the observations of the next 4 steps are fetched into registers one iteration ahead (from lines that
         // were pulled into L1 kYAhead steps ahead), so neither the DRAM nor the L1 latency sits in the dependent chain
         R yn[4] = {R(0), R(0), R(0), R(0)}, sn[4] = {R(1), R(1), R(1), R(1)};
-        auto load4 = [&](int jj, const R* p, const R* q) {           // observations (and, SIG, their z-scales: one more streamed array per series)
+        auto load4 = [&](int jj, const YRef<R, YSM> p, const R* q) {  // observations (and, SIG, their z-scales: one more streamed array per series)
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const bool in = jj + u < ch.Tw && (!ragged || jj + u >= ch.off);
-                yn[u] = in ? ld_ro(p + u * yld) : R(0);
+                yn[u] = in ? (p + u * yld).ld() : R(0);
                 if constexpr (SIG) sn[u] = in ? ld_ro(q + u * ch.sld) : R(1);
             }
         };
@@ -607,7 +645,7 @@ struct GibbsWarp {
                     if (j + kYAhead + 3 < ch.Tw && (!ragged || j + kYAhead >= ch.off)) {   // rows of this lane's own window only
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            prefetch_l1(yp + (kYAhead + u) * yld);
+                            prefetch_l1((yp + (kYAhead + u) * yld).gptr());
                             if constexpr (SIG) { if (ch.sld != 1) prefetch_l1(sp + (kYAhead + u) * ch.sld); }   // (a mask shared by every series stays in L1)
                         }
                     }
@@ -634,7 +672,7 @@ struct GibbsWarp {
     struct NoAcc {};
     struct TransAcc { int n[K * K]; };                               // flushed transition counts (K > 4)
     struct BackOut : std::conditional<Pack::kFlush, TransAcc, NoAcc>::type { Back b; int xN; bool bad; bool lost; };   // lost: a bulk copy never completed (HMC_TMA)
-    template <bool RAGGED, bool GATED, bool STREAM = false, bool ALLSIG = false>
+    template <bool RAGGED, bool GATED, bool STREAM = false, bool ALLSIG = false, bool YSM = false>
     static __device__ HMC_BACK_ATTR BackOut backward_pass(const Chain ch, const Vec pf_in, const RngKey key, const uint32_t sweep,
                                                          const unsigned flags, const bool save) {
         BackOut o;
@@ -674,7 +712,9 @@ struct GibbsWarp {
         b.inc = 0; b.gate = R(1);
 #pragma unroll
         for (int s = 0; s < K; ++s) { b.Acol[s] = R(0); b.pb[s] = R(0); }
-        const R* yp = ch.y0 + (long long)(Tw - 1) * ys;
+        static_assert(!YSM || (!STREAM && !GATED), "shared-memory observations: unit stride");
+        YRef<R, YSM> yp;
+        if constexpr (YSM) yp.a = ch.ysm + (unsigned)((Tw - 1) * (int)sizeof(R)); else yp.p = ch.y0 + (long long)(Tw - 1) * ys;
         const R* sp = nullptr;
         long long ss = 0;                                             // stride of the z-scale rows (SIG)
         if constexpr (SIG) {
@@ -723,7 +763,7 @@ struct GibbsWarp {
             }
             R swN = R(1);
             if constexpr (SIG) swN = ld_ro(sp);
-            commit<ALLSIG>(b, ch, lt, pf, ld_ro(yp), swN, true);
+            commit<ALLSIG>(b, ch, lt, pf, yp.ld(), swN, true);
         }
         int i = 1;
         // one step; u = position inside the current group of 4 (pointers move once per group).  The filtered rows and
@@ -740,7 +780,7 @@ struct GibbsWarp {
 #pragma unroll
                 for (int s = 0; s < K; ++s) pt[s] = ld_stream(rp + s * 128);
             }
-            yt = (!ragged || i + u < T) ? ld_ro(yp - (u + 1) * ys) : R(0);
+            yt = (!ragged || i + u < T) ? (yp - (u + 1) * ys).ld() : R(0);
             st = load_sw(u);
         };
 #define HMC_BACK_NB(NB, u, word, PT, YT, ST)                                                                           \
@@ -848,10 +888,10 @@ struct GibbsWarp {
             for (int g = 0; g < (kTma ? kCopies : kRing) - 1; ++g) issue();
             unsigned rstage = 0;                                         // byte offset of the stage read in this iteration
             R ynx[4] = {R(0), R(0), R(0), R(0)}, snx[4] = {R(1), R(1), R(1), R(1)};
-            auto loady4 = [&](int ii, const R* p, const R* q) {          // observations (SIG: and z-scales) of steps ii..ii+3 (rows below p / q)
+            auto loady4 = [&](int ii, const YRef<R, YSM> p, const R* q) {   // observations (SIG: and z-scales) of steps ii..ii+3 (rows below p / q)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    ynx[u] = (!ragged || ii + u < T) ? ld_ro(p - (u + 1) * ys) : R(0);
+                    ynx[u] = (!ragged || ii + u < T) ? (p - (u + 1) * ys).ld() : R(0);
                     if constexpr (SIG) snx[u] = (!ragged || ii + u < T) ? ld_ro(q - (u + 1) * ss) : R(1);
                 }
             };
@@ -861,7 +901,7 @@ struct GibbsWarp {
                 if (STREAM && i + kYAhead + 3 < T) {                       // rows of steps i+kYAhead .. i+kYAhead+3 (this lane's window)
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        prefetch_l1(yp - (kYAhead + u + 1) * ys);
+                        prefetch_l1((yp - (kYAhead + u + 1) * ys).gptr());
                         if constexpr (SIG) { if (ss != 1) prefetch_l1(sp - (kYAhead + u + 1) * ss); }
                     }
                 }
@@ -890,10 +930,10 @@ struct GibbsWarp {
                     s0 = snx[0]; s1 = snx[1]; s2 = snx[2]; s3 = snx[3];
                     if (g + 1 < n_groups) loady4(i + 4, yp - 4 * ys, sp - 4 * ss);
                 } else {
-                    y0 = (!ragged || i + 0 < T) ? ld_ro(yp - 1 * ys) : R(0);
-                    y1 = (!ragged || i + 1 < T) ? ld_ro(yp - 2 * ys) : R(0);
-                    y2 = (!ragged || i + 2 < T) ? ld_ro(yp - 3 * ys) : R(0);
-                    y3 = (!ragged || i + 3 < T) ? ld_ro(yp - 4 * ys) : R(0);
+                    y0 = (!ragged || i + 0 < T) ? (yp - 1 * ys).ld() : R(0);
+                    y1 = (!ragged || i + 1 < T) ? (yp - 2 * ys).ld() : R(0);
+                    y2 = (!ragged || i + 2 < T) ? (yp - 3 * ys).ld() : R(0);
+                    y3 = (!ragged || i + 3 < T) ? (yp - 4 * ys).ld() : R(0);
                 }
                 if constexpr (!STREAM) { s0 = load_sw(0); s1 = load_sw(1); s2 = load_sw(2); s3 = load_sw(3); }
                 w = rng_block_states(key, sweep, (uint32_t)(i >> 2));
@@ -963,6 +1003,11 @@ struct GibbsWarp {
             for (int j = 0; j < a.n_h; ++j) yf[j * kGibbsThreads] = reinterpret_cast<const R*>(a.yfut)[(size_t)a.h_slot[j] * ns + slot];
         }
         ch.y0 = reinterpret_cast<const R*>(a.y) + a.ybase[slot] - (long long)ch.off * ch.yld;
+        // (the copy of the series sits behind everything else in the block's shared memory; rows in front of a ragged lane's window
+        //  are never read, so the address may point in front of the copy, like y0)
+        if constexpr (sizeof(R) == 8)
+            ch.ysm = (unsigned)__cvta_generic_to_shared(smem_base()) + (unsigned)gibbs_smem_bytes<R, K, WIDE>(accum, a.n_h)
+                     + (unsigned)(((int)a.ybase[slot] - ch.off) * (int)sizeof(R));
         ch.c = reinterpret_cast<const R*>(a.cshift)[slot];
         ch.tab_s = (unsigned)__cvta_generic_to_shared(smem_base()) + (unsigned)(threadIdx.x * sizeof(Entry));
         ch.ring_off = (unsigned)(sizeof(Entry) * K * kGibbsThreads + sizeof(R) * (threadIdx.x >> 5) * (kRing * 4 * K * 32));
@@ -973,7 +1018,12 @@ struct GibbsWarp {
             ch.opi = nullptr; ch.ocs = 0;
         }
         const int T = ch.T;
-        const bool stream_y = a.yld != 1;     // distinct series per chain: y is streamed from HBM (prefetching passes)
+        // distinct series per chain: y is streamed from HBM (prefetching passes).  One series: the hot passes read it from the block's
+        // shared-memory copy (y_sm_elems > 0); a single series too long for that also takes the streaming passes (stride 1)
+        // (fp64 only: measured on C2 x 256, same box — fp64 7.19 -> 7.60e10 with the copy, fp32 2.19 -> 2.13e11: there the extra LDS in
+        //  the dependent chain costs more than the 6 instructions per 4 steps it saves, so fp32 keeps reading y through L1)
+        constexpr bool kYsm = sizeof(R) == 8;
+        const bool stream_y = a.yld != 1 || (kYsm && a.y_sm_elems <= 0);
         // padding lanes (T = 0) only exist in the last warp, which therefore counts as ragged
         ch.rag_rows = (int)__reduce_max_sync(0xffffffffu, (unsigned)ch.off);
         const R totS = reinterpret_cast<const R*>(a.totS)[slot], totQ = reinterpret_cast<const R*>(a.totQ)[slot];
@@ -1067,7 +1117,7 @@ struct GibbsWarp {
                 }
                 if (!facc_done)
                     fo = stream_y ? (ch.rag_rows > 0 ? forward_pass<true, false, true>(ch, em, rv) : forward_pass<false, false, true>(ch, em, rv))
-                                  : (ch.rag_rows > 0 ? forward_pass<true, false>(ch, em, rv) : forward_pass<false, false>(ch, em, rv));
+                                  : (ch.rag_rows > 0 ? forward_pass<true, false, false, false, kYsm>(ch, em, rv) : forward_pass<false, false, false, false, kYsm>(ch, em, rv));
                 R chk = fo.pf.v[0];
 #pragma unroll
                 for (int s = 1; s < K; ++s) chk += fo.pf.v[s];
@@ -1149,16 +1199,16 @@ struct GibbsWarp {
                         if (a.all_signal) {                          // every time step a signal: no observation statistics (warp-uniform)
                             bo = stream_y ? (ch.rag_rows > 0 ? backward_pass<true, false, true, true>(ch, pv, key, sweep, a.flags, save)
                                                              : backward_pass<false, false, true, true>(ch, pv, key, sweep, a.flags, save))
-                                          : (ch.rag_rows > 0 ? backward_pass<true, false, false, true>(ch, pv, key, sweep, a.flags, save)
-                                                             : backward_pass<false, false, false, true>(ch, pv, key, sweep, a.flags, save));
+                                          : (ch.rag_rows > 0 ? backward_pass<true, false, false, true, kYsm>(ch, pv, key, sweep, a.flags, save)
+                                                             : backward_pass<false, false, false, true, kYsm>(ch, pv, key, sweep, a.flags, save));
                             done_b = true;
                         }
                     }
                     if (!done_b)
                     bo = stream_y ? (ch.rag_rows > 0 ? backward_pass<true, false, true>(ch, pv, key, sweep, a.flags, save)
                                                : backward_pass<false, false, true>(ch, pv, key, sweep, a.flags, save))
-                                  : (ch.rag_rows > 0 ? backward_pass<true, false>(ch, pv, key, sweep, a.flags, save)
-                                               : backward_pass<false, false>(ch, pv, key, sweep, a.flags, save));
+                                  : (ch.rag_rows > 0 ? backward_pass<true, false, false, false, kYsm>(ch, pv, key, sweep, a.flags, save)
+                                               : backward_pass<false, false, false, false, kYsm>(ch, pv, key, sweep, a.flags, save));
                     // quirk Q5 fired somewhere: redo the pass exactly (counter-based RNG: identical draws otherwise)
                     // (warp-uniform: the pass stages rows through the warp's cp.async ring and synchronises the warp, so every
                     //  lane must take part; lanes that had no Q5 case get identical results from the gated pass)
@@ -1245,6 +1295,12 @@ __global__ void __launch_bounds__(kGibbsThreads, gibbs_min_blocks<R, K, SIG>()) 
     typename W::Entry* tab = reinterpret_cast<typename W::Entry*>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * (kGibbsThreads / 32) + (threadIdx.x >> 5);
+    if (sizeof(R) == 8 && a.y_sm_elems > 0) {                        // ONE short series (fp64): every block keeps a copy (see YRef)
+        R* ysm = reinterpret_cast<R*>(smem_raw + gibbs_smem_bytes<R, K, WIDE>((a.flags & (8u | 64u)) != 0u, a.n_h));
+        const R* ysrc = reinterpret_cast<const R*>(a.y);
+        for (int i = threadIdx.x; i < a.y_sm_elems; i += kGibbsThreads) ysm[i] = __ldg(ysrc + i);
+        __syncthreads();
+    }
     if (g >= a.n_tasks) return;
     W::run(a, a.task0 + g * a.task_stride, lane, tab);
 }

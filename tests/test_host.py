@@ -443,3 +443,17 @@ def test_bench_reference_arm_prints_one_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_committed_headline_profile_matches_kernel_sources():
+    """bench.py's issue roofline takes warp-instructions per warp-step and DRAM bytes per state-step from the ncu capture in
+    profiles/r2_headline_profile.json, and uses them only when the capture was taken from the kernel sources it runs
+    (hot_source_hash = sha256 of gibbs_kernel.cuh, hmm_device.cuh, rng.cuh and the compiler flags).  A kernel edit without a new
+    capture (scripts/profile_headline.sh on the GPU box) must not go unnoticed: the committed capture has to match the sources."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "hmc.jl_b200"))
+    import build as hb
+    prof = json.load(open(os.path.join(ROOT, "profiles", "r2_headline_profile.json")))
+    assert prof["hot_source_hash"] == hb.hot_source_hash(), "kernel sources changed since the committed ncu capture: run scripts/profile_headline.sh"
+    assert 60 < prof["warp_inst_per_warp_step"] < 130 and 10 < prof["dram_bytes_per_state_step"] < 40
