@@ -128,6 +128,10 @@ template <typename T> struct YRef<T, true> {
     __device__ __forceinline__ const void* gptr() const { return nullptr; }
 };
 // observations of one series kept in shared memory by the thread-per-chain kernel (GibbsArgs::y_sm_elems): at most this many bytes
+#ifndef HMC_YSM_F32
+#define HMC_YSM_F32 0          // 1: fp32 also reads the one shared series from the shared-memory copy (A/B knob)
+#endif
+template <typename R> __host__ __device__ constexpr bool y_in_smem() { return sizeof(R) == 8 || HMC_YSM_F32; }
 constexpr int kYSmemMaxBytes = 8 * 1024;    // (1024 fp64 observations; tables + rings + forecasts are ~61 KB per block at 3 blocks per SM)
 // Batches of distinct series (yld > 1) stream y from HBM once per pass: the rows are pulled into L1 kYAhead steps ahead
 // of their use so the DRAM latency does not sit in front of every group of 4 steps.  (Windows of ONE series keep y in L1.)
@@ -313,17 +317,16 @@ struct GibbsWarp {
     using Entry = GibbsEntry<R, K, WIDE>;
 
     // per-sweep constants of one chain
-    // (fp64 only: row 0 of the lane's frame in the shared-memory copy of the series, byte address.  The fp32 struct must NOT grow: it
-    //  is passed BY VALUE to the out-of-line passes, and four more bytes push it over the size ptxas passes in registers — the
-    //  kernel's frame went from 424 to 2208 bytes and C2 x 256 lost 3 %)
-    struct NoYsm {};
-    struct WithYsm { unsigned ysm; };
-    struct Chain : std::conditional<SIG, SigChain<R>, NoSig>::type, std::conditional<sizeof(R) == 8, WithYsm, NoYsm>::type {
+    // (the struct is passed BY VALUE to the out-of-line passes and sits exactly at the 128 bytes (fp32, K = 3) ptxas still passes in
+    //  registers: 4 more bytes pushed the kernel's frame from 424 to 2208 bytes and cost 3 % on C2 x 256.  `ysm` therefore lives in the
+    //  4-byte alignment hole in front of `yld` — K*K + K + 5 words precede it, always an odd number)
+    struct Chain : std::conditional<SIG, SigChain<R>, NoSig>::type {
         R A[K][K];
         R c;                      // shift of the sufficient statistics
         int rank[K];              // position of each chain label in increasing-mu order
         int T, Tw, off;           // window length, warp length, right-alignment offset (row j <-> t = j - off)
         int rag_rows;             // rows [0, rag_rows) of the warp's frame lie before the window of some lane (shorter window or padding lane): steps there are guarded per lane; 0 = all windows equal
+        unsigned ysm;             // row 0 of the lane's frame in the shared-memory copy of the series (byte address; y_sm_elems > 0)
         long long yld;
         const R* y0;              // row j -> y0[j*yld]
         R* pi0;                   // row j, state k -> pi0[((j + pad) >> 2)*4*K*32 + k*128 + ((j + pad) & 3)]  (lane*4 folded in)
@@ -1005,7 +1008,8 @@ struct GibbsWarp {
         ch.y0 = reinterpret_cast<const R*>(a.y) + a.ybase[slot] - (long long)ch.off * ch.yld;
         // (the copy of the series sits behind everything else in the block's shared memory; rows in front of a ragged lane's window
         //  are never read, so the address may point in front of the copy, like y0)
-        if constexpr (sizeof(R) == 8)
+        ch.ysm = 0u;
+        if constexpr (y_in_smem<R>())
             ch.ysm = (unsigned)__cvta_generic_to_shared(smem_base()) + (unsigned)gibbs_smem_bytes<R, K, WIDE>(accum, a.n_h)
                      + (unsigned)(((int)a.ybase[slot] - ch.off) * (int)sizeof(R));
         ch.c = reinterpret_cast<const R*>(a.cshift)[slot];
@@ -1022,7 +1026,7 @@ struct GibbsWarp {
         // shared-memory copy (y_sm_elems > 0); a single series too long for that also takes the streaming passes (stride 1)
         // (fp64 only: measured on C2 x 256, same box — fp64 7.19 -> 7.60e10 with the copy, fp32 2.19 -> 2.13e11: there the extra LDS in
         //  the dependent chain costs more than the 6 instructions per 4 steps it saves, so fp32 keeps reading y through L1)
-        constexpr bool kYsm = sizeof(R) == 8;
+        constexpr bool kYsm = y_in_smem<R>();
         const bool stream_y = a.yld != 1 || (kYsm && a.y_sm_elems <= 0);
         // padding lanes (T = 0) only exist in the last warp, which therefore counts as ragged
         ch.rag_rows = (int)__reduce_max_sync(0xffffffffu, (unsigned)ch.off);
@@ -1295,7 +1299,7 @@ __global__ void __launch_bounds__(kGibbsThreads, gibbs_min_blocks<R, K, SIG>()) 
     typename W::Entry* tab = reinterpret_cast<typename W::Entry*>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * (kGibbsThreads / 32) + (threadIdx.x >> 5);
-    if (sizeof(R) == 8 && a.y_sm_elems > 0) {                        // ONE short series (fp64): every block keeps a copy (see YRef)
+    if (y_in_smem<R>() && a.y_sm_elems > 0) {                        // ONE short series (fp64): every block keeps a copy (see YRef)
         R* ysm = reinterpret_cast<R*>(smem_raw + gibbs_smem_bytes<R, K, WIDE>((a.flags & (8u | 64u)) != 0u, a.n_h));
         const R* ysrc = reinterpret_cast<const R*>(a.y);
         for (int i = threadIdx.x; i < a.y_sm_elems; i += kGibbsThreads) ysm[i] = __ldg(ysrc + i);

@@ -1748,7 +1748,7 @@ static int plan_build(hmcgpu_plan* pl, const hmcgpu_problem* p, bool want_defer)
     a.sigw = pl->sigw.p; a.sbase = pl->sbase.as<long long>(); a.sld = sld; a.cntM = pl->cntM.as<int>(); a.Sm = pl->Sm.p; a.Qm = pl->Qm.p; a.totSm = pl->totSm.p; a.totQm = pl->totQm.p;
     a.totM = pl->totM.as<int>(); a.kappa = p->kappa; a.pi_back = p->pi_row_back;
     // one short series shared by every window (the rolling job), fp64: the thread-per-chain kernel keeps a copy in shared memory
-    a.y_sm_elems = (sizeof(R) == 8 && nser == 1 && K <= 4 && !pl->wide && !pl->scan && !pl->seg && (size_t)p->y_len * sizeof(R) <= (size_t)kYSmemMaxBytes &&
+    a.y_sm_elems = (y_in_smem<R>() && nser == 1 && K <= 4 && !pl->wide && !pl->scan && !pl->seg && (size_t)p->y_len * sizeof(R) <= (size_t)kYSmemMaxBytes &&
                     !(getenv("HMCGPU_Y_SMEM") && atoi(getenv("HMCGPU_Y_SMEM")) == 0)) ? (int)p->y_len : 0;
     a.all_signal = 0;
     if (p->is_signal) {
