@@ -531,7 +531,11 @@ def main():
             yc4 = wide_series(65536, 2000)
             # e2e: the 1 GB of series in PAGE-LOCKED host memory (the bench contract's host side; the library then copies it with
             # one DMA), e2e_pageable: the same from an ordinary numpy array (the library stages it through its own pinned buffers)
-            yc4_pinned = torch.from_numpy(yc4).pin_memory().numpy()
+            try:
+                yc4_pinned = torch.from_numpy(yc4).pin_memory().numpy()
+            except Exception as exc:                   # (a host that refuses to page-lock 1 GB: both records then come from pageable memory)
+                print(f"[bench] could not page-lock the C4 series ({exc}); e2e = e2e_pageable", file=sys.stderr, flush=True)
+                yc4_pinned = yc4
             c4 = {}
             for prec in (32, 64):
                 mk = lambda ysrc: H.ProblemSpec(ysrc, np.ones(65536, dtype=np.int32), np.full(65536, 2000, dtype=np.int32), K=3, n_chains=1,
